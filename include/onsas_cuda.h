@@ -1,0 +1,192 @@
+/*
+ * onsas_cuda.h -- C ABI of libonsas_cuda, the B200-native replacement of ONSAS.jl's
+ * Newton-Raphson hot path (per-element f_int / K_t / stress evaluation, global assembly,
+ * the linear solve inside each Newton iteration).
+ *
+ * The reference (ONSAS.jl v0.4.6, pure Julia) has no FFI on this path; it extends by multiple
+ * dispatch.  The entry points below are what a `ccall` shim placed at the reference's own seams
+ * would bind (INTEGRATION.md shows the Julia side).  file:line citations are relative to the
+ * reference's src/ directory.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all floating point data is FP64, all host pointers;
+ *   - every function returns an int32 status (ONSAS_OK = 0); onsas_last_error() gives the text;
+ *   - node ids, element ids and dofs are 0-based (the Julia glue subtracts 1 once at upload);
+ *   - global dof of component c of node i is dim*i + c  (Meshes/Meshes.jl:85-98 set_dofs!);
+ *   - element dofs are node-major (Entities/Entities.jl:156-171 local_dofs);
+ *   - 3x3 tensors and K_e are column-major = Julia `Matrix` memory order;
+ *   - "stress" is P = F*S and "strain" is C = F'F for hyperelastic tetrahedra
+ *     (Entities/Tetrahedrons.jl:218-221), Cauchy stress / small strain for
+ *     IsotropicLinearElastic (:265), [1,1]-only for trusses (Entities/Trusses.jl:148-152);
+ *   - the caller owns every host buffer; the library copies and never keeps a host pointer;
+ *   - a context is used by one host thread at a time; different contexts are independent;
+ *   - there is NO CPU fallback: without a CUDA device onsas_create fails with ONSAS_ERR_CUDA.
+ */
+#ifndef ONSAS_CUDA_H
+#define ONSAS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct onsas_ctx onsas_ctx;
+
+/* status codes */
+#define ONSAS_OK 0
+#define ONSAS_ERR_INVALID_ARG 1
+#define ONSAS_ERR_NEGATIVE_VOLUME 2 /* -> ArgumentError("Element with negative volume, check connectivity.") Tetrahedrons.jl:136 */
+#define ONSAS_ERR_CUDA 3
+#define ONSAS_ERR_NOT_READY 4 /* mesh not finalized / state missing */
+#define ONSAS_ERR_UNSUPPORTED 5
+#define ONSAS_ERR_COMM 6
+#define ONSAS_ERR_ALLOC 7
+
+/* material kinds: parameters (p0, p1) */
+#define ONSAS_MAT_SVK 0        /* (lambda, G)   Materials/SVKMaterial.jl:25-54 */
+#define ONSAS_MAT_NEOHOOKEAN 1 /* (K, G)        Materials/NeoHookeanMaterial.jl:25-56 */
+#define ONSAS_MAT_ISOLINEAR 2  /* (E, nu)       Materials/IsotropicLinearElasticMaterial.jl:22-35 */
+
+/* truss strain models (Entities/Trusses.jl:26-45) */
+#define ONSAS_STRAIN_ROTATED_ENGINEERING 0
+#define ONSAS_STRAIN_GREEN 1
+
+/* element families */
+#define ONSAS_FAMILY_TET 0
+#define ONSAS_FAMILY_TRUSS 1
+
+/* preconditioners for the CG solve */
+#define ONSAS_PRECOND_NONE 0   /* IterativeSolversJL_CG default of the reference, StructuralSolvers.jl:29 */
+#define ONSAS_PRECOND_JACOBI 1 /* the north-star solver */
+
+/* tuning keys for onsas_set_option */
+#define ONSAS_OPT_CG_MODE 1      /* 0 = one persistent cooperative kernel (default, 1 GPU), 1 = one launch per phase */
+#define ONSAS_OPT_ASM_MINBLOCKS 2 /* 1, 2 or 3 resident CTAs per SM the assembly kernel is compiled for (default 2) */
+#define ONSAS_OPT_CG_CHECK_EVERY 3 /* multi-launch CG: iterations enqueued between host convergence checks (default 16) */
+#define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: CTAs per SM (0 = occupancy maximum) */
+
+/* ---------------------------------------------------------------- life cycle */
+
+/* Creates a context on CUDA device `device` (replaces nothing in the reference: the device
+ * state is the analogue of FullStaticState, StructuralAnalyses/StaticStates.jl:33-102). */
+int32_t onsas_create(int32_t device, onsas_ctx** ctx);
+int32_t onsas_destroy(onsas_ctx* ctx);
+const char* onsas_last_error(onsas_ctx* ctx); /* ctx may be NULL: last error of onsas_create */
+int32_t onsas_version(void);
+/* Run all work on the given cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
+int32_t onsas_set_stream(onsas_ctx* ctx, void* cuda_stream);
+int32_t onsas_set_option(onsas_ctx* ctx, int32_t key, int64_t value);
+
+/* ---------------------------------------------------------------- mesh upload (once per Structure) */
+
+/* xyz: dim x n_nodes column-major (node-interleaved).  Entities/Nodes.jl:74-84, Meshes/Meshes.jl:158-184.
+ * Multi-GPU: the first n_owned nodes are the block rows this rank owns, the rest are halo nodes
+ * (columns only); single GPU: n_owned = n_nodes. */
+int32_t onsas_set_nodes(onsas_ctx* ctx, int64_t n_nodes, int64_t n_owned, int32_t dim, const double* xyz);
+/* kind[n], params 2 x n column-major.  StructuralModel/StructuralMaterials.jl:25-47. */
+int32_t onsas_set_materials(onsas_ctx* ctx, int32_t n, const int32_t* kind, const double* params);
+/* conn: 4 x n column-major node ids; mat_id[n] or NULL (= material 0).  Entities/Tetrahedrons.jl:24-36. */
+int32_t onsas_set_tets(onsas_ctx* ctx, int64_t n, const int32_t* conn, const int32_t* mat_id);
+/* conn: 2 x n; area[n] = area(cross_section(e)).  Entities/Trusses.jl:54-72. */
+int32_t onsas_set_trusses(onsas_ctx* ctx, int64_t n, const int32_t* conn, const int32_t* mat_id, const double* area,
+                          int32_t strain_model);
+/* free dofs of the owned nodes (Structures.jl:129-142 free_dofs), any order, local numbering.
+ * n_free_global = number of free dofs of the whole structure (= n_free on one GPU); it is the CG
+ * default maxiter (StructuralSolvers.jl:229-234). */
+int32_t onsas_set_free_dofs(onsas_ctx* ctx, int64_t n_free, const int64_t* free_dofs, int64_t n_free_global);
+/* Builds the sparsity pattern, the row-owner pair lists and contribution lists, uploads everything,
+ * checks element volumes (Tetrahedrons.jl:134-138).  Replaces Assembler construction and the
+ * first end_assemble! (Assemblers.jl:28-40, 84-88; StaticStates.jl:79-102). */
+int32_t onsas_finalize_mesh(onsas_ctx* ctx);
+
+/* ---------------------------------------------------------------- state vectors (n_local_dofs = dim*n_nodes) */
+
+int32_t onsas_set_U(onsas_ctx* ctx, const double* U);       /* displacements(state), StructuralAnalyses.jl:74 */
+int32_t onsas_get_U(onsas_ctx* ctx, double* U);
+int32_t onsas_set_Fext(onsas_ctx* ctx, const double* Fext); /* external_forces(state), :88; result of apply! :228-241 */
+int32_t onsas_get_Fint(onsas_ctx* ctx, double* Fint);       /* internal_forces(state), :85; reactions = Fint at fixed dofs */
+int32_t onsas_get_dU(onsas_ctx* ctx, double* dU);           /* Delta_displacements(state) scattered to a full dof vector */
+
+/* ---------------------------------------------------------------- hot path */
+
+/* assemble!(s, sa): reset, evaluate every element at the current U, assemble F_int, K, stress, strain.
+ * StructuralAnalyses/StaticAnalyses.jl:99-132.  Multi-GPU: refreshes the halo part of U first. */
+int32_t onsas_assemble(onsas_ctx* ctx);
+
+/* internal_forces(mat, e, u_e[, cache]) for elements [first, first+count) of one family, un-assembled:
+ * f (ndof_e per element), K (ndof_e^2, column-major), sig, eps (9 each, column-major).
+ * Entities/Entities.jl:174-218; Tetrahedrons.jl:186-266; Trusses.jl:126-184. */
+int32_t onsas_eval_elements(onsas_ctx* ctx, int32_t family, int64_t first, int64_t count, double* f, double* K,
+                            double* sig, double* eps);
+
+typedef struct onsas_step_info {
+    double norm_dU;   /* ||dU||                    NonLinearStaticAnalyses.jl:138 */
+    double norm_U;    /* ||U|| BEFORE the update   :139 */
+    double norm_r;    /* ||r|| at the START of the iteration :140 */
+    double norm_Fext; /* ||F_ext|| (full vector)   :141 */
+    int64_t cg_iters;
+    double cg_residual; /* final ||r_cg|| */
+    double cg_tol;      /* max(reltol*||r0||, abstol) */
+    double ms_assemble; /* device time of the assembly of this call (CUDA events) */
+    double ms_solve;    /* device time of residual + PCG + update */
+} onsas_step_info;
+
+/* One Newton iteration = assemble! + step! (NonLinearStaticAnalyses.jl:92-95, 107-148):
+ * assemble at U, r = (F_ext - F_int)[free], solve K[free,free] dU = r by (P)CG with
+ * tolerance max(cg_reltol*||r||, cg_abstol) and at most cg_maxiter iterations (<= 0: n_free, the
+ * reference default StructuralSolvers.jl:229-234), U[free] += dU, norms. */
+int32_t onsas_newton_step(onsas_ctx* ctx, int32_t precond, double cg_reltol, double cg_abstol, int64_t cg_maxiter,
+                          onsas_step_info* info);
+
+/* step! without the assembly: residual, solve, update, norms on the K / F_int already assembled.
+ * update_U = 0 leaves U untouched (dU still available through onsas_get_dU). */
+int32_t onsas_step(onsas_ctx* ctx, int32_t precond, double cg_reltol, double cg_abstol, int64_t cg_maxiter,
+                   int32_t update_U, onsas_step_info* info);
+
+/* The linear solve alone: K[free,free] x = b[free] on the assembled K, zero initial guess
+ * (solve(LinearProblem(A,b), IterativeSolversJL_CG(); abstol, reltol, maxiter), NonLinearStaticAnalyses.jl:129-134).
+ * b, x: full dof vectors (entries at fixed dofs ignored / zero). */
+int32_t onsas_pcg(onsas_ctx* ctx, const double* b, double* x, int32_t precond, double reltol, double abstol,
+                  int64_t maxiter, int64_t* iters, double* residual);
+
+/* y = K[free,free] * x with full-length vectors (zeros at fixed dofs): one SpMV launch, exposed for tests/bench. */
+int32_t onsas_spmv(onsas_ctx* ctx, const double* x, double* y);
+
+/* Measurement hooks (asynchronous, device-resident data only): one SpMV launch on whatever the search
+ * direction buffer currently holds; and a stream synchronisation that also reports deferred errors
+ * (negative element volume seen by an asynchronous onsas_assemble). */
+int32_t onsas_spmv_resident(onsas_ctx* ctx);
+int32_t onsas_synchronize(onsas_ctx* ctx);
+
+/* ---------------------------------------------------------------- results */
+
+/* tangent_matrix(state) as scalar CSR with sorted columns: n_rows = dim*n_owned rows over dim*n_nodes columns,
+ * fixed dofs included (StaticStates.jl:84-88). */
+int32_t onsas_get_csr_size(onsas_ctx* ctx, int64_t* n_rows, int64_t* nnz);
+int32_t onsas_get_csr(onsas_ctx* ctx, int64_t* rowptr, int32_t* col, double* val);
+/* stress(state)[e], strain(state)[e] for a whole family: 9 doubles per element each, column-major.
+ * StructuralAnalyses.jl:115-120; StaticAnalyses.jl:157-174 (store!). */
+int32_t onsas_get_stress_strain(onsas_ctx* ctx, int32_t family, double* sig, double* eps);
+
+/* Sizes of the device-side tables, for roofline accounting: out[0]=n_slices, [1]=padded block slots,
+ * [2]=true nonzero blocks, [3]=tet pairs, [4]=truss pairs, [5]=max pairs per slice, [6]=bytes of K values,
+ * [7]=persistent CG grid size. */
+int32_t onsas_get_table_stats(onsas_ctx* ctx, int64_t out[8]);
+
+/* ---------------------------------------------------------------- multi-GPU (one process per GPU) */
+
+/* NCCL bootstrap: rank 0 calls onsas_comm_unique_id and the host broadcasts the 128 bytes
+ * (torch.distributed / MPI); every rank then calls onsas_comm_init. */
+int32_t onsas_comm_unique_id(void* id128);
+int32_t onsas_comm_init(onsas_ctx* ctx, int32_t n_ranks, int32_t rank, const void* id128);
+/* Halo plan: for neighbour k (rank nbr_rank[k]) send the values of owned nodes
+ * send_nodes[send_ptr[k] .. send_ptr[k+1]) and receive into the halo nodes
+ * [n_owned + recv_ptr[k], n_owned + recv_ptr[k+1]) (halo nodes are grouped by owner). */
+int32_t onsas_set_halo(onsas_ctx* ctx, int32_t n_nbr, const int32_t* nbr_rank, const int64_t* send_ptr,
+                       const int32_t* send_nodes, const int64_t* recv_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONSAS_CUDA_H */

@@ -1,0 +1,646 @@
+// kernels.cuh -- sm_100a kernels of the Newton-Raphson hot path.
+//
+//   k_assemble<FAMILY,KIND,DIM,ACCUM>  fused element evaluation + deterministic row-owner assembly
+//                                      (replaces StaticAnalyses.jl:99-132 + Assemblers.jl:46-88)
+//   k_eval_tets / k_eval_trusses       un-assembled f_e, K_e, sigma, eps (Entities.jl:174-218 contract)
+//   cg_persistent<BS>                  whole Jacobi-PCG solve + residual + update + norms in ONE
+//                                      cooperative launch (NonLinearStaticAnalyses.jl:107-148 and the
+//                                      IterativeSolvers.jl cg! it calls)
+//   k_cg_* / k_spmv_dot<BS>            the same phases as separate launches (multi-GPU path, where the
+//                                      halo exchange and all-reduce sit between them)
+//
+// All FP64, no tensor cores: nothing here is a dense contraction.  HBM-bound kernels are laid out
+// for full-sector coalesced access (BSELL slices of 8 rows = 64-byte segments, 128-byte element
+// output records); every reduction has a fixed order, so results are bitwise run-to-run reproducible.
+#pragma once
+#include <cooperative_groups.h>
+#include <cstdint>
+
+#include "element_math.cuh"
+#include "tables.hpp"
+
+namespace onsas {
+namespace cg = cooperative_groups;
+
+template <int V>
+struct IC {
+    static constexpr int value = V;
+};
+
+constexpr int C = SLICE_ROWS;
+constexpr int TET_REC = 39;  // 4 blocks * 9 + 3 force entries per (row, element) pair; odd -> conflict-free smem
+
+// ------------------------------------------------------------------------------------------------
+// assembly
+// ------------------------------------------------------------------------------------------------
+struct AsmArgs {
+    int64_t n_rows;
+    const double* X;  // dim per node
+    const double* U;  // dim per node
+    const int32_t* conn;
+    const int32_t* mat_id;  // may be null (all elements use material 0)
+    const int32_t* mat_kind;
+    const double* mat_params;  // 2 per material
+    const double* area;        // trusses
+    int strain_model;          // trusses
+    const int64_t* pair_ptr;
+    const int32_t* pair_code;
+    const uint32_t* cptr;
+    const uint16_t* ccode;
+    const int64_t* slice_ptr;
+    double* val;
+    double* F_int;
+    double* elem_out;  // tets: 16 doubles per element; trusses: 2 per element
+    int* err_flag;     // set to 1 when an element has non-positive volume
+};
+
+template <int KIND>
+__device__ __forceinline__ void tet_pair(const AsmArgs& A, int32_t code, double* rec) {
+    const int64_t e = code >> 2;
+    const int a = code & 3;
+    const int4 cn = __ldg(reinterpret_cast<const int4*>(A.conn) + e);
+    const int nd[4] = {cn.x, cn.y, cn.z, cn.w};
+    double X[4][3], U[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double* xp = A.X + 3 * (int64_t)nd[k];
+        const double* up = A.U + 3 * (int64_t)nd[k];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            X[k][c] = __ldg(xp + c);
+            U[k][c] = __ldg(up + c);
+        }
+    }
+    const int m = A.mat_id ? __ldg(A.mat_id + e) : 0;
+    const double p0 = __ldg(A.mat_params + 2 * m), p1 = __ldg(A.mat_params + 2 * m + 1);
+    int kind = KIND;
+    if (KIND == MAT_MIXED) kind = __ldg(A.mat_kind + m);
+
+    double vol;
+    auto run = [&](auto tag) {
+        constexpr int K = decltype(tag)::value;
+        TetCommon c;
+        tet_common<K>(X, U, p0, p1, c);
+        vol = c.vol;
+        if (a == 0) {  // the owner of the element's first node also writes its stress / strain record
+            double out[16];
+            tet_stress_out<K>(c, p0, p1, out);
+            double2* o = reinterpret_cast<double2*>(A.elem_out + 16 * e);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = make_double2(out[2 * k], out[2 * k + 1]);
+        }
+        tet_row<K>(c, U, a, rec, rec + 36);
+    };
+    if (kind == MAT_SVK)
+        run(IC<MAT_SVK>());
+    else if (kind == MAT_NEOHOOKEAN)
+        run(IC<MAT_NEOHOOKEAN>());
+    else
+        run(IC<MAT_ISOLINEAR>());
+    if (!(vol > 0.0)) *A.err_flag = 1;  // Tetrahedrons.jl:134-138
+}
+
+template <int DIM>
+__device__ __forceinline__ void truss_pair(const AsmArgs& A, int32_t code, double* rec) {
+    const int64_t e = code >> 1;
+    const int a = code & 1;
+    const int n0 = __ldg(A.conn + 2 * e), n1 = __ldg(A.conn + 2 * e + 1);
+    double X[2][3], U[2][3];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+        X[0][c] = __ldg(A.X + DIM * (int64_t)n0 + c);
+        X[1][c] = __ldg(A.X + DIM * (int64_t)n1 + c);
+        U[0][c] = __ldg(A.U + DIM * (int64_t)n0 + c);
+        U[1][c] = __ldg(A.U + DIM * (int64_t)n1 + c);
+    }
+    const int m = A.mat_id ? __ldg(A.mat_id + e) : 0;
+    const double Emod = truss_modulus(__ldg(A.mat_kind + m), __ldg(A.mat_params + 2 * m), __ldg(A.mat_params + 2 * m + 1));
+    double blk[2][9], f[3], se[2];
+    truss_row<DIM>(A.strain_model, X, U, Emod, __ldg(A.area + e), a, blk, f, se);
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int k = 0; k < DIM * DIM; ++k) rec[b * DIM * DIM + k] = blk[b][k];
+#pragma unroll
+    for (int r = 0; r < DIM; ++r) rec[2 * DIM * DIM + r] = f[r];
+    if (a == 0) {
+        A.elem_out[2 * e] = se[0];
+        A.elem_out[2 * e + 1] = se[1];
+    }
+}
+
+constexpr __host__ __device__ int truss_rec(int dim) { return (2 * dim * dim + dim) | 1; }
+
+// One CTA per BSELL slice (8 block rows).  Phase A: one thread per (row, element) pair evaluates
+// its block-row into shared memory.  Phase B: one thread per matrix entry of the slice sums its
+// contributions in ascending element order and writes K exactly once, fully coalesced; the last
+// 8*DIM items do the same for F_int.  ACCUM adds onto what a previous family already wrote.
+template <int FAMILY, int KIND, int DIM, bool ACCUM, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_assemble(AsmArgs A) {
+    extern __shared__ double stage[];
+    constexpr int BB = DIM * DIM;
+    constexpr int REC = FAMILY == 0 ? TET_REC : truss_rec(DIM);
+    constexpr int FOFF = FAMILY == 0 ? 36 : 2 * BB;
+    constexpr int SHIFT = 2;  // ccode = local_pair*4 + b for both families
+    const int64_t sl = blockIdx.x;
+    const int64_t r0 = sl * C;
+    const int64_t r1 = (r0 + C < A.n_rows) ? r0 + C : A.n_rows;
+    const int64_t p0 = A.pair_ptr[r0];
+    const int np = (int)(A.pair_ptr[r1] - p0);
+
+    for (int t = threadIdx.x; t < np; t += blockDim.x) {
+        const int32_t code = __ldg(A.pair_code + p0 + t);
+        if (FAMILY == 0)
+            tet_pair<KIND>(A, code, stage + (size_t)t * REC);
+        else
+            truss_pair<DIM>(A, code, stage + (size_t)t * REC);
+    }
+    __syncthreads();
+
+    const int64_t base = A.slice_ptr[sl];
+    const int width = (int)(A.slice_ptr[sl + 1] - base);
+    const int nK = width * BB * C;
+    const int nF = C * DIM;
+    for (int w = threadIdx.x; w < nK + nF; w += blockDim.x) {
+        if (w < nK) {
+            const int lane = w % C;
+            const int k = (w / C) % BB;
+            const int s = w / (C * BB);
+            const int64_t gs = (base + s) * C + lane;
+            const uint32_t q0 = __ldg(A.cptr + gs), q1 = __ldg(A.cptr + gs + 1);
+            double acc = 0.0;
+            for (uint32_t q = q0; q < q1; ++q) {
+                const int cc = __ldg(A.ccode + q);
+                acc += stage[(cc >> SHIFT) * REC + (cc & 3) * BB + k];
+            }
+            const int64_t idx = base * BB * C + w;
+            if (ACCUM) acc += A.val[idx];
+            A.val[idx] = acc;
+        } else {
+            const int j = w - nK;
+            const int lane = j / DIM, r = j % DIM;
+            const int64_t row = r0 + lane;
+            if (row < r1) {
+                const int t0 = (int)(A.pair_ptr[row] - p0), t1 = (int)(A.pair_ptr[row + 1] - p0);
+                double acc = 0.0;
+                for (int t = t0; t < t1; ++t) acc += stage[t * REC + FOFF + r];
+                if (ACCUM) acc += A.F_int[row * DIM + r];
+                A.F_int[row * DIM + r] = acc;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// un-assembled element evaluation (parity API)
+// ------------------------------------------------------------------------------------------------
+struct EvalArgs {
+    int64_t first, count;
+    int dim;
+    const double* X;
+    const double* U;
+    const int32_t* conn;
+    const int32_t* mat_id;
+    const int32_t* mat_kind;
+    const double* mat_params;
+    const double* area;
+    int strain_model;
+    double* f;    // ndof_e per element
+    double* K;    // ndof_e^2 per element, column-major
+    double* sig;  // 9 per element, column-major
+    double* eps;  // 9 per element
+    int* err_flag;
+};
+
+__global__ void k_eval_tets(EvalArgs A) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= A.count) return;
+    const int64_t e = A.first + i;
+    double X[4][3], U[4][3];
+    for (int k = 0; k < 4; ++k) {
+        const int64_t nd = A.conn[4 * e + k];
+        for (int c = 0; c < 3; ++c) {
+            X[k][c] = A.X[3 * nd + c];
+            U[k][c] = A.U[3 * nd + c];
+        }
+    }
+    const int m = A.mat_id ? A.mat_id[e] : 0;
+    const double p0 = A.mat_params[2 * m], p1 = A.mat_params[2 * m + 1];
+    const int kind = A.mat_kind[m];
+    double* K = A.K + 144 * i;
+    double* f = A.f + 12 * i;
+    double out[16];
+    double vol = 0;
+    auto run = [&](auto tag) {
+        constexpr int KD = decltype(tag)::value;
+        TetCommon c;
+        tet_common<KD>(X, U, p0, p1, c);
+        vol = c.vol;
+        for (int a = 0; a < 4; ++a) {
+            double blk[36], fa[3];
+            tet_row<KD>(c, U, a, blk, fa);
+            for (int r = 0; r < 3; ++r) {
+                f[3 * a + r] = fa[r];
+                for (int b = 0; b < 4; ++b)
+                    for (int q = 0; q < 3; ++q) K[(3 * a + r) + 12 * (3 * b + q)] = blk[9 * b + 3 * r + q];
+            }
+        }
+        tet_stress_out<KD>(c, p0, p1, out);
+    };
+    if (kind == MAT_SVK)
+        run(IC<MAT_SVK>());
+    else if (kind == MAT_NEOHOOKEAN)
+        run(IC<MAT_NEOHOOKEAN>());
+    else
+        run(IC<MAT_ISOLINEAR>());
+    if (!(vol > 0.0)) *A.err_flag = 1;
+    for (int k = 0; k < 9; ++k) A.sig[9 * i + k] = out[k];
+    const int VI[6] = {0, 1, 2, 1, 0, 0}, VJ[6] = {0, 1, 2, 2, 2, 1};
+    for (int v = 0; v < 6; ++v) {
+        A.eps[9 * i + VI[v] + 3 * VJ[v]] = out[9 + v];
+        A.eps[9 * i + VJ[v] + 3 * VI[v]] = out[9 + v];
+    }
+}
+
+template <int DIM>
+__global__ void k_eval_trusses(EvalArgs A) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= A.count) return;
+    const int64_t e = A.first + i;
+    double X[2][3], U[2][3];
+    for (int k = 0; k < 2; ++k) {
+        const int64_t nd = A.conn[2 * e + k];
+        for (int c = 0; c < DIM; ++c) {
+            X[k][c] = A.X[DIM * nd + c];
+            U[k][c] = A.U[DIM * nd + c];
+        }
+    }
+    const int m = A.mat_id ? A.mat_id[e] : 0;
+    const double Emod = truss_modulus(A.mat_kind[m], A.mat_params[2 * m], A.mat_params[2 * m + 1]);
+    constexpr int N = 2 * DIM;
+    double* K = A.K + N * N * i;
+    double* f = A.f + N * i;
+    double se[2];
+    for (int a = 0; a < 2; ++a) {
+        double blk[2][9], fa[3];
+        truss_row<DIM>(A.strain_model, X, U, Emod, A.area[e], a, blk, fa, se);
+        for (int r = 0; r < DIM; ++r) {
+            f[DIM * a + r] = fa[r];
+            for (int b = 0; b < 2; ++b)
+                for (int q = 0; q < DIM; ++q) K[(DIM * a + r) + N * (DIM * b + q)] = blk[b][DIM * r + q];
+        }
+    }
+    for (int k = 0; k < 9; ++k) {
+        A.sig[9 * i + k] = 0.0;
+        A.eps[9 * i + k] = 0.0;
+    }
+    A.sig[9 * i] = se[0];  // Trusses.jl:148-152: only [1,1] is set
+    A.eps[9 * i] = se[1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Jacobi-PCG
+// ------------------------------------------------------------------------------------------------
+// Scalars of one solve; lives in device memory, copied to pinned host memory at the end.
+struct CgState {
+    double rho, rho_prev, res, tol, pAp;
+    double rr0, ff, uu, dd;  // ||r0||^2, ||F_ext||^2, ||U||^2 (before update), ||dU||^2
+    long long it;
+    int done;
+    int pad;
+};
+
+enum : int { P_RR = 0, P_RZ = 1, P_FF = 2, P_UU = 3, P_PAP = 4, P_DD = 5, P_COUNT = 6 };
+
+struct CgArgs {
+    int64_t n_rows;   // owned block rows
+    int64_t n;        // owned dofs = n_rows * BS
+    const int64_t* slice_ptr;
+    const int32_t* col;
+    const double* val;
+    const int32_t* diag_slot;  // per row: position of the diagonal block in the row
+    const uint8_t* mask;       // 1 = free dof
+    double* x;                 // solution (dU), owned dofs
+    double* r;
+    double* p;   // search direction, n_local dofs (owned + halo)
+    double* Ap;
+    double* dinv;
+    const double* Fext;
+    const double* Fint;
+    const double* rhs;  // if non-null the right-hand side is mask*rhs instead of mask*(Fext - Fint)
+    double* U;          // updated in the epilogue when update_U != 0
+    int update_U;
+    int precond;        // 0 = none (reference default), 1 = Jacobi
+    double reltol, abstol;
+    long long maxiter;
+    double* partials;   // [P_COUNT][part_stride]
+    int part_stride;
+    CgState* st;
+};
+
+// fixed-order block reduction; result valid in every thread
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NT / 32; ++i) s += sh[i];
+    return s;
+}
+
+// every CTA sums the per-CTA partials in the same order -> identical value everywhere
+template <int NT>
+__device__ __forceinline__ double sum_partials(const double* part, int nblk, double* sh) {
+    double v = 0.0;
+    for (int j = threadIdx.x; j < nblk; j += NT) v += __ldcg(part + j);
+    return block_sum<NT>(v, sh);
+}
+
+template <int BS>
+__device__ __forceinline__ double diag_entry(const CgArgs& A, int64_t i) {
+    const int64_t row = i / BS;
+    const int c = (int)(i % BS);
+    const int64_t base = A.slice_ptr[row / C];
+    const int s = A.diag_slot[row];
+    return A.val[((base + s) * BS * BS + c * BS + c) * C + (row % C)];
+}
+
+// y = (M K M p)[row]; returns p[row] . y
+template <int BS>
+__device__ __forceinline__ double spmv_row(const CgArgs& A, int64_t row) {
+    const int64_t sl = row / C;
+    const int lane = (int)(row % C);
+    const int64_t base = A.slice_ptr[sl];
+    const int width = (int)(A.slice_ptr[sl + 1] - base);
+    double acc[BS];
+#pragma unroll
+    for (int r = 0; r < BS; ++r) acc[r] = 0.0;
+    const int32_t* cp = A.col + base * C + lane;
+    const double* vp = A.val + base * BS * BS * C + lane;
+#pragma unroll 2
+    for (int s = 0; s < width; ++s) {
+        const int64_t cnode = __ldg(cp + (int64_t)s * C);
+        double xv[BS];
+#pragma unroll
+        for (int q = 0; q < BS; ++q) xv[q] = A.p[cnode * BS + q];
+#pragma unroll
+        for (int r = 0; r < BS; ++r)
+#pragma unroll
+            for (int q = 0; q < BS; ++q) acc[r] += __ldcs(vp + ((int64_t)s * BS * BS + r * BS + q) * C) * xv[q];
+    }
+    double d = 0.0;
+#pragma unroll
+    for (int r = 0; r < BS; ++r) {
+        const int64_t i = row * BS + r;
+        const double y = A.mask[i] ? acc[r] : 0.0;
+        A.Ap[i] = y;
+        d += A.p[i] * y;
+    }
+    return d;
+}
+
+// ---- phase bodies shared by the persistent and the multi-launch drivers (grid-stride)
+template <int BS>
+__device__ __forceinline__ void cg_prologue_body(const CgArgs& A, int64_t gtid, int64_t gsz, double s[4]) {
+    s[0] = s[1] = s[2] = s[3] = 0.0;
+    for (int64_t i = gtid; i < A.n; i += gsz) {
+        const bool m = A.mask[i] != 0;
+        double ri = 0.0;
+        if (m) ri = A.rhs ? A.rhs[i] : (A.Fext[i] - A.Fint[i]);
+        double di = m ? 1.0 : 0.0;
+        if (m && A.precond) di = 1.0 / diag_entry<BS>(A, i);
+        A.r[i] = ri;
+        A.x[i] = 0.0;
+        A.p[i] = 0.0;
+        A.dinv[i] = di;
+        const double fe = A.Fext ? A.Fext[i] : 0.0, u = A.U ? A.U[i] : 0.0;
+        s[P_RR] += ri * ri;
+        s[P_RZ] += ri * ri * di;
+        s[P_FF] += fe * fe;
+        s[P_UU] += u * u;
+    }
+}
+
+__device__ __forceinline__ void cg_update_p_body(const CgArgs& A, int64_t gtid, int64_t gsz, double beta) {
+    for (int64_t i = gtid; i < A.n; i += gsz) A.p[i] = A.r[i] * A.dinv[i] + beta * A.p[i];
+}
+
+__device__ __forceinline__ void cg_update_xr_body(const CgArgs& A, int64_t gtid, int64_t gsz, double alpha, double s[2]) {
+    s[0] = s[1] = 0.0;
+    for (int64_t i = gtid; i < A.n; i += gsz) {
+        A.x[i] += alpha * A.p[i];
+        const double ri = A.r[i] - alpha * A.Ap[i];
+        A.r[i] = ri;
+        s[0] += ri * ri;
+        s[1] += ri * ri * A.dinv[i];
+    }
+}
+
+__device__ __forceinline__ double cg_epilogue_body(const CgArgs& A, int64_t gtid, int64_t gsz) {
+    double dd = 0.0;
+    for (int64_t i = gtid; i < A.n; i += gsz) {
+        const double dx = A.x[i];
+        dd += dx * dx;
+        if (A.update_U) A.U[i] += dx;  // NonLinearStaticAnalyses.jl:144 (x is zero at fixed dofs)
+    }
+    return dd;
+}
+
+constexpr int CG_THREADS = 256;
+
+// The whole linear solve of one Newton iteration in one cooperative launch:
+// residual r = (F_ext - F_int)[free] (StaticStates.jl:113-116), PCG exactly as IterativeSolvers'
+// (P)CGIterable runs it (tolerance = max(reltol*||r0||, abstol), stop when ||r|| <= tol or
+// it >= maxiter), then dU norms and U[free] += dU (NonLinearStaticAnalyses.jl:136-144).
+template <int BS>
+__global__ void __launch_bounds__(CG_THREADS) cg_persistent(CgArgs A) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[CG_THREADS / 32];
+    const int64_t gtid = blockIdx.x * (int64_t)CG_THREADS + threadIdx.x;
+    const int64_t gsz = gridDim.x * (int64_t)CG_THREADS;
+    const int nb = gridDim.x;
+    double* part = A.partials;
+    const int ps = A.part_stride;
+
+    double s4[4];
+    cg_prologue_body<BS>(A, gtid, gsz, s4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double b = block_sum<CG_THREADS>(s4[k], sh);
+        if (threadIdx.x == 0) part[k * ps + blockIdx.x] = b;
+    }
+    grid.sync();
+    const double rr0 = sum_partials<CG_THREADS>(part + P_RR * ps, nb, sh);
+    const double ff = sum_partials<CG_THREADS>(part + P_FF * ps, nb, sh);
+    const double uu = sum_partials<CG_THREADS>(part + P_UU * ps, nb, sh);
+    double rho = sum_partials<CG_THREADS>(part + P_RZ * ps, nb, sh);
+    double res = sqrt(rr0);
+    const double tol = fmax(A.reltol * res, A.abstol);
+    double rho_prev = 1.0;
+    long long it = 0;
+
+    while (!(it >= A.maxiter || res <= tol)) {
+        const double beta = rho / rho_prev;
+        cg_update_p_body(A, gtid, gsz, beta);
+        grid.sync();
+        double d = 0.0;
+        for (int64_t row = gtid; row < A.n_rows; row += gsz) d += spmv_row<BS>(A, row);
+        d = block_sum<CG_THREADS>(d, sh);
+        if (threadIdx.x == 0) part[P_PAP * ps + blockIdx.x] = d;
+        grid.sync();
+        const double pAp = sum_partials<CG_THREADS>(part + P_PAP * ps, nb, sh);
+        const double alpha = rho / pAp;
+        double s2[2];
+        cg_update_xr_body(A, gtid, gsz, alpha, s2);
+        const double b0 = block_sum<CG_THREADS>(s2[0], sh);
+        const double b1 = block_sum<CG_THREADS>(s2[1], sh);
+        if (threadIdx.x == 0) {
+            part[P_RR * ps + blockIdx.x] = b0;
+            part[P_RZ * ps + blockIdx.x] = b1;
+        }
+        grid.sync();
+        const double rr = sum_partials<CG_THREADS>(part + P_RR * ps, nb, sh);
+        rho_prev = rho;
+        rho = sum_partials<CG_THREADS>(part + P_RZ * ps, nb, sh);
+        res = sqrt(rr);
+        ++it;
+    }
+
+    double dd = cg_epilogue_body(A, gtid, gsz);
+    dd = block_sum<CG_THREADS>(dd, sh);
+    if (threadIdx.x == 0) part[P_DD * ps + blockIdx.x] = dd;
+    grid.sync();
+    dd = sum_partials<CG_THREADS>(part + P_DD * ps, nb, sh);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        CgState* st = A.st;
+        st->rho = rho;
+        st->rho_prev = rho_prev;
+        st->res = res;
+        st->tol = tol;
+        st->pAp = 0.0;
+        st->rr0 = rr0;
+        st->ff = ff;
+        st->uu = uu;
+        st->dd = dd;
+        st->it = it;
+        st->done = 1;
+    }
+}
+
+// ---- multi-launch driver kernels (single- or multi-GPU).  Sums that cross GPUs live in
+// red[] (device doubles) so an in-stream ncclAllReduce can sit between a *_reduce kernel and
+// its consumer.  Every kernel is a no-op once st->done is set, so the host may enqueue
+// iterations ahead of the convergence check without changing the result.
+template <int BS>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_prologue(CgArgs A) {
+    __shared__ double sh[CG_THREADS / 32];
+    const int64_t gtid = blockIdx.x * (int64_t)CG_THREADS + threadIdx.x;
+    const int64_t gsz = gridDim.x * (int64_t)CG_THREADS;
+    double s4[4];
+    cg_prologue_body<BS>(A, gtid, gsz, s4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double b = block_sum<CG_THREADS>(s4[k], sh);
+        if (threadIdx.x == 0) A.partials[k * A.part_stride + blockIdx.x] = b;
+    }
+}
+
+// single CTA: red[k] = sum of partial array first+k, k < count (fixed order)
+__global__ void __launch_bounds__(CG_THREADS) k_reduce_partials(const double* partials, int part_stride, int nblk,
+                                                               int first, int count, double* red, const CgState* st,
+                                                               int gate) {
+    __shared__ double sh[CG_THREADS / 32];
+    if (gate && st->done) return;
+    for (int k = 0; k < count; ++k) {
+        const double v = sum_partials<CG_THREADS>(partials + (first + k) * part_stride, nblk, sh);
+        if (threadIdx.x == 0) red[first + k] = v;
+    }
+}
+
+// after the (all-)reduction of the prologue sums
+__global__ void k_cg_init_state(CgArgs A, const double* red) {
+    CgState* st = A.st;
+    st->rr0 = red[P_RR];
+    st->ff = red[P_FF];
+    st->uu = red[P_UU];
+    st->rho = red[P_RZ];
+    st->rho_prev = 1.0;
+    st->res = sqrt(red[P_RR]);
+    st->tol = fmax(A.reltol * st->res, A.abstol);
+    st->it = 0;
+    st->dd = 0.0;
+    st->done = (0 >= A.maxiter || st->res <= st->tol) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_cg_update_p(CgArgs A) {
+    if (A.st->done) return;
+    const double beta = A.st->rho / A.st->rho_prev;
+    cg_update_p_body(A, blockIdx.x * (int64_t)CG_THREADS + threadIdx.x, gridDim.x * (int64_t)CG_THREADS, beta);
+}
+
+template <int BS>
+__global__ void __launch_bounds__(CG_THREADS) k_spmv_dot(CgArgs A, int gate) {
+    __shared__ double sh[CG_THREADS / 32];
+    if (gate && A.st->done) return;
+    const int64_t gtid = blockIdx.x * (int64_t)CG_THREADS + threadIdx.x;
+    const int64_t gsz = gridDim.x * (int64_t)CG_THREADS;
+    double d = 0.0;
+    for (int64_t row = gtid; row < A.n_rows; row += gsz) d += spmv_row<BS>(A, row);
+    d = block_sum<CG_THREADS>(d, sh);
+    if (threadIdx.x == 0) A.partials[P_PAP * A.part_stride + blockIdx.x] = d;
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_cg_update_xr(CgArgs A, const double* red) {
+    __shared__ double sh[CG_THREADS / 32];
+    if (A.st->done) return;
+    const double alpha = A.st->rho / red[P_PAP];
+    double s2[2];
+    cg_update_xr_body(A, blockIdx.x * (int64_t)CG_THREADS + threadIdx.x, gridDim.x * (int64_t)CG_THREADS, alpha, s2);
+    const double b0 = block_sum<CG_THREADS>(s2[0], sh);
+    const double b1 = block_sum<CG_THREADS>(s2[1], sh);
+    if (threadIdx.x == 0) {
+        A.partials[P_RR * A.part_stride + blockIdx.x] = b0;
+        A.partials[P_RZ * A.part_stride + blockIdx.x] = b1;
+    }
+}
+
+// after the (all-)reduction of rr, rz
+__global__ void k_cg_advance(CgArgs A, const double* red) {
+    CgState* st = A.st;
+    if (st->done) return;
+    st->rho_prev = st->rho;
+    st->rho = red[P_RZ];
+    st->res = sqrt(red[P_RR]);
+    st->it += 1;
+    if (st->it >= A.maxiter || st->res <= st->tol) st->done = 1;
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_cg_epilogue(CgArgs A) {
+    __shared__ double sh[CG_THREADS / 32];
+    double dd = cg_epilogue_body(A, blockIdx.x * (int64_t)CG_THREADS + threadIdx.x, gridDim.x * (int64_t)CG_THREADS);
+    dd = block_sum<CG_THREADS>(dd, sh);
+    if (threadIdx.x == 0) A.partials[P_DD * A.part_stride + blockIdx.x] = dd;
+}
+
+__global__ void k_cg_finish(CgArgs A, const double* red) { A.st->dd = red[P_DD]; }
+
+// ---- halo exchange helpers (multi-GPU): pack owned values the neighbours need
+__global__ void k_pack(const double* __restrict__ v, const int32_t* __restrict__ send_nodes, int64_t n_send, int bs,
+                       double* __restrict__ buf, const CgState* st, int gate) {
+    if (gate && st->done) return;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_send * bs) return;
+    buf[i] = v[(int64_t)send_nodes[i / bs] * bs + (i % bs)];
+}
+
+__global__ void k_fill(double* v, int64_t n, double a) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) v[i] = a;
+}
+
+}  // namespace onsas

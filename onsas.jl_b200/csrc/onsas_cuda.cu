@@ -1,0 +1,1022 @@
+// onsas_cuda.cu -- context, host orchestration and the C ABI of libonsas_cuda (include/onsas_cuda.h).
+// There is no CPU execution path in this library: every entry point that computes launches CUDA
+// kernels on the context's device and fails with ONSAS_ERR_CUDA when that is impossible.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/onsas_cuda.h"
+#include "kernels.cuh"
+#include "tables.hpp"
+
+using namespace onsas;
+
+namespace {
+
+struct OnsasError : std::runtime_error {
+    int code;
+    OnsasError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_CHECK(expr)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            throw OnsasError(ONSAS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +   \
+                                                 __FILE__ + ":" + std::to_string(__LINE__) + ")");         \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) {
+            cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+            if (e != cudaSuccess) {
+                p = nullptr;
+                n = 0;
+                throw OnsasError(ONSAS_ERR_ALLOC, std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) +
+                                                      " bytes failed: " + cudaGetErrorString(e));
+            }
+        }
+    }
+    void zero(cudaStream_t s) {
+        if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+    void upload(const T* h, size_t count, cudaStream_t s) {
+        if (count != n) alloc(count);
+        if (count) CUDA_CHECK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void upload(const std::vector<T>& v, cudaStream_t s) { upload(v.data(), v.size(), s); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+// ---- NCCL through dlopen so that single-GPU use has no NCCL dependency
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (h) return true;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) {
+            err = std::string("cannot load libnccl: ") + dlerror();
+            return false;
+        }
+#define LOAD(sym)                                                    \
+    *(void**)(&sym) = dlsym(h, "nccl" #sym);                         \
+    if (!sym) {                                                      \
+        err = "libnccl lacks nccl" #sym;                             \
+        return false;                                                \
+    }
+        LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(Send) LOAD(Recv) LOAD(GroupStart)
+        LOAD(GroupEnd) LOAD(GetErrorString)
+#undef LOAD
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::string g_create_error;
+
+#define NCCL_CHECK(expr)                                                                                    \
+    do {                                                                                                    \
+        ncclResult_t _r = (expr);                                                                           \
+        if (_r != ncclSuccess)                                                                              \
+            throw OnsasError(ONSAS_ERR_COMM, std::string(#expr) + ": " + g_nccl.GetErrorString(_r));        \
+    } while (0)
+
+}  // namespace
+
+struct onsas_ctx {
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+
+    // host copy of the mesh until finalize
+    int dim = 3;
+    int64_t n_nodes = 0, n_owned = 0;
+    std::vector<double> h_xyz;
+    std::vector<int32_t> h_tets, h_tet_mat, h_trusses, h_truss_mat;
+    bool tet_has_mat = false, truss_has_mat = false;
+    std::vector<double> h_area;
+    int strain_model = 0;
+    std::vector<int32_t> h_mat_kind;
+    std::vector<double> h_mat_params;
+    std::vector<uint8_t> h_mask;
+    int64_t n_free = 0, n_free_global = 0;
+    bool have_nodes = false, have_free = false, finalized = false;
+    int64_t n_tets = 0, n_trusses = 0;
+    int tet_kind = MAT_SVK;  // uniform kind or MAT_MIXED
+
+    MeshTables tab;
+
+    // device
+    DevBuf<double> X, U, Fext, Fint, val, x, r, p, Ap, dinv, rhs, partials, red, tet_out, truss_out, area, mat_params;
+    DevBuf<int32_t> tets, tet_mat, trusses, truss_mat, mat_kind, col, diag_slot, pair_code[2], send_nodes;
+    DevBuf<int64_t> slice_ptr, pair_ptr[2];
+    DevBuf<uint32_t> cptr[2];
+    DevBuf<uint16_t> ccode[2];
+    DevBuf<uint8_t> mask;
+    DevBuf<int> err_flag;
+    DevBuf<CgState> st;
+    DevBuf<double> sendbuf;
+    CgState* h_st = nullptr;  // pinned
+    int* h_flag = nullptr;    // pinned
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+
+    // options
+    int cg_mode = 0, asm_minb = 2, check_every = 16, cg_bps = 0;
+    int cg_grid = 0, part_stride = 4096;
+
+    // comm
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+    std::vector<int32_t> nbr_rank;
+    std::vector<int64_t> send_ptr, recv_ptr;
+
+    int64_t n_local_dofs() const { return n_nodes * dim; }
+    int64_t n_own_dofs() const { return n_owned * dim; }
+};
+
+namespace {
+
+template <typename F>
+int32_t guard(onsas_ctx* ctx, F&& f) {
+    try {
+        if (ctx) {
+            cudaError_t e = cudaSetDevice(ctx->device);
+            if (e != cudaSuccess) throw OnsasError(ONSAS_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+        }
+        f();
+        return ONSAS_OK;
+    } catch (const OnsasError& e) {
+        if (ctx) ctx->err = e.what();
+        else g_create_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        if (ctx) ctx->err = "host allocation failed";
+        return ONSAS_ERR_ALLOC;
+    } catch (const std::exception& e) {
+        if (ctx) ctx->err = e.what();
+        return ONSAS_ERR_INVALID_ARG;
+    } catch (...) {
+        if (ctx) ctx->err = "unknown error";
+        return ONSAS_ERR_INVALID_ARG;
+    }
+}
+
+void require(bool cond, int code, const char* msg) {
+    if (!cond) throw OnsasError(code, msg);
+}
+
+// ---------------------------------------------------------------- assembly launch
+template <int FAMILY, int KIND, int DIM, bool ACCUM, int MAXT, int MINB>
+void launch_asm_inst(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
+    auto kern = k_assemble<FAMILY, KIND, DIM, ACCUM, MAXT, MINB>;
+    static size_t configured = 0;  // per instantiation
+    if (smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    kern<<<(unsigned)c->tab.n_slices, threads, smem, c->stream>>>(A);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+template <int KIND>
+void launch_asm_tets_kind(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
+    // register budget variants: 1 -> unconstrained, 2 -> 128 regs (2 CTAs of 256), 3 -> 112 regs (3 CTAs of 192)
+    if (c->asm_minb == 1) launch_asm_inst<0, KIND, 3, false, 256, 1>(c, A, threads, smem);
+    else if (c->asm_minb == 3 && threads <= 192) launch_asm_inst<0, KIND, 3, false, 192, 3>(c, A, threads, smem);
+    else launch_asm_inst<0, KIND, 3, false, 256, 2>(c, A, threads, smem);
+}
+
+AsmArgs make_asm_args(onsas_ctx* c, int family) {
+    AsmArgs A{};
+    A.n_rows = c->n_owned;
+    A.X = c->X.p;
+    A.U = c->U.p;
+    A.conn = family == 0 ? c->tets.p : c->trusses.p;
+    A.mat_id = family == 0 ? (c->tet_has_mat ? c->tet_mat.p : nullptr) : (c->truss_has_mat ? c->truss_mat.p : nullptr);
+    A.mat_kind = c->mat_kind.p;
+    A.mat_params = c->mat_params.p;
+    A.area = c->area.p;
+    A.strain_model = c->strain_model;
+    A.pair_ptr = c->pair_ptr[family].p;
+    A.pair_code = c->pair_code[family].p;
+    A.cptr = c->cptr[family].p;
+    A.ccode = c->ccode[family].p;
+    A.slice_ptr = c->slice_ptr.p;
+    A.val = c->val.p;
+    A.F_int = c->Fint.p;
+    A.elem_out = family == 0 ? c->tet_out.p : c->truss_out.p;
+    A.err_flag = c->err_flag.p;
+    return A;
+}
+
+int round_threads(int pairs) {
+    int t = ((std::max(pairs, 1) + 31) / 32) * 32;
+    return std::min(std::max(t, 64), 256);
+}
+
+void halo_exchange(onsas_ctx* c, double* v, int gate);
+
+void launch_assemble(onsas_ctx* c) {
+    require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
+    if (c->n_ranks > 1) halo_exchange(c, c->U.p, 0);
+    bool wrote = false;
+    if (c->n_tets > 0) {
+        AsmArgs A = make_asm_args(c, 0);
+        const int mp = c->tab.fam[0].max_pairs_per_slice;
+        const int threads = round_threads(mp);
+        const size_t smem = (size_t)std::max(mp, 1) * TET_REC * sizeof(double);
+        switch (c->tet_kind) {
+            case MAT_SVK: launch_asm_tets_kind<MAT_SVK>(c, A, threads, smem); break;
+            case MAT_NEOHOOKEAN: launch_asm_tets_kind<MAT_NEOHOOKEAN>(c, A, threads, smem); break;
+            case MAT_ISOLINEAR: launch_asm_tets_kind<MAT_ISOLINEAR>(c, A, threads, smem); break;
+            default: launch_asm_tets_kind<MAT_MIXED>(c, A, threads, smem); break;
+        }
+        wrote = true;
+    }
+    if (c->n_trusses > 0) {
+        AsmArgs A = make_asm_args(c, 1);
+        const int mp = c->tab.fam[1].max_pairs_per_slice;
+        const int threads = round_threads(mp);
+        const size_t smem = (size_t)std::max(mp, 1) * truss_rec(c->dim) * sizeof(double);
+        if (wrote) {
+            if (c->dim == 3) launch_asm_inst<1, 0, 3, true, 256, 2>(c, A, threads, smem);
+            else if (c->dim == 2) launch_asm_inst<1, 0, 2, true, 256, 2>(c, A, threads, smem);
+            else launch_asm_inst<1, 0, 1, true, 256, 2>(c, A, threads, smem);
+        } else {
+            if (c->dim == 3) launch_asm_inst<1, 0, 3, false, 256, 2>(c, A, threads, smem);
+            else if (c->dim == 2) launch_asm_inst<1, 0, 2, false, 256, 2>(c, A, threads, smem);
+            else launch_asm_inst<1, 0, 1, false, 256, 2>(c, A, threads, smem);
+        }
+        wrote = true;
+    }
+    if (!wrote) {  // structure without elements: K = 0, F_int = 0
+        c->val.zero(c->stream);
+        c->Fint.zero(c->stream);
+    }
+}
+
+// ---------------------------------------------------------------- halo exchange (NCCL send/recv)
+void halo_exchange(onsas_ctx* c, double* v, int gate) {
+    if (c->n_ranks <= 1 || c->nbr_rank.empty()) return;
+    const int bs = c->dim;
+    const int64_t n_send = c->send_ptr.back();
+    if (n_send > 0) {
+        const int64_t tot = n_send * bs;
+        k_pack<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(v, c->send_nodes.p, n_send, bs, c->sendbuf.p, c->st.p, gate);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    NCCL_CHECK(g_nccl.GroupStart());
+    for (size_t k = 0; k < c->nbr_rank.size(); ++k) {
+        const int64_t ns = (c->send_ptr[k + 1] - c->send_ptr[k]) * bs, nr = (c->recv_ptr[k + 1] - c->recv_ptr[k]) * bs;
+        if (ns > 0) NCCL_CHECK(g_nccl.Send(c->sendbuf.p + c->send_ptr[k] * bs, (size_t)ns, ncclDouble, c->nbr_rank[k], c->comm, c->stream));
+        if (nr > 0) NCCL_CHECK(g_nccl.Recv(v + (c->n_owned + c->recv_ptr[k]) * bs, (size_t)nr, ncclDouble, c->nbr_rank[k], c->comm, c->stream));
+    }
+    NCCL_CHECK(g_nccl.GroupEnd());
+}
+
+void allreduce(onsas_ctx* c, double* d, int count) {
+    if (c->n_ranks <= 1) return;
+    NCCL_CHECK(g_nccl.AllReduce(d, d, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
+}
+
+// ---------------------------------------------------------------- CG drivers
+CgArgs make_cg_args(onsas_ctx* c, int precond, double reltol, double abstol, int64_t maxiter, bool use_rhs, int update_U) {
+    CgArgs A{};
+    A.n_rows = c->n_owned;
+    A.n = c->n_own_dofs();
+    A.slice_ptr = c->slice_ptr.p;
+    A.col = c->col.p;
+    A.val = c->val.p;
+    A.diag_slot = c->diag_slot.p;
+    A.mask = c->mask.p;
+    A.x = c->x.p;
+    A.r = c->r.p;
+    A.p = c->p.p;
+    A.Ap = c->Ap.p;
+    A.dinv = c->dinv.p;
+    A.Fext = c->Fext.p;
+    A.Fint = c->Fint.p;
+    A.rhs = use_rhs ? c->rhs.p : nullptr;
+    A.U = c->U.p;
+    A.update_U = update_U;
+    A.precond = precond;
+    A.reltol = reltol;
+    A.abstol = abstol;
+    A.maxiter = maxiter > 0 ? maxiter : c->n_free_global;
+    A.partials = c->partials.p;
+    A.part_stride = c->part_stride;
+    A.st = c->st.p;
+    return A;
+}
+
+template <int BS>
+int persistent_grid(onsas_ctx* c) {
+    int bps = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, cg_persistent<BS>, CG_THREADS, 0));
+    require(bps > 0, ONSAS_ERR_CUDA, "persistent CG kernel does not fit on an SM");
+    if (c->cg_bps > 0) bps = std::min(bps, c->cg_bps);
+    int g = bps * c->n_sm;
+    return std::min(g, c->part_stride);
+}
+
+template <int BS>
+void run_cg_bs(onsas_ctx* c, CgArgs A) {
+    const int64_t n = A.n;
+    if (c->cg_mode == 0 && c->n_ranks == 1) {
+        if (c->cg_grid == 0) c->cg_grid = persistent_grid<BS>(c);
+        void* args[] = {&A};
+        CUDA_CHECK(cudaLaunchCooperativeKernel((void*)cg_persistent<BS>, dim3(c->cg_grid), dim3(CG_THREADS), args, 0, c->stream));
+        return;
+    }
+    // one launch per phase; collectives in-stream between them
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>((n + CG_THREADS - 1) / CG_THREADS, (int64_t)c->n_sm * 8));
+    const int Gr = (int)std::max<int64_t>(1, std::min<int64_t>((A.n_rows + CG_THREADS - 1) / CG_THREADS, (int64_t)c->n_sm * 8));
+    cudaStream_t s = c->stream;
+    double* red = c->red.p;
+    k_cg_prologue<BS><<<G, CG_THREADS, 0, s>>>(A);
+    k_reduce_partials<<<1, CG_THREADS, 0, s>>>(A.partials, A.part_stride, G, 0, 4, red, A.st, 0);
+    allreduce(c, red, 4);
+    k_cg_init_state<<<1, 1, 0, s>>>(A, red);
+    CUDA_CHECK(cudaGetLastError());
+    for (;;) {
+        for (int j = 0; j < c->check_every; ++j) {
+            k_cg_update_p<<<G, CG_THREADS, 0, s>>>(A);
+            halo_exchange(c, A.p, 1);
+            k_spmv_dot<BS><<<Gr, CG_THREADS, 0, s>>>(A, 1);
+            k_reduce_partials<<<1, CG_THREADS, 0, s>>>(A.partials, A.part_stride, Gr, P_PAP, 1, red, A.st, 1);
+            allreduce(c, red + P_PAP, 1);
+            k_cg_update_xr<<<G, CG_THREADS, 0, s>>>(A, red);
+            k_reduce_partials<<<1, CG_THREADS, 0, s>>>(A.partials, A.part_stride, G, 0, 2, red, A.st, 1);
+            allreduce(c, red, 2);
+            k_cg_advance<<<1, 1, 0, s>>>(A, red);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(c->h_flag, &A.st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        if (*c->h_flag) break;
+    }
+    k_cg_epilogue<<<G, CG_THREADS, 0, s>>>(A);
+    k_reduce_partials<<<1, CG_THREADS, 0, s>>>(A.partials, A.part_stride, G, P_DD, 1, red, A.st, 0);
+    allreduce(c, red + P_DD, 1);
+    k_cg_finish<<<1, 1, 0, s>>>(A, red);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void run_cg(onsas_ctx* c, const CgArgs& A) {
+    require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
+    switch (c->dim) {
+        case 1: run_cg_bs<1>(c, A); break;
+        case 2: run_cg_bs<2>(c, A); break;
+        default: run_cg_bs<3>(c, A); break;
+    }
+}
+
+void fetch_state(onsas_ctx* c) {
+    CUDA_CHECK(cudaMemcpyAsync(c->h_st, c->st.p, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+void check_deferred(onsas_ctx* c) {
+    if (*c->h_flag != 0) {
+        c->err_flag.zero(c->stream);
+        *c->h_flag = 0;
+        throw OnsasError(ONSAS_ERR_NEGATIVE_VOLUME, "Element with negative volume, check connectivity.");
+    }
+}
+
+void fill_info(onsas_ctx* c, onsas_step_info* info, float ms_a, float ms_s) {
+    const CgState& s = *c->h_st;
+    info->norm_dU = std::sqrt(s.dd);
+    info->norm_U = std::sqrt(s.uu);
+    info->norm_r = std::sqrt(s.rr0);
+    info->norm_Fext = std::sqrt(s.ff);
+    info->cg_iters = s.it;
+    info->cg_residual = s.res;
+    info->cg_tol = s.tol;
+    info->ms_assemble = ms_a;
+    info->ms_solve = ms_s;
+}
+
+void download(onsas_ctx* c, double* h, const double* d, size_t n) {
+    CUDA_CHECK(cudaMemcpyAsync(h, d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int32_t onsas_version(void) { return 100; }
+
+const char* onsas_last_error(onsas_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t onsas_create(int32_t device, onsas_ctx** out) {
+    if (!out) return ONSAS_ERR_INVALID_ARG;
+    *out = nullptr;
+    onsas_ctx* c = nullptr;
+    int32_t st = guard(nullptr, [&] {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw OnsasError(ONSAS_ERR_CUDA, std::string("no CUDA device available (libonsas_cuda has no CPU fallback): ") +
+                                                 cudaGetErrorString(e));
+        require(device >= 0 && device < ndev, ONSAS_ERR_INVALID_ARG, "device index out of range");
+        CUDA_CHECK(cudaSetDevice(device));
+        c = new onsas_ctx();
+        c->device = device;
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        c->n_sm = prop.multiProcessorCount;
+        require(prop.cooperativeLaunch != 0, ONSAS_ERR_UNSUPPORTED, "device lacks cooperative launch");
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
+        CUDA_CHECK(cudaMallocHost(&c->h_st, sizeof(CgState)));
+        CUDA_CHECK(cudaMallocHost(&c->h_flag, sizeof(int)));
+        std::memset(c->h_st, 0, sizeof(CgState));
+        *c->h_flag = 0;
+        for (auto& ev : c->ev) CUDA_CHECK(cudaEventCreate(&ev));
+        c->err_flag.alloc(1);
+        c->err_flag.zero(c->stream);
+        c->st.alloc(1);
+        c->st.zero(c->stream);
+        c->partials.alloc((size_t)P_COUNT * c->part_stride);
+        c->partials.zero(c->stream);
+        c->red.alloc(8);
+        c->red.zero(c->stream);
+    });
+    if (st != ONSAS_OK) {
+        delete c;
+        return st;
+    }
+    *out = c;
+    return ONSAS_OK;
+}
+
+int32_t onsas_destroy(onsas_ctx* c) {
+    if (!c) return ONSAS_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto& ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->h_st) cudaFreeHost(c->h_st);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return ONSAS_OK;
+}
+
+int32_t onsas_set_stream(onsas_ctx* c, void* s) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->stream = s ? (cudaStream_t)s : c->own_stream;
+    });
+}
+
+int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        switch (key) {
+            case ONSAS_OPT_CG_MODE: require(value == 0 || value == 1, ONSAS_ERR_INVALID_ARG, "cg mode must be 0 or 1"); c->cg_mode = (int)value; break;
+            case ONSAS_OPT_ASM_MINBLOCKS: require(value >= 1 && value <= 3, ONSAS_ERR_INVALID_ARG, "min blocks must be 1..3"); c->asm_minb = (int)value; break;
+            case ONSAS_OPT_CG_CHECK_EVERY: require(value >= 1 && value <= 4096, ONSAS_ERR_INVALID_ARG, "check_every out of range"); c->check_every = (int)value; break;
+            case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
+            default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
+        }
+    });
+}
+
+// ---------------------------------------------------------------- mesh upload
+int32_t onsas_set_nodes(onsas_ctx* c, int64_t n_nodes, int64_t n_owned, int32_t dim, const double* xyz) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(dim >= 1 && dim <= 3, ONSAS_ERR_INVALID_ARG, "dim must be 1, 2 or 3");
+        require(n_nodes >= 0 && n_owned >= 0 && n_owned <= n_nodes, ONSAS_ERR_INVALID_ARG, "bad node counts");
+        require(n_nodes == 0 || xyz, ONSAS_ERR_INVALID_ARG, "xyz is NULL");
+        require(n_nodes * dim < (int64_t)0x7fffffff, ONSAS_ERR_UNSUPPORTED, "more than 2^31 dofs per GPU are not supported");
+        c->dim = dim;
+        c->n_nodes = n_nodes;
+        c->n_owned = n_owned;
+        c->h_xyz.assign(xyz, xyz + n_nodes * dim);
+        c->have_nodes = true;
+        c->finalized = false;
+    });
+}
+
+int32_t onsas_set_materials(onsas_ctx* c, int32_t n, const int32_t* kind, const double* params) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(n > 0 && kind && params, ONSAS_ERR_INVALID_ARG, "bad material table");
+        for (int i = 0; i < n; ++i) require(kind[i] >= 0 && kind[i] <= 2, ONSAS_ERR_INVALID_ARG, "unknown material kind");
+        c->h_mat_kind.assign(kind, kind + n);
+        c->h_mat_params.assign(params, params + 2 * n);
+        if (c->finalized) {  // material swap on a finalized mesh (replace!(s, material), Structures.jl)
+            c->mat_kind.upload(c->h_mat_kind, c->stream);
+            c->mat_params.upload(c->h_mat_params, c->stream);
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            c->finalized = false;  // element kinds must be re-derived
+        }
+    });
+}
+
+int32_t onsas_set_tets(onsas_ctx* c, int64_t n, const int32_t* conn, const int32_t* mat_id) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(n >= 0 && (n == 0 || conn), ONSAS_ERR_INVALID_ARG, "bad tetrahedron table");
+        c->n_tets = n;
+        c->h_tets.assign(conn, conn + 4 * n);
+        c->tet_has_mat = mat_id != nullptr;
+        if (mat_id) c->h_tet_mat.assign(mat_id, mat_id + n);
+        else c->h_tet_mat.clear();
+        c->finalized = false;
+    });
+}
+
+int32_t onsas_set_trusses(onsas_ctx* c, int64_t n, const int32_t* conn, const int32_t* mat_id, const double* area,
+                          int32_t strain_model) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(n >= 0 && (n == 0 || (conn && area)), ONSAS_ERR_INVALID_ARG, "bad truss table");
+        require(strain_model == 0 || strain_model == 1, ONSAS_ERR_INVALID_ARG, "unknown strain model");
+        c->n_trusses = n;
+        c->h_trusses.assign(conn, conn + 2 * n);
+        c->h_area.assign(area, area + n);
+        c->truss_has_mat = mat_id != nullptr;
+        if (mat_id) c->h_truss_mat.assign(mat_id, mat_id + n);
+        else c->h_truss_mat.clear();
+        c->strain_model = strain_model;
+        c->finalized = false;
+    });
+}
+
+int32_t onsas_set_free_dofs(onsas_ctx* c, int64_t n_free, const int64_t* free_dofs, int64_t n_free_global) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->have_nodes, ONSAS_ERR_NOT_READY, "onsas_set_nodes must be called first");
+        require(n_free >= 0 && (n_free == 0 || free_dofs), ONSAS_ERR_INVALID_ARG, "bad free dof list");
+        const int64_t nd = c->n_own_dofs();
+        c->h_mask.assign((size_t)c->n_local_dofs(), 0);
+        for (int64_t k = 0; k < n_free; ++k) {
+            require(free_dofs[k] >= 0 && free_dofs[k] < nd, ONSAS_ERR_INVALID_ARG, "free dof out of the owned range");
+            c->h_mask[free_dofs[k]] = 1;
+        }
+        c->n_free = n_free;
+        c->n_free_global = n_free_global > 0 ? n_free_global : n_free;
+        c->have_free = true;
+        if (c->finalized) {
+            c->mask.upload(c->h_mask, c->stream);
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        }
+    });
+}
+
+int32_t onsas_finalize_mesh(onsas_ctx* c) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->have_nodes, ONSAS_ERR_NOT_READY, "onsas_set_nodes has not been called");
+        require(!c->h_mat_kind.empty(), ONSAS_ERR_NOT_READY, "onsas_set_materials has not been called");
+        require(c->have_free, ONSAS_ERR_NOT_READY, "onsas_set_free_dofs has not been called");
+        const int nm = (int)c->h_mat_kind.size();
+        auto check_mat = [&](const std::vector<int32_t>& ids, int64_t n) {
+            for (int64_t e = 0; e < (int64_t)ids.size() && e < n; ++e)
+                require(ids[e] >= 0 && ids[e] < nm, ONSAS_ERR_INVALID_ARG, "element material id out of range");
+        };
+        if (c->tet_has_mat) check_mat(c->h_tet_mat, c->n_tets);
+        if (c->truss_has_mat) check_mat(c->h_truss_mat, c->n_trusses);
+        // kinds in use
+        if (c->n_tets > 0) {
+            int kind = -1;
+            bool mixed = false;
+            if (!c->tet_has_mat) kind = c->h_mat_kind[0];
+            else
+                for (int64_t e = 0; e < c->n_tets; ++e) {
+                    int k = c->h_mat_kind[c->h_tet_mat[e]];
+                    if (kind < 0) kind = k;
+                    else if (k != kind) { mixed = true; break; }
+                }
+            c->tet_kind = mixed ? MAT_MIXED : kind;
+        }
+        if (c->n_trusses > 0) {
+            for (int64_t e = 0; e < c->n_trusses; ++e) {
+                int k = c->h_mat_kind[c->truss_has_mat ? c->h_truss_mat[e] : 0];
+                // Trusses.jl:126,159 dispatch on AbstractHyperElasticMaterial only
+                require(k != MAT_ISOLINEAR, ONSAS_ERR_UNSUPPORTED, "trusses need a hyperelastic material (SVK / NeoHookean)");
+            }
+        }
+        std::string msg = build_mesh_tables(c->dim, c->n_nodes, c->n_owned, c->n_tets, c->h_tets.data(), c->n_trusses,
+                                            c->h_trusses.data(), c->tab);
+        if (!msg.empty()) throw OnsasError(ONSAS_ERR_INVALID_ARG, msg);
+        // reference volume check (Tetrahedrons.jl:134-138), once: X never changes
+        {
+            bool bad = false;
+            const double* X = c->h_xyz.data();
+#pragma omp parallel for schedule(static) reduction(|| : bad)
+            for (int64_t e = 0; e < c->n_tets; ++e) {
+                const int32_t* nd = &c->h_tets[4 * e];
+                double c0[3], c1[3], c2[3];
+                for (int i = 0; i < 3; ++i) {
+                    c0[i] = X[3 * (int64_t)nd[0] + i] - X[3 * (int64_t)nd[1] + i];
+                    c1[i] = X[3 * (int64_t)nd[3] + i] - X[3 * (int64_t)nd[1] + i];
+                    c2[i] = X[3 * (int64_t)nd[2] + i] - X[3 * (int64_t)nd[1] + i];
+                }
+                double det = c0[0] * (c1[1] * c2[2] - c1[2] * c2[1]) + c0[1] * (c1[2] * c2[0] - c1[0] * c2[2]) +
+                             c0[2] * (c1[0] * c2[1] - c1[1] * c2[0]);
+                if (!(det / 6.0 > 0.0)) bad = true;
+            }
+            if (bad) throw OnsasError(ONSAS_ERR_NEGATIVE_VOLUME, "Element with negative volume, check connectivity.");
+        }
+        const size_t max_smem = 227 * 1024;
+        require((size_t)c->tab.fam[0].max_pairs_per_slice * TET_REC * 8 <= max_smem &&
+                    (size_t)c->tab.fam[1].max_pairs_per_slice * truss_rec(c->dim) * 8 <= max_smem,
+                ONSAS_ERR_UNSUPPORTED, "node valence too high: a slice of 8 nodes has more element pairs than fit in shared memory");
+
+        // diagonal block position per row
+        std::vector<int32_t> dslot((size_t)c->n_owned, 0);
+        for (int64_t i = 0; i < c->n_owned; ++i) {
+            const int64_t base = c->tab.slice_ptr[i / SLICE_ROWS];
+            const int l = (int)(i % SLICE_ROWS);
+            int s = 0;
+            while (s < c->tab.row_nblk[i] && c->tab.col[(base + s) * SLICE_ROWS + l] != i) ++s;
+            dslot[i] = s;
+        }
+
+        cudaStream_t s = c->stream;
+        const size_t nl = (size_t)c->n_local_dofs(), no = (size_t)c->n_own_dofs();
+        c->X.upload(c->h_xyz, s);
+        c->mat_kind.upload(c->h_mat_kind, s);
+        c->mat_params.upload(c->h_mat_params, s);
+        c->tets.upload(c->h_tets, s);
+        if (c->tet_has_mat) c->tet_mat.upload(c->h_tet_mat, s);
+        c->trusses.upload(c->h_trusses, s);
+        if (c->truss_has_mat) c->truss_mat.upload(c->h_truss_mat, s);
+        c->area.upload(c->h_area, s);
+        c->mask.upload(c->h_mask, s);
+        c->slice_ptr.upload(c->tab.slice_ptr, s);
+        c->col.upload(c->tab.col, s);
+        c->diag_slot.upload(dslot, s);
+        for (int f = 0; f < 2; ++f) {
+            c->pair_ptr[f].upload(c->tab.fam[f].pair_ptr, s);
+            c->pair_code[f].upload(c->tab.fam[f].pair_code, s);
+            c->cptr[f].upload(c->tab.fam[f].cptr, s);
+            c->ccode[f].upload(c->tab.fam[f].ccode, s);
+        }
+        c->val.alloc((size_t)c->tab.n_slots() * c->dim * c->dim);
+        c->val.zero(s);
+        c->U.alloc(nl); c->U.zero(s);
+        c->Fext.alloc(nl); c->Fext.zero(s);
+        c->Fint.alloc(nl); c->Fint.zero(s);
+        c->p.alloc(nl); c->p.zero(s);
+        c->rhs.alloc(nl); c->rhs.zero(s);
+        c->x.alloc(no); c->x.zero(s);
+        c->r.alloc(no); c->r.zero(s);
+        c->Ap.alloc(no); c->Ap.zero(s);
+        c->dinv.alloc(no); c->dinv.zero(s);
+        c->tet_out.alloc((size_t)c->n_tets * 16); c->tet_out.zero(s);
+        c->truss_out.alloc((size_t)c->n_trusses * 2); c->truss_out.zero(s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        c->cg_grid = 0;
+        c->finalized = true;
+    });
+}
+
+// ---------------------------------------------------------------- state vectors
+int32_t onsas_set_U(onsas_ctx* c, const double* U) {
+    if (!c || !U) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        CUDA_CHECK(cudaMemcpyAsync(c->U.p, U, c->n_local_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));  // the caller may free U right after return
+    });
+}
+int32_t onsas_get_U(onsas_ctx* c, double* U) {
+    if (!c || !U) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        download(c, U, c->U.p, (size_t)c->n_local_dofs());
+    });
+}
+int32_t onsas_set_Fext(onsas_ctx* c, const double* F) {
+    if (!c || !F) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        CUDA_CHECK(cudaMemcpyAsync(c->Fext.p, F, c->n_local_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+int32_t onsas_get_Fint(onsas_ctx* c, double* F) {
+    if (!c || !F) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        std::fill(F, F + c->n_local_dofs(), 0.0);
+        download(c, F, c->Fint.p, (size_t)c->n_own_dofs());
+        CUDA_CHECK(cudaMemcpy(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        check_deferred(c);
+    });
+}
+int32_t onsas_get_dU(onsas_ctx* c, double* dU) {
+    if (!c || !dU) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        std::fill(dU, dU + c->n_local_dofs(), 0.0);
+        download(c, dU, c->x.p, (size_t)c->n_own_dofs());
+    });
+}
+
+// ---------------------------------------------------------------- hot path
+int32_t onsas_assemble(onsas_ctx* c) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] { launch_assemble(c); });  // asynchronous; errors surface at the next synchronizing call
+}
+
+int32_t onsas_eval_elements(onsas_ctx* c, int32_t family, int64_t first, int64_t count, double* f, double* K, double* sig,
+                            double* eps) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        require(family == 0 || family == 1, ONSAS_ERR_INVALID_ARG, "unknown element family");
+        const int64_t ne = family == 0 ? c->n_tets : c->n_trusses;
+        require(first >= 0 && count >= 0 && first + count <= ne, ONSAS_ERR_INVALID_ARG, "element range out of bounds");
+        require(f && K && sig && eps, ONSAS_ERR_INVALID_ARG, "NULL output buffer");
+        if (count == 0) return;
+        const int nde = (family == 0 ? 4 : 2) * c->dim;
+        DevBuf<double> df, dK, ds, de;
+        df.alloc((size_t)count * nde);
+        dK.alloc((size_t)count * nde * nde);
+        ds.alloc((size_t)count * 9);
+        de.alloc((size_t)count * 9);
+        EvalArgs A{};
+        A.first = first; A.count = count; A.dim = c->dim;
+        A.X = c->X.p; A.U = c->U.p;
+        A.conn = family == 0 ? c->tets.p : c->trusses.p;
+        A.mat_id = family == 0 ? (c->tet_has_mat ? c->tet_mat.p : nullptr) : (c->truss_has_mat ? c->truss_mat.p : nullptr);
+        A.mat_kind = c->mat_kind.p; A.mat_params = c->mat_params.p; A.area = c->area.p; A.strain_model = c->strain_model;
+        A.f = df.p; A.K = dK.p; A.sig = ds.p; A.eps = de.p; A.err_flag = c->err_flag.p;
+        const unsigned grid = (unsigned)((count + 127) / 128);
+        if (family == 0) k_eval_tets<<<grid, 128, 0, c->stream>>>(A);
+        else if (c->dim == 3) k_eval_trusses<3><<<grid, 128, 0, c->stream>>>(A);
+        else if (c->dim == 2) k_eval_trusses<2><<<grid, 128, 0, c->stream>>>(A);
+        else k_eval_trusses<1><<<grid, 128, 0, c->stream>>>(A);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(f, df.p, df.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(K, dK.p, dK.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(sig, ds.p, ds.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(eps, de.p, de.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        check_deferred(c);
+    });
+}
+
+static void step_impl(onsas_ctx* c, bool assemble, int32_t precond, double reltol, double abstol, int64_t maxiter,
+                      int update_U, onsas_step_info* info) {
+    require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+    require(info != nullptr, ONSAS_ERR_INVALID_ARG, "info is NULL");
+    require(precond == 0 || precond == 1, ONSAS_ERR_INVALID_ARG, "unknown preconditioner");
+    CUDA_CHECK(cudaEventRecord(c->ev[0], c->stream));
+    if (assemble) launch_assemble(c);
+    CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
+    CgArgs A = make_cg_args(c, precond, reltol, abstol, maxiter, false, update_U);
+    run_cg(c, A);
+    CUDA_CHECK(cudaEventRecord(c->ev[2], c->stream));
+    fetch_state(c);
+    float ms_a = 0, ms_s = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms_a, c->ev[0], c->ev[1]));
+    CUDA_CHECK(cudaEventElapsedTime(&ms_s, c->ev[1], c->ev[2]));
+    check_deferred(c);
+    fill_info(c, info, ms_a, ms_s);
+}
+
+int32_t onsas_newton_step(onsas_ctx* c, int32_t precond, double cg_reltol, double cg_abstol, int64_t cg_maxiter,
+                          onsas_step_info* info) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] { step_impl(c, true, precond, cg_reltol, cg_abstol, cg_maxiter, 1, info); });
+}
+
+int32_t onsas_step(onsas_ctx* c, int32_t precond, double cg_reltol, double cg_abstol, int64_t cg_maxiter, int32_t update_U,
+                   onsas_step_info* info) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] { step_impl(c, false, precond, cg_reltol, cg_abstol, cg_maxiter, update_U ? 1 : 0, info); });
+}
+
+int32_t onsas_pcg(onsas_ctx* c, const double* b, double* x, int32_t precond, double reltol, double abstol, int64_t maxiter,
+                  int64_t* iters, double* residual) {
+    if (!c || !b || !x) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        require(precond == 0 || precond == 1, ONSAS_ERR_INVALID_ARG, "unknown preconditioner");
+        CUDA_CHECK(cudaMemcpyAsync(c->rhs.p, b, c->n_local_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CgArgs A = make_cg_args(c, precond, reltol, abstol, maxiter, true, 0);
+        run_cg(c, A);
+        fetch_state(c);
+        std::fill(x, x + c->n_local_dofs(), 0.0);
+        download(c, x, c->x.p, (size_t)c->n_own_dofs());
+        if (iters) *iters = c->h_st->it;
+        if (residual) *residual = c->h_st->res;
+    });
+}
+
+int32_t onsas_spmv(onsas_ctx* c, const double* x, double* y) {
+    if (!c || !x || !y) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        CUDA_CHECK(cudaMemcpyAsync(c->p.p, x, c->n_local_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CgArgs A = make_cg_args(c, 0, 0, 0, 1, false, 0);
+        const int Gr = (int)std::max<int64_t>(1, std::min<int64_t>((A.n_rows + CG_THREADS - 1) / CG_THREADS, (int64_t)c->n_sm * 8));
+        if (c->n_ranks > 1) halo_exchange(c, A.p, 0);
+        switch (c->dim) {
+            case 1: k_spmv_dot<1><<<Gr, CG_THREADS, 0, c->stream>>>(A, 0); break;
+            case 2: k_spmv_dot<2><<<Gr, CG_THREADS, 0, c->stream>>>(A, 0); break;
+            default: k_spmv_dot<3><<<Gr, CG_THREADS, 0, c->stream>>>(A, 0); break;
+        }
+        CUDA_CHECK(cudaGetLastError());
+        std::fill(y, y + c->n_local_dofs(), 0.0);
+        download(c, y, c->Ap.p, (size_t)c->n_own_dofs());
+    });
+}
+
+/* Device-resident SpMV on whatever p currently holds (bench / profiling hook; asynchronous). */
+int32_t onsas_spmv_resident(onsas_ctx* c) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        CgArgs A = make_cg_args(c, 0, 0, 0, 1, false, 0);
+        const int Gr = (int)std::max<int64_t>(1, std::min<int64_t>((A.n_rows + CG_THREADS - 1) / CG_THREADS, (int64_t)c->n_sm * 8));
+        switch (c->dim) {
+            case 1: k_spmv_dot<1><<<Gr, CG_THREADS, 0, c->stream>>>(A, 0); break;
+            case 2: k_spmv_dot<2><<<Gr, CG_THREADS, 0, c->stream>>>(A, 0); break;
+            default: k_spmv_dot<3><<<Gr, CG_THREADS, 0, c->stream>>>(A, 0); break;
+        }
+        CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+/* Blocks until the context's stream is idle and reports deferred errors (negative volume). */
+int32_t onsas_synchronize(onsas_ctx* c) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        check_deferred(c);
+    });
+}
+
+// ---------------------------------------------------------------- results
+int32_t onsas_get_csr_size(onsas_ctx* c, int64_t* n_rows, int64_t* nnz) {
+    if (!c || !n_rows || !nnz) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        *n_rows = c->n_own_dofs();
+        *nnz = c->tab.nnz_blocks * c->dim * c->dim;
+    });
+}
+
+int32_t onsas_get_csr(onsas_ctx* c, int64_t* rowptr, int32_t* col, double* val) {
+    if (!c || !rowptr || !col || !val) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        std::vector<int64_t> rp;
+        std::vector<int32_t> ci;
+        bsell_to_csr_pattern(c->tab, rp, ci);
+        std::copy(rp.begin(), rp.end(), rowptr);
+        std::copy(ci.begin(), ci.end(), col);
+        std::vector<double> h(c->val.n);
+        download(c, h.data(), c->val.p, c->val.n);
+        bsell_to_csr_values(c->tab, h.data(), val);
+    });
+}
+
+int32_t onsas_get_stress_strain(onsas_ctx* c, int32_t family, double* sig, double* eps) {
+    if (!c || !sig || !eps) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        require(family == 0 || family == 1, ONSAS_ERR_INVALID_ARG, "unknown element family");
+        if (family == 0) {
+            std::vector<double> h(c->tet_out.n);
+            if (!h.empty()) download(c, h.data(), c->tet_out.p, h.size());
+            const int VI[6] = {0, 1, 2, 1, 0, 0}, VJ[6] = {0, 1, 2, 2, 2, 1};
+            for (int64_t e = 0; e < c->n_tets; ++e) {
+                for (int k = 0; k < 9; ++k) sig[9 * e + k] = h[16 * e + k];
+                for (int v = 0; v < 6; ++v) {
+                    eps[9 * e + VI[v] + 3 * VJ[v]] = h[16 * e + 9 + v];
+                    eps[9 * e + VJ[v] + 3 * VI[v]] = h[16 * e + 9 + v];
+                }
+            }
+        } else {
+            std::vector<double> h(c->truss_out.n);
+            if (!h.empty()) download(c, h.data(), c->truss_out.p, h.size());
+            for (int64_t e = 0; e < c->n_trusses; ++e) {
+                for (int k = 0; k < 9; ++k) sig[9 * e + k] = eps[9 * e + k] = 0.0;
+                sig[9 * e] = h[2 * e];
+                eps[9 * e] = h[2 * e + 1];
+            }
+        }
+    });
+}
+
+int32_t onsas_get_table_stats(onsas_ctx* c, int64_t out[8]) {
+    if (!c || !out) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        out[0] = c->tab.n_slices;
+        out[1] = c->tab.n_slots();
+        out[2] = c->tab.nnz_blocks;
+        out[3] = (int64_t)c->tab.fam[0].pair_code.size();
+        out[4] = (int64_t)c->tab.fam[1].pair_code.size();
+        out[5] = std::max(c->tab.fam[0].max_pairs_per_slice, c->tab.fam[1].max_pairs_per_slice);
+        out[6] = (int64_t)(c->val.n * sizeof(double));
+        if (c->cg_grid == 0) {
+            switch (c->dim) {
+                case 1: c->cg_grid = persistent_grid<1>(c); break;
+                case 2: c->cg_grid = persistent_grid<2>(c); break;
+                default: c->cg_grid = persistent_grid<3>(c); break;
+            }
+        }
+        out[7] = c->cg_grid;
+    });
+}
+
+// ---------------------------------------------------------------- multi-GPU
+int32_t onsas_comm_unique_id(void* id128) {
+    if (!id128) return ONSAS_ERR_INVALID_ARG;
+    std::string err;
+    if (!g_nccl.load(err)) {
+        g_create_error = err;
+        return ONSAS_ERR_COMM;
+    }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return ONSAS_ERR_COMM;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(id128, &id, 128);
+    return ONSAS_OK;
+}
+
+int32_t onsas_comm_init(onsas_ctx* c, int32_t n_ranks, int32_t rank, const void* id128) {
+    if (!c || !id128) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(n_ranks >= 1 && rank >= 0 && rank < n_ranks, ONSAS_ERR_INVALID_ARG, "bad rank / n_ranks");
+        std::string err;
+        if (!g_nccl.load(err)) throw OnsasError(ONSAS_ERR_COMM, err);
+        ncclUniqueId id;
+        std::memcpy(&id, id128, 128);
+        NCCL_CHECK(g_nccl.CommInitRank(&c->comm, n_ranks, id, rank));
+        c->n_ranks = n_ranks;
+        c->rank = rank;
+    });
+}
+
+int32_t onsas_set_halo(onsas_ctx* c, int32_t n_nbr, const int32_t* nbr_rank, const int64_t* send_ptr,
+                       const int32_t* send_nodes, const int64_t* recv_ptr) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(n_nbr >= 0, ONSAS_ERR_INVALID_ARG, "bad neighbour count");
+        require(n_nbr == 0 || (nbr_rank && send_ptr && recv_ptr), ONSAS_ERR_INVALID_ARG, "NULL halo arrays");
+        c->nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
+        c->send_ptr.assign(send_ptr, send_ptr + n_nbr + 1);
+        c->recv_ptr.assign(recv_ptr, recv_ptr + n_nbr + 1);
+        const int64_t ns = n_nbr ? send_ptr[n_nbr] : 0;
+        require(ns == 0 || send_nodes, ONSAS_ERR_INVALID_ARG, "NULL send list");
+        for (int64_t k = 0; k < ns; ++k)
+            require(send_nodes[k] >= 0 && send_nodes[k] < c->n_owned, ONSAS_ERR_INVALID_ARG, "send node is not owned");
+        require((n_nbr ? recv_ptr[n_nbr] : 0) == c->n_nodes - c->n_owned, ONSAS_ERR_INVALID_ARG,
+                "receive ranges do not cover the halo nodes");
+        c->send_nodes.upload(send_nodes, (size_t)ns, c->stream);
+        c->sendbuf.alloc((size_t)std::max<int64_t>(ns, 1) * c->dim);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+}  // extern "C"

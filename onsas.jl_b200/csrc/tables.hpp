@@ -1,0 +1,61 @@
+// tables.hpp -- host-side preprocessing done once per mesh by onsas_finalize_mesh():
+// node->element "pair" lists for the row-owner assembly, the block sparsity pattern of K in
+// the sliced-ELL layout the SpMV reads, and the fixed-order contribution lists that make the
+// assembly deterministic.  Replaces the reference's per-iteration COO buffers and per-entry
+// sparse insertion (StructuralSolvers/Assemblers.jl:16-88, StaticAnalyses.jl:125-132).
+//
+// Layout ("BSELL-C", C = SLICE_ROWS block rows per slice):
+//   slice sl covers block rows [sl*C, sl*C+C); width[sl] = max #blocks of its rows;
+//   slice_ptr = exclusive prefix sum of width (units: block-columns);
+//   col[(slice_ptr[sl] + s)*C + lane]                 -> node id of the s-th block of row sl*C+lane
+//   val[((slice_ptr[sl] + s)*BS*BS + k)*C + lane]     -> entry k = BS*r + c of that block
+//   padding blocks have col = the row itself and zero values.
+// Within a row the blocks are sorted by node id, so block (row, col) is found by binary search.
+//
+// A "pair" is (row node i, element e, local node a with conn[e][a] == i); the thread that
+// evaluates it produces the block-row a of K_e and f_a.  Pairs of a row are sorted by element
+// id, so every entry of K and F_int is summed in ascending element order (the reference's
+// order for a single-material structure) -- run-to-run and launch-configuration independent.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace onsas {
+
+constexpr int SLICE_ROWS = 8;
+
+struct FamilyTables {
+    int npe = 0;                     // nodes per element (4 tets, 2 trusses)
+    int64_t n_elem = 0;
+    std::vector<int64_t> pair_ptr;   // [n_rows+1] pairs of row i
+    std::vector<int32_t> pair_code;  // [n_pairs] e*npe + a, ascending e within a row
+    std::vector<uint32_t> cptr;      // [n_slots+1] contribution ranges per block slot (slot = slice_ptr*C + s*C + lane)
+    std::vector<uint16_t> ccode;     // [n_pairs*npe] (pair index local to the slice)*4 + b
+    int32_t max_pairs_per_slice = 0;
+};
+
+struct MeshTables {
+    int dim = 3;
+    int64_t n_nodes = 0;  // local nodes (owned + halo)
+    int64_t n_rows = 0;   // owned nodes = block rows of K
+    int64_t n_slices = 0;
+    std::vector<int64_t> slice_ptr;  // [n_slices+1]
+    std::vector<int32_t> col;        // [slice_ptr.back()*C]
+    std::vector<int32_t> row_nblk;   // [n_rows] true number of blocks per row
+    int64_t nnz_blocks = 0;          // sum of row_nblk
+    FamilyTables fam[2];             // 0 = tets, 1 = trusses
+    int64_t n_slots() const { return slice_ptr.empty() ? 0 : slice_ptr.back() * SLICE_ROWS; }
+};
+
+// conn arrays are element-major (npe per element), 0-based local node ids.
+// Returns empty string on success, else an error message.
+std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t n_tets, const int32_t* tets,
+                              int64_t n_trusses, const int32_t* trusses, MeshTables& out);
+
+// Scalar CSR (n_rows*dim rows, n_nodes*dim columns, sorted columns) index arrays of the same pattern.
+void bsell_to_csr_pattern(const MeshTables& t, std::vector<int64_t>& rowptr, std::vector<int32_t>& colidx);
+// Scatter BSELL values into the CSR value array produced for the pattern above.
+void bsell_to_csr_values(const MeshTables& t, const double* val, double* csr_val);
+
+}  // namespace onsas

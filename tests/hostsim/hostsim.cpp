@@ -1,0 +1,324 @@
+// hostsim.cpp -- TEST-ONLY CPU walk-through of the device algorithms in onsas.jl_b200/csrc.
+//
+// This container has no GPU, so the arithmetic (element_math.cuh, compiled here with g++) and
+// the host-built tables (tables.cpp) are exercised by a serial transliteration of the kernels'
+// control flow: phase A / phase B of k_assemble, spmv_row and the PCG phase order.  It is NOT
+// part of the product, is never loaded by onsas.jl_b200, and is not a CPU fallback: the library
+// has none.  tests/test_hostsim.py compares its output with the oracle.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../onsas.jl_b200/csrc/element_math.cuh"
+#include "../../onsas.jl_b200/csrc/tables.hpp"
+
+using namespace onsas;
+
+namespace {
+constexpr int C = SLICE_ROWS;
+constexpr int TET_REC = 39;
+int truss_rec(int dim) { return (2 * dim * dim + dim) | 1; }
+
+template <int K>
+void tet_pair_k(const double X[4][3], const double U[4][3], double p0, double p1, int a, double* rec, double* out16) {
+    TetCommon c;
+    tet_common<K>(X, U, p0, p1, c);
+    if (a == 0 && out16) tet_stress_out<K>(c, p0, p1, out16);
+    tet_row<K>(c, U, a, rec, rec + 36);
+}
+
+void tet_pair(int kind, const double X[4][3], const double U[4][3], double p0, double p1, int a, double* rec, double* out16) {
+    if (kind == MAT_SVK) tet_pair_k<MAT_SVK>(X, U, p0, p1, a, rec, out16);
+    else if (kind == MAT_NEOHOOKEAN) tet_pair_k<MAT_NEOHOOKEAN>(X, U, p0, p1, a, rec, out16);
+    else tet_pair_k<MAT_ISOLINEAR>(X, U, p0, p1, a, rec, out16);
+}
+
+template <int DIM>
+void truss_pair_d(int strain_model, const double X[2][3], const double U[2][3], double Emod, double A, int a, double* rec,
+                  double* se) {
+    double blk[2][9], f[3];
+    truss_row<DIM>(strain_model, X, U, Emod, A, a, blk, f, se);
+    for (int b = 0; b < 2; ++b)
+        for (int k = 0; k < DIM * DIM; ++k) rec[b * DIM * DIM + k] = blk[b][k];
+    for (int r = 0; r < DIM; ++r) rec[2 * DIM * DIM + r] = f[r];
+}
+}  // namespace
+
+extern "C" {
+
+// un-assembled tets through tet_row (mirrors k_eval_tets)
+int hs_eval_tets(int64_t n, const int32_t* conn, const int32_t* mat_id, const int32_t* kind, const double* params,
+                 const double* xyz, const double* Uv, double* f, double* K, double* sig, double* eps) {
+    for (int64_t e = 0; e < n; ++e) {
+        double X[4][3], U[4][3];
+        for (int k = 0; k < 4; ++k)
+            for (int c = 0; c < 3; ++c) {
+                X[k][c] = xyz[3 * (int64_t)conn[4 * e + k] + c];
+                U[k][c] = Uv[3 * (int64_t)conn[4 * e + k] + c];
+            }
+        int m = mat_id ? mat_id[e] : 0;
+        double out[16];
+        for (int a = 0; a < 4; ++a) {
+            double rec[TET_REC];
+            tet_pair(kind[m], X, U, params[2 * m], params[2 * m + 1], a, rec, out);
+            for (int r = 0; r < 3; ++r) {
+                f[12 * e + 3 * a + r] = rec[36 + r];
+                for (int b = 0; b < 4; ++b)
+                    for (int q = 0; q < 3; ++q) K[144 * e + (3 * a + r) + 12 * (3 * b + q)] = rec[9 * b + 3 * r + q];
+            }
+        }
+        const int VI[6] = {0, 1, 2, 1, 0, 0}, VJ[6] = {0, 1, 2, 2, 2, 1};
+        for (int k = 0; k < 9; ++k) sig[9 * e + k] = out[k];
+        for (int v = 0; v < 6; ++v) {
+            eps[9 * e + VI[v] + 3 * VJ[v]] = out[9 + v];
+            eps[9 * e + VJ[v] + 3 * VI[v]] = out[9 + v];
+        }
+    }
+    return 0;
+}
+
+int hs_eval_trusses(int64_t n, int dim, int strain_model, const int32_t* conn, const int32_t* mat_id, const int32_t* kind,
+                    const double* params, const double* area, const double* xyz, const double* Uv, double* f, double* K,
+                    double* sig, double* eps) {
+    const int N = 2 * dim;
+    for (int64_t e = 0; e < n; ++e) {
+        double X[2][3] = {{0}}, U[2][3] = {{0}};
+        for (int k = 0; k < 2; ++k)
+            for (int c = 0; c < dim; ++c) {
+                X[k][c] = xyz[dim * (int64_t)conn[2 * e + k] + c];
+                U[k][c] = Uv[dim * (int64_t)conn[2 * e + k] + c];
+            }
+        int m = mat_id ? mat_id[e] : 0;
+        double Emod = truss_modulus(kind[m], params[2 * m], params[2 * m + 1]);
+        double se[2];
+        for (int a = 0; a < 2; ++a) {
+            double rec[32];
+            if (dim == 3) truss_pair_d<3>(strain_model, X, U, Emod, area[e], a, rec, se);
+            else if (dim == 2) truss_pair_d<2>(strain_model, X, U, Emod, area[e], a, rec, se);
+            else truss_pair_d<1>(strain_model, X, U, Emod, area[e], a, rec, se);
+            for (int r = 0; r < dim; ++r) {
+                f[N * e + dim * a + r] = rec[2 * dim * dim + r];
+                for (int b = 0; b < 2; ++b)
+                    for (int q = 0; q < dim; ++q) K[N * N * e + (dim * a + r) + N * (dim * b + q)] = rec[b * dim * dim + dim * r + q];
+            }
+        }
+        for (int k = 0; k < 9; ++k) sig[9 * e + k] = eps[9 * e + k] = 0.0;
+        sig[9 * e] = se[0];
+        eps[9 * e] = se[1];
+    }
+    return 0;
+}
+
+struct HsModel {
+    MeshTables tab;
+    std::vector<double> val, Fint, tet_out, truss_out;
+    std::vector<int64_t> rowptr;
+    std::vector<int32_t> colidx;
+    std::string err;
+};
+
+HsModel* hs_create(int dim, int64_t n_nodes, int64_t n_rows, int64_t n_tets, const int32_t* tets, int64_t n_trusses,
+                   const int32_t* trusses) {
+    HsModel* m = new HsModel();
+    m->err = build_mesh_tables(dim, n_nodes, n_rows, n_tets, tets, n_trusses, trusses, m->tab);
+    if (m->err.empty()) {
+        m->val.assign((size_t)m->tab.n_slots() * dim * dim, 0.0);
+        m->Fint.assign((size_t)n_rows * dim, 0.0);
+        m->tet_out.assign((size_t)n_tets * 16, 0.0);
+        m->truss_out.assign((size_t)n_trusses * 2, 0.0);
+        bsell_to_csr_pattern(m->tab, m->rowptr, m->colidx);
+    }
+    return m;
+}
+const char* hs_error(HsModel* m) { return m->err.c_str(); }
+void hs_destroy(HsModel* m) { delete m; }
+int64_t hs_nnz(HsModel* m) { return (int64_t)m->colidx.size(); }
+int64_t hs_stat(HsModel* m, int which) {
+    switch (which) {
+        case 0: return m->tab.n_slices;
+        case 1: return m->tab.n_slots();
+        case 2: return m->tab.nnz_blocks;
+        case 3: return m->tab.fam[0].max_pairs_per_slice;
+        case 4: return m->tab.fam[1].max_pairs_per_slice;
+        default: return -1;
+    }
+}
+
+// walk k_assemble for both families at displacement Uv; `threads` emulates blockDim.x
+int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const int32_t* trusses, const int32_t* truss_mat,
+                const double* area, int strain_model, const int32_t* kind, const double* params, const double* xyz,
+                const double* Uv, int threads) {
+    const MeshTables& t = m->tab;
+    const int dim = t.dim, BB = dim * dim;
+    bool wrote = false;
+    for (int fam = 0; fam < 2; ++fam) {
+        const FamilyTables& F = t.fam[fam];
+        if (F.n_elem == 0) continue;
+        const int REC = fam == 0 ? TET_REC : truss_rec(dim);
+        const int FOFF = fam == 0 ? 36 : 2 * BB;
+        const bool ACCUM = wrote;
+        std::vector<double> stage((size_t)std::max(F.max_pairs_per_slice, 1) * REC);
+        for (int64_t sl = 0; sl < t.n_slices; ++sl) {  // one CTA per slice
+            const int64_t r0 = sl * C, r1 = std::min<int64_t>(r0 + C, t.n_rows);
+            const int64_t p0 = F.pair_ptr[r0];
+            const int np = (int)(F.pair_ptr[r1] - p0);
+            for (int tid = 0; tid < threads; ++tid)  // phase A
+                for (int tt = tid; tt < np; tt += threads) {
+                    const int32_t code = F.pair_code[p0 + tt];
+                    double* rec = stage.data() + (size_t)tt * REC;
+                    if (fam == 0) {
+                        const int64_t e = code >> 2;
+                        const int a = code & 3;
+                        double X[4][3], U[4][3];
+                        for (int k = 0; k < 4; ++k)
+                            for (int c = 0; c < 3; ++c) {
+                                X[k][c] = xyz[3 * (int64_t)tets[4 * e + k] + c];
+                                U[k][c] = Uv[3 * (int64_t)tets[4 * e + k] + c];
+                            }
+                        const int mm = tet_mat ? tet_mat[e] : 0;
+                        tet_pair(kind[mm], X, U, params[2 * mm], params[2 * mm + 1], a, rec,
+                                 a == 0 ? m->tet_out.data() + 16 * e : nullptr);
+                    } else {
+                        const int64_t e = code >> 1;
+                        const int a = code & 1;
+                        double X[2][3] = {{0}}, U[2][3] = {{0}};
+                        for (int k = 0; k < 2; ++k)
+                            for (int c = 0; c < dim; ++c) {
+                                X[k][c] = xyz[dim * (int64_t)trusses[2 * e + k] + c];
+                                U[k][c] = Uv[dim * (int64_t)trusses[2 * e + k] + c];
+                            }
+                        const int mm = truss_mat ? truss_mat[e] : 0;
+                        const double Emod = truss_modulus(kind[mm], params[2 * mm], params[2 * mm + 1]);
+                        double se[2];
+                        if (dim == 3) truss_pair_d<3>(strain_model, X, U, Emod, area[e], a, rec, se);
+                        else if (dim == 2) truss_pair_d<2>(strain_model, X, U, Emod, area[e], a, rec, se);
+                        else truss_pair_d<1>(strain_model, X, U, Emod, area[e], a, rec, se);
+                        if (a == 0) {
+                            m->truss_out[2 * e] = se[0];
+                            m->truss_out[2 * e + 1] = se[1];
+                        }
+                    }
+                }
+            // phase B
+            const int64_t base = t.slice_ptr[sl];
+            const int width = (int)(t.slice_ptr[sl + 1] - base);
+            const int nK = width * BB * C, nF = C * dim;
+            for (int tid = 0; tid < threads; ++tid)
+                for (int w = tid; w < nK + nF; w += threads) {
+                    if (w < nK) {
+                        const int lane = w % C, k = (w / C) % BB, s = w / (C * BB);
+                        const int64_t gs = (base + s) * C + lane;
+                        double acc = 0.0;
+                        for (uint32_t q = F.cptr[gs]; q < F.cptr[gs + 1]; ++q) {
+                            const int cc = F.ccode[q];
+                            acc += stage[(size_t)(cc >> 2) * REC + (cc & 3) * BB + k];
+                        }
+                        const int64_t idx = base * BB * C + w;
+                        if (ACCUM) acc += m->val[idx];
+                        m->val[idx] = acc;
+                    } else {
+                        const int j = w - nK, lane = j / dim, r = j % dim;
+                        const int64_t row = r0 + lane;
+                        if (row < r1) {
+                            double acc = 0.0;
+                            for (int64_t tt = F.pair_ptr[row] - p0; tt < F.pair_ptr[row + 1] - p0; ++tt)
+                                acc += stage[(size_t)tt * REC + FOFF + r];
+                            if (ACCUM) acc += m->Fint[row * dim + r];
+                            m->Fint[row * dim + r] = acc;
+                        }
+                    }
+                }
+        }
+        wrote = true;
+    }
+    return 0;
+}
+
+void hs_get(HsModel* m, int64_t* rowptr, int32_t* col, double* csr_val, double* Fint, double* tet_out, double* truss_out) {
+    std::copy(m->rowptr.begin(), m->rowptr.end(), rowptr);
+    std::copy(m->colidx.begin(), m->colidx.end(), col);
+    bsell_to_csr_values(m->tab, m->val.data(), csr_val);
+    std::copy(m->Fint.begin(), m->Fint.end(), Fint);
+    std::copy(m->tet_out.begin(), m->tet_out.end(), tet_out);
+    std::copy(m->truss_out.begin(), m->truss_out.end(), truss_out);
+}
+
+// spmv_row walk: y = M K M x on the BSELL arrays (x has n_nodes*dim entries)
+void hs_spmv(HsModel* m, const uint8_t* mask, const double* x, double* y) {
+    const MeshTables& t = m->tab;
+    const int BS = t.dim;
+    for (int64_t row = 0; row < t.n_rows; ++row) {
+        const int64_t sl = row / C;
+        const int lane = (int)(row % C);
+        const int64_t base = t.slice_ptr[sl];
+        const int width = (int)(t.slice_ptr[sl + 1] - base);
+        double acc[3] = {0, 0, 0};
+        for (int s = 0; s < width; ++s) {
+            const int64_t cn = t.col[(base + s) * C + lane];
+            for (int r = 0; r < BS; ++r)
+                for (int q = 0; q < BS; ++q)
+                    acc[r] += m->val[((base + s) * BS * BS + r * BS + q) * C + lane] * x[cn * BS + q];
+        }
+        for (int r = 0; r < BS; ++r) y[row * BS + r] = mask[row * BS + r] ? acc[r] : 0.0;
+    }
+}
+
+// PCG in the device phase order (prologue, [update_p, spmv+dot, update_xr]*, epilogue)
+int hs_pcg(HsModel* m, const uint8_t* mask, const double* b, double* x, int precond, double reltol, double abstol,
+           int64_t maxiter, int64_t* iters, double* res_out) {
+    const MeshTables& t = m->tab;
+    const int BS = t.dim;
+    const int64_t n = t.n_rows * BS;
+    std::vector<double> r(n), p((size_t)t.n_nodes * BS, 0.0), Ap(n), dinv(n);
+    double rr = 0, rho = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const bool fr = mask[i] != 0;
+        const double ri = fr ? b[i] : 0.0;
+        double di = fr ? 1.0 : 0.0;
+        if (fr && precond) {
+            const int64_t row = i / BS;
+            const int c = (int)(i % BS);
+            const int64_t base = t.slice_ptr[row / C];
+            int s = 0;
+            while (t.col[(base + s) * C + row % C] != row) ++s;
+            di = 1.0 / m->val[((base + s) * BS * BS + c * BS + c) * C + (row % C)];
+        }
+        r[i] = ri;
+        x[i] = 0.0;
+        dinv[i] = di;
+        rr += ri * ri;
+        rho += ri * ri * di;
+    }
+    double res = std::sqrt(rr);
+    const double tol = std::max(reltol * res, abstol);
+    double rho_prev = 1.0;
+    int64_t it = 0;
+    while (!(it >= maxiter || res <= tol)) {
+        const double beta = rho / rho_prev;
+        for (int64_t i = 0; i < n; ++i) p[i] = r[i] * dinv[i] + beta * p[i];
+        hs_spmv(m, mask, p.data(), Ap.data());
+        double pAp = 0;
+        for (int64_t i = 0; i < n; ++i) pAp += p[i] * Ap[i];
+        const double alpha = rho / pAp;
+        rr = 0;
+        double rz = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            x[i] += alpha * p[i];
+            r[i] -= alpha * Ap[i];
+            rr += r[i] * r[i];
+            rz += r[i] * r[i] * dinv[i];
+        }
+        rho_prev = rho;
+        rho = rz;
+        res = std::sqrt(rr);
+        ++it;
+    }
+    *iters = it;
+    *res_out = res;
+    return 0;
+}
+
+}  // extern "C"
