@@ -1,0 +1,173 @@
+"""End-to-end parity: the reference's examples solved through the mirrored API on the GPU vs the oracle's
+Newton driver with a direct solve (displacements, reactions, iteration counts within 1e-8) and vs the analytic answers."""
+import math
+
+import numpy as np
+import pytest
+
+from onsas_jl_b200 import meshgen as mg
+from tests import cases
+from tests.golden import reference_vectors as G
+from tests.test_host_logic import _uniaxial_structure
+
+pytestmark = pytest.mark.gpu
+SOLVE_RTOL = 1e-8
+
+
+def test_uniaxial_extension_as_shipped(ob, oracle):
+    """configs[0]: examples/uniaxial_extension Case 1 through Structure / NonLinearStaticAnalysis / NewtonRaphson / solve."""
+    s, n, t = _uniaxial_structure(ob)
+    sa = ob.NonLinearStaticAnalysis(s, NSTEPS=8)
+    nr = ob.NewtonRaphson(ob.ConvergenceSettings(1e-8, 1e-8, 30), cg_reltol=1e-13, cg_maxiter=500)
+    sol = ob.solve(sa, nr)
+    assert sa.current_step == 1 and sa._ctx is None           # solve() works on a deep copy
+    ux, uy, uz = sol.displacements(n[6])
+    alpha, beta = 1 + ux[-1] / 2.0, 1 + uy[-1] / 1.0
+    assert alpha == pytest.approx(2.0, rel=1e-4) and beta == pytest.approx(math.sqrt(0.1), rel=1e-4)   # :201-202
+    fl = s.flat
+    fm = oracle.FlatModel(xyz=fl.xyz, tets=fl.tets, mat_kind=fl.mat_kind, mat_params=fl.mat_params, free_dofs=fl.free_dofs)
+    ref = oracle.newton_solve(fm, sa.load_factors(), fl.fext, oracle.ConvergenceSettings(1e-8, 1e-8, 30))
+    assert sol.iterations() == ref.iterations == G.UNIAXIAL_EXTENSION_ITERS
+    for k in range(8):
+        assert cases.rel_err(sol.U[k], ref.U[k]) < SOLVE_RTOL
+        assert cases.rel_err(sol.F_int[k], ref.F_int[k]) < SOLVE_RTOL
+        assert cases.rel_err(sol.tet_stress[k], ref.tet_sig[k]) < SOLVE_RTOL
+    e = t[2]
+    F = np.diag([alpha, beta, beta])
+    np.testing.assert_allclose(sol.strain(e)[-1], F.T @ F, rtol=1e-4, atol=1e-8)       # :203
+    assert sol.reactions()[-1].reshape(-1, 3)[:4, 0].sum() == pytest.approx(-3.0, rel=1e-7)
+    assert all(isinstance(c, (ob.ResidualForceCriterion, ob.DeltaUCriterion)) for c in sol.criterion())
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "none"])
+def test_uniaxial_compression_neohookean(ob, oracle, precond):
+    """configs[1] at oracle-sized refinement: NeoHookean cube compression, 9 steps, tol 1e-10."""
+    m, mesh = cases.box_model(6, 3, 3, mat="neo")
+    unit = mg.global_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["x1"], (-1.0, 0.0, 0.0))
+    s = ob.Structure.from_arrays(m.xyz, tets=m.tets, materials=[ob.NeoHookean(E=1.0, nu=0.3)], free_dofs=m.free_dofs,
+                                 fext=lambda t: unit * t)
+    sa = ob.NonLinearStaticAnalysis(s, NSTEPS=9)
+    sol = ob.solve_(sa, ob.NewtonRaphson(ob.ConvergenceSettings(1e-10, 1e-10, 20), preconditioner=precond, cg_reltol=1e-13))
+    ref = oracle.newton_solve(m, sa.load_factors(), lambda t: unit * t, oracle.ConvergenceSettings(1e-10, 1e-10, 20))
+    assert sol.iterations() == ref.iterations == G.UNIAXIAL_COMPRESSION_ITERS
+    for k in range(9):
+        assert cases.rel_err(sol.U[k], ref.U[k]) < SOLVE_RTOL
+        assert cases.rel_err(sol.F_int[k], ref.F_int[k]) < SOLVE_RTOL
+    corner = int(np.argmax(mesh.xyz @ np.ones(3)))
+    U = sol.U[-1].reshape(-1, 3)
+    assert 1 + U[corner, 0] / 2 == pytest.approx(G.UNIAXIAL_COMPRESSION_ALPHA, rel=1e-8)
+    assert 1 + U[corner, 1] == pytest.approx(G.UNIAXIAL_COMPRESSION_BETA, rel=1e-8)
+    P = sol.tet_stress[-1][0].reshape(3, 3, order="F")
+    assert P[0, 0] == pytest.approx(-1.0, rel=1e-4) and abs(P[1, 1]) < 1e-8 and abs(P[2, 2]) < 1e-8
+
+
+def test_reference_default_linear_solver_settings(ob, oracle):
+    """Un-preconditioned CG at reltol sqrt(eps) (the reference's defaults) still lands on the analytic state."""
+    m, mesh = cases.box_model(4, 2, 2, mat="svk")
+    unit = mg.global_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["x1"], (3.0, 0.0, 0.0))
+    s = ob.Structure.from_arrays(m.xyz, tets=m.tets, materials=[ob.SVK(E=1.0, nu=0.3)], free_dofs=m.free_dofs, fext=lambda t: unit * t)
+    sol = ob.solve(ob.NonLinearStaticAnalysis(s, NSTEPS=8), ob.NewtonRaphson(ob.ConvergenceSettings(1e-8, 1e-8, 30), preconditioner="none"))
+    np.testing.assert_allclose(sol.U[-1], mg.homogeneous_field(mesh.xyz, 2.0, math.sqrt(0.1)), atol=1e-5)
+    ref = oracle.newton_solve(m, np.linspace(1 / 8, 1, 8), lambda t: unit * t, oracle.ConvergenceSettings(1e-8, 1e-8, 30), linear="cg")
+    assert sol.iterations() == ref.iterations
+
+
+@pytest.mark.parametrize("name,strain_cls", [("roteng", "RotatedEngineeringStrain"), ("green", "GreenStrain")])
+def test_von_mises_truss(ob, oracle, name, strain_cls):
+    """examples/von_misses_truss through the object API."""
+    strain = getattr(ob, strain_cls)
+    m, fext, p = cases.von_mises_truss(strain.code)
+    n1, n2, n3 = ob.Node(*m.xyz[0]), ob.Node(*m.xyz[1]), ob.Node(*m.xyz[2])
+    d, a = math.sqrt(4 * p["A"] / math.pi), math.sqrt(p["A"])
+    tl, tr = ob.Truss(n1, n2, ob.Circle(d), strain, "left_truss"), ob.Truss(n2, n3, ob.Square(a), strain, "right_truss")
+    mesh = ob.Mesh(nodes=[n1, n2, n3], elements=[tl, tr])
+    ob.set_dofs(mesh, "u", 3)
+    bcs = ob.StructuralBoundaryCondition((ob.FixedField("u", [1, 2, 3]), [n1, n3]), (ob.FixedField("u", [2]), [n2]),
+                                         (ob.GlobalLoad("u", lambda t: [0, 0, p["Fk"] * t]), [n2]))
+    s = ob.Structure(mesh, ob.StructuralMaterial((ob.SVK(E=p["E"], nu=0.0, label="steel"), [tl, tr])), bcs)
+    sol = ob.solve(ob.NonLinearStaticAnalysis(s, NSTEPS=5), ob.NewtonRaphson(ob.ConvergenceSettings(1e-10, 1e-10, 10), cg_reltol=1e-13, cg_maxiter=50))
+    ref = oracle.newton_solve(m, np.linspace(0.2, 1, 5), fext, oracle.ConvergenceSettings(1e-10, 1e-10, 10))
+    assert sol.iterations() == ref.iterations == [G.VON_MISES_ITERS[name]] * 5
+    uk = sol.displacements(n2, 3)
+    assert uk[-1] == pytest.approx(G.VON_MISES_UK[name], rel=1e-8)
+    for k in range(5):
+        assert cases.rel_err(sol.U[k], ref.U[k]) < SOLVE_RTOL
+        assert cases.rel_err(sol.F_int[k], ref.F_int[k]) < SOLVE_RTOL
+    assert abs(sol.displacements(n2, 1)[-1]) <= 100 * np.finfo(float).eps
+    assert sol.stress(tr)[-1][0, 0] == pytest.approx(ref.truss_sig[-1][1, 0], rel=1e-8)
+
+
+def test_clamped_truss_1d(ob, oracle):
+    m, fext, p = cases.clamped_truss(100)
+    s = ob.Structure.from_arrays(m.xyz, trusses=m.trusses, truss_area=m.truss_area, truss_strain=ob.GreenStrain,
+                                 materials=[ob.SVK(E=p["E"], nu=0.3)], free_dofs=m.free_dofs, fext=fext)
+    sol = ob.solve(ob.NonLinearStaticAnalysis(s, NSTEPS=10), ob.NewtonRaphson(cg_reltol=1e-13, cg_maxiter=5000))
+    ref = oracle.newton_solve(m, np.linspace(0.1, 1, 10), fext, oracle.ConvergenceSettings())
+    assert sol.iterations() == ref.iterations
+    for k in range(10):
+        assert cases.rel_err(sol.U[k], ref.U[k]) < SOLVE_RTOL
+    u = sol.U[-1][-1]
+    eg = 0.5 * ((p["L"] + u) ** 2 - p["L"] ** 2) / p["L"] ** 2
+    assert (p["L"] + u) / p["L"] * p["E"] * eg * p["A"] == pytest.approx(p["F"], rel=1e-3)
+
+
+def test_cylinder_linear_analysis_lame(ob, oracle):
+    """configs[2] at oracle size: IsotropicLinearElastic cylinder as the reference ships it (LinearStaticAnalysis) and as
+    a Newton analysis; Lame solution u_r = A r + B / r."""
+    Ri, Re, Lz, E, nu, p = 100.0, 200.0, 30.0, 210.0, 0.3, 10.0
+    mesh = mg.cylinder_tet_mesh(6, 32, 2, Ri, Re, Lz)
+    fixed = {2: mesh.node_sets["z_caps"], 0: mesh.node_sets["outer_on_y_axis"], 1: mesh.node_sets["outer_on_x_axis"]}
+    free = mg.free_dofs_from_fixed(mesh.n_nodes, 3, fixed)
+    Fp = mg.pressure_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["inner"], p)
+    s = ob.Structure.from_arrays(mesh.xyz, tets=mesh.tets, materials=[ob.IsotropicLinearElastic(E, nu)], free_dofs=free, fext=lambda t: Fp * t)
+    lin = ob.solve(ob.LinearStaticAnalysis(s, NSTEPS=3), ob.NewtonRaphson(cg_reltol=1e-13))
+    m = oracle.FlatModel(xyz=mesh.xyz, tets=mesh.tets, mat_kind=[oracle.MAT_ISOLINEAR], mat_params=[[E, nu]], free_dofs=free)
+    ref = oracle.newton_solve(m, [1.0], lambda t: Fp * t, oracle.ConvergenceSettings(1e-8, 1e-8, 5))
+    assert cases.rel_err(lin.U[-1], ref.U[0]) < SOLVE_RTOL
+    np.testing.assert_allclose(lin.U[0] * 3, lin.U[-1], rtol=1e-7, atol=1e-12)   # linear in the load factor
+    r = np.linalg.norm(mesh.xyz[:, :2], axis=1)
+    ur = (lin.U[-1].reshape(-1, 3)[:, :2] * mesh.xyz[:, :2] / r[:, None]).sum(axis=1)
+    A = (1 + nu) * (1 - 2 * nu) * Ri ** 2 * p / (E * (Re ** 2 - Ri ** 2))
+    B = (1 + nu) * Ri ** 2 * Re ** 2 * p / (E * (Re ** 2 - Ri ** 2))
+    np.testing.assert_allclose(ur, A * r + B / r, atol=1e-2 * (Re - Ri))
+    nl = ob.solve(ob.NonLinearStaticAnalysis(s, NSTEPS=1), ob.NewtonRaphson(ob.ConvergenceSettings(1e-8, 1e-8, 5), cg_reltol=1e-13))
+    assert nl.iterations() == ref.iterations and cases.rel_err(nl.U[-1], ref.U[0]) < SOLVE_RTOL
+
+
+def test_million_tet_cube_size_independent_properties(ob):
+    """configs[1] at full size (998 250 tets): properties that need no oracle -- (i) at the analytic homogeneous state the
+    residual vanishes: F_int balances the lumped traction; (ii) stress / strain are the analytic P, C in every element;
+    (iii) K is symmetric: x.(K y) == y.(K x); (iv) re-assembly is bitwise reproducible; (v) one Newton step from a
+    perturbed state returns to the analytic solution."""
+    n = 55
+    mesh = mg.box_tet_mesh(n, n, n, 1.0, 1.0, 1.0)
+    assert mesh.n_tets == 998_250
+    free = mg.free_dofs_from_fixed(mesh.n_nodes, 3, mg.uniaxial_fixed(mesh))
+    E, nu = 1.0, 0.3
+    mu, K = E / 2.6, E / (3 * 0.4)
+    alpha, beta = G.UNIAXIAL_COMPRESSION_ALPHA, G.UNIAXIAL_COMPRESSION_BETA   # NeoHookean, p = 1 compression
+    ctx = ob.context_from_flat(mesh.xyz, tets=mesh.tets, mat_kind=[ob.MAT_NEOHOOKEAN], mat_params=[[K, mu]], free_dofs=free)
+    U = mg.homogeneous_field(mesh.xyz, alpha, beta)
+    Fext = mg.global_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["x1"], (-1.0, 0.0, 0.0))
+    ctx.set_U(U)
+    ctx.set_Fext(Fext)
+    ctx.assemble()
+    Fint = ctx.get_Fint()
+    mask = np.zeros(mesh.n_nodes * 3, bool)
+    mask[free] = True
+    assert np.abs((Fext - Fint)[mask]).max() < 1e-7 * np.abs(Fext).max()   # alpha, beta known to ~1e-11
+    s, e = ctx.get_stress_strain(ob.FAMILY_TET)
+    P11 = mu * alpha - mu / alpha + K * beta ** 2 * (alpha * beta ** 2 - 1)
+    assert np.abs(s[:, 0] - P11).max() < 1e-9 and np.abs(s[:, 4]).max() < 1e-9 and np.abs(s[:, 1]).max() < 1e-12
+    np.testing.assert_allclose(e[:, [0, 4, 8]], np.tile([alpha ** 2, beta ** 2, beta ** 2], (len(e), 1)), rtol=1e-12)
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal(U.size) * mask, rng.standard_normal(U.size) * mask
+    Kx, Ky = ctx.spmv(x), ctx.spmv(y)
+    assert abs(y @ Kx - x @ Ky) < 1e-11 * abs(y @ Kx)
+    ctx.assemble()
+    np.testing.assert_array_equal(ctx.get_Fint(), Fint)
+    np.testing.assert_array_equal(ctx.spmv(x), Kx)
+    ctx.set_U(U + 1e-3 * rng.standard_normal(U.size) * mask)
+    for _ in range(4):
+        info = ctx.newton_step(ob.PRECOND_JACOBI, 1e-10)
+    assert np.abs(ctx.get_U() - U).max() < 1e-8 and info.norm_r / info.norm_Fext < 1e-8

@@ -1,0 +1,226 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+Bars (north star): per-element f_int / K_t within 1e-10 relative; converged displacements, reactions and Newton
+iteration counts within 1e-8 relative of the direct-solve result.  Run with `pytest -m gpu` on a B200."""
+import math
+
+import numpy as np
+import pytest
+
+from tests import cases
+from tests.golden import reference_vectors as G
+
+pytestmark = pytest.mark.gpu
+
+ELEM_RTOL = 1e-10   # north star: per-element f_int and K_t
+SOLVE_RTOL = 1e-8   # north star: converged displacements / reactions
+
+
+def _ctx(ob, m, **kw):
+    return ob.context_from_flat(m.xyz, tets=m.tets, trusses=m.trusses, truss_area=m.truss_area,
+                                truss_strain=m.truss_strain, mat_kind=m.mat_kind, mat_params=m.mat_params,
+                                tet_mat=m.tet_mat, truss_mat=m.truss_mat, free_dofs=m.free_dofs, **kw)
+
+
+def _rowwise_rel(a, b):
+    scale = np.abs(b).max(axis=1, keepdims=True)
+    return float((np.abs(a - b) / scale).max())
+
+
+def test_golden_tet_through_the_abi(ob):
+    """test/entities/tetrahedrons.jl:73-99 literal vectors, rtol 1e-3 as in the reference."""
+    ctx = ob.context_from_flat(G.TET_NODES, tets=[[0, 1, 2, 3]], mat_kind=[ob.MAT_SVK], mat_params=[[G.TET_LAMBDA, G.TET_G]])
+    ctx.set_U(G.TET_U)
+    f, K, s, e = ctx.eval_elements(ob.FAMILY_TET)
+    np.testing.assert_allclose(f[0], G.TET_F_INT, rtol=1e-3)
+    np.testing.assert_allclose(K[0].reshape(12, 12, order="F"), G.TET_K, rtol=1e-3)
+    np.testing.assert_allclose(e[0].reshape(3, 3, order="F"), G.TET_C, rtol=1e-3)
+    # assembled path on the same single element
+    ctx.assemble()
+    np.testing.assert_allclose(ctx.get_Fint(), G.TET_F_INT, rtol=1e-3)
+    rp, ci, v = ctx.get_csr()
+    import scipy.sparse as sp
+    np.testing.assert_allclose(sp.csr_matrix((v, ci, rp), shape=(12, 12)).toarray(), G.TET_K, rtol=1e-3)
+
+
+@pytest.mark.parametrize("mat", ["svk", "neo", "iso"])
+def test_per_element_parity_1e5_random_tets(ob, oracle, mat):
+    """SURVEY.md 8d per-element parity set: 1e5 random distorted tets, f_e / K_e / stress / strain within 1e-10."""
+    m, U = cases.random_tet_model(100_000, mat)
+    f, K, s, e = oracle.eval_tets(m, U)
+    ctx = _ctx(ob, m)
+    ctx.set_U(U)
+    f2, K2, s2, e2 = ctx.eval_elements(ob.FAMILY_TET)
+    assert _rowwise_rel(f2, f) < ELEM_RTOL and _rowwise_rel(K2, K) < ELEM_RTOL
+    assert _rowwise_rel(s2, s) < ELEM_RTOL and _rowwise_rel(e2, e) < ELEM_RTOL
+    # chunked access returns the same numbers
+    f3, K3, _, _ = ctx.eval_elements(ob.FAMILY_TET, first=777, count=1000)
+    np.testing.assert_array_equal(f3, f2[777:1777])
+    np.testing.assert_array_equal(K3, K2[777:1777])
+    # the fused assembly kernel evaluates the same rows: disconnected tets -> K is block diagonal = K_e
+    ctx.assemble()
+    assert cases.rel_err(ctx.get_Fint(), f.ravel()) < ELEM_RTOL
+    s4, e4 = ctx.get_stress_strain(ob.FAMILY_TET)
+    assert _rowwise_rel(s4, s) < ELEM_RTOL and _rowwise_rel(e4, e) < ELEM_RTOL
+    rp, ci, v = ctx.get_csr()
+    assert np.all(np.diff(rp) == 12)
+    Kasm = v.reshape(-1, 12, 12)            # 12 rows of 12 entries per tet, row-major
+    Kref = K.reshape(-1, 12, 12).transpose(0, 2, 1)  # oracle is column-major
+    assert float((np.abs(Kasm - Kref).max(axis=(1, 2)) / np.abs(Kref).max(axis=(1, 2))).max()) < ELEM_RTOL
+
+
+@pytest.mark.parametrize("strain", [0, 1])
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_per_element_parity_trusses(ob, oracle, strain, dim):
+    rng = np.random.default_rng(11)
+    n = 20_000
+    xyz = rng.uniform(0, 1, (2 * n, dim))
+    xyz[1::2] += 0.5
+    bars = np.arange(2 * n, dtype=np.int32).reshape(n, 2)
+    m = oracle.FlatModel(xyz=xyz, dim=dim, trusses=bars, truss_area=rng.uniform(0.5, 2, n), truss_strain=strain,
+                         mat_kind=[0, 1], mat_params=[[0.4, 1.1], [2.0, 0.7]], truss_mat=rng.integers(0, 2, n),
+                         free_dofs=np.arange(2 * n * dim))
+    U = rng.uniform(-0.2, 0.2, 2 * n * dim)
+    f, K, s, e = oracle.eval_trusses(m, U)
+    ctx = _ctx(ob, m)
+    ctx.set_U(U)
+    f2, K2, s2, e2 = ctx.eval_elements(ob.FAMILY_TRUSS)
+    assert _rowwise_rel(f2, f) < ELEM_RTOL and _rowwise_rel(K2, K) < ELEM_RTOL
+    assert cases.rel_err(s2, s) < ELEM_RTOL and cases.rel_err(e2, e) < ELEM_RTOL
+    ctx.assemble()
+    assert cases.rel_err(ctx.get_Fint(), f.ravel()) < ELEM_RTOL
+    s3, e3 = ctx.get_stress_strain(ob.FAMILY_TRUSS)
+    assert cases.rel_err(s3, s) < ELEM_RTOL and cases.rel_err(e3, e) < ELEM_RTOL
+
+
+@pytest.mark.parametrize("mat,grid", [("svk", (12, 6, 6)), ("neo", (7, 5, 3)), ("iso", (9, 2, 1)), ("svk", (1, 1, 1))])
+def test_assembled_system_matches_reference_order_assembly(ob, oracle, mat, grid):
+    m, _ = cases.box_model(*grid, mat=mat, jitter=0.15)
+    U = cases.random_U(m)
+    ref = oracle.Assembly(m).assemble(U)
+    ctx = _ctx(ob, m)
+    ctx.set_U(U)
+    ctx.assemble()
+    rp, ci, v = ctx.get_csr()
+    np.testing.assert_array_equal(rp, ref.rowptr)
+    np.testing.assert_array_equal(ci, ref.col)
+    # SURVEY.md 8c summation-order caveat: compare against the row's absolute scale
+    row_scale = np.repeat(np.maximum.reduceat(np.abs(ref.val), ref.rowptr[:-1]), np.diff(ref.rowptr))
+    assert float((np.abs(v - ref.val) / row_scale).max()) < 1e-12
+    assert cases.rel_err(ctx.get_Fint(), ref.F_int) < 1e-12
+    s, e = ctx.get_stress_strain(ob.FAMILY_TET)
+    assert _rowwise_rel(s, ref.tet_sig) < ELEM_RTOL and _rowwise_rel(e, ref.tet_eps) < ELEM_RTOL
+
+
+def test_assembly_is_bitwise_deterministic_and_launch_independent(ob, oracle):
+    m, _ = cases.box_model(16, 8, 8, mat="neo", jitter=0.1)
+    U = cases.random_U(m)
+    runs = []
+    for minb in (2, 2, 1, 3):
+        ctx = _ctx(ob, m)
+        ctx.set_option(ob._lib.OPT_ASM_MINBLOCKS, minb)
+        ctx.set_U(U)
+        ctx.assemble()
+        ctx.assemble()   # re-assembly overwrites, it does not accumulate (reset_assemble!, StaticAnalyses.jl:125-132)
+        runs.append((ctx.get_csr()[2], ctx.get_Fint()))
+        ctx.close()
+    for v, F in runs[1:]:
+        np.testing.assert_array_equal(v, runs[0][0])
+        np.testing.assert_array_equal(F, runs[0][1])
+
+
+def test_mixed_materials_and_families(ob, oracle):
+    m, mesh = cases.box_model(5, 3, 3, jitter=0.1)
+    rng = np.random.default_rng(2)
+    bars = np.stack([np.arange(0, mesh.n_nodes - 1), np.arange(1, mesh.n_nodes)], axis=1).astype(np.int32)
+    mm = oracle.FlatModel(xyz=m.xyz, tets=m.tets, tet_mat=rng.integers(0, 3, len(m.tets)), trusses=bars,
+                          truss_mat=rng.integers(0, 2, len(bars)), truss_area=rng.uniform(0.1, 0.3, len(bars)),
+                          truss_strain=1, mat_kind=[0, 1, 2], mat_params=[[0.58, 0.38], [0.83, 0.38], [1.0, 0.3]],
+                          free_dofs=m.free_dofs)
+    U = cases.random_U(mm, 0.03)
+    ref = oracle.Assembly(mm).assemble(U)
+    ctx = _ctx(ob, mm)
+    ctx.set_U(U)
+    ctx.assemble()
+    rp, ci, v = ctx.get_csr()
+    np.testing.assert_array_equal(ci, ref.col)
+    assert cases.rel_err(v, ref.val) < 1e-12 and cases.rel_err(ctx.get_Fint(), ref.F_int) < 1e-12
+    s, e = ctx.get_stress_strain(ob.FAMILY_TRUSS)
+    assert cases.rel_err(s, ref.truss_sig) < 1e-12 and cases.rel_err(e, ref.truss_eps) < 1e-12
+
+
+def test_negative_volume_is_reported(ob):
+    X = G.TET_NODES[[1, 0, 2, 3]]
+    with pytest.raises(ob.NegativeVolumeError, match="Element with negative volume, check connectivity."):
+        ob.context_from_flat(X, tets=[[0, 1, 2, 3]], mat_kind=[0], mat_params=[[1.0, 1.0]])
+
+
+def test_abi_argument_errors(ob):
+    ctx = ob.DeviceContext(0)
+    with pytest.raises(ob.OnsasError) as ei:
+        ctx.assemble()
+    assert ei.value.status == ob._lib.ERR_NOT_READY
+    ctx.set_nodes(np.zeros((4, 3)))
+    ctx.set_materials([0], [[1.0, 1.0]])
+    ctx.set_tets([[0, 1, 2, 9]])
+    ctx.set_free_dofs(np.arange(12))
+    with pytest.raises(ob.OnsasError) as ei:
+        ctx.finalize()
+    assert ei.value.status == ob._lib.ERR_INVALID_ARG
+    with pytest.raises(ob.OnsasError):
+        ctx.set_materials([7], [[1.0, 1.0]])
+
+
+# ----------------------------------------------------------------------------- linear solve
+
+@pytest.mark.parametrize("cg_mode", [0, 1])
+@pytest.mark.parametrize("precond", [0, 1])
+def test_spmv_and_pcg_match_oracle(ob, oracle, cg_mode, precond):
+    m, _ = cases.box_model(10, 5, 5, jitter=0.1)
+    U = cases.random_U(m, 0.02)
+    ref = oracle.Assembly(m).assemble(U)
+    ctx = _ctx(ob, m)
+    ctx.set_option(ob._lib.OPT_CG_MODE, cg_mode)
+    ctx.set_U(U)
+    ctx.assemble()
+    mask = m.free_mask()
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(m.n_dofs) * mask
+    assert cases.rel_err(ctx.spmv(x), (ref.csr() @ x) * mask) < 1e-13
+    b = rng.standard_normal(m.n_dofs)
+    diag = np.where(mask, ref.csr().diagonal(), 1.0) if precond else None
+    import scipy.sparse.linalg as spla
+    A = ref.csr()
+    xd = np.zeros(m.n_dofs)
+    xd[m.free_dofs] = spla.spsolve(A[m.free_dofs][:, m.free_dofs].tocsc(), b[m.free_dofs])
+    for reltol in (None, 1e-12):
+        xo, ito, reso = oracle.cg(ref.rowptr, ref.col, ref.val, mask, b, diag=diag, reltol=reltol)
+        xs, its, res = ctx.pcg(b, precond, reltol)
+        assert abs(its - ito) <= max(2, ito // 50)
+        tol = (reltol or math.sqrt(np.finfo(float).eps))
+        nb = np.linalg.norm(b * mask)
+        assert res <= tol * nb * (1 + 1e-12)
+        assert np.linalg.norm((A @ xs - b) * mask) <= 10 * tol * nb          # true residual
+        assert cases.rel_err(xs, xo) < 1e4 * tol and np.all(xs[mask == 0] == 0)
+    assert cases.rel_err(xs, xd) < 1e-8                                        # tight solve == direct solve
+    # deterministic: the same solve twice gives the same bits
+    x1, i1, _ = ctx.pcg(b, precond, 1e-12)
+    x2, i2, _ = ctx.pcg(b, precond, 1e-12)
+    assert i1 == i2
+    np.testing.assert_array_equal(x1, x2)
+    # maxiter is honoured, zero rhs takes zero iterations (IterativeSolvers: residual 0 <= tol 0)
+    assert ctx.pcg(b, precond, 1e-12, maxiter=3)[1] == 3
+    assert ctx.pcg(np.zeros(m.n_dofs), precond)[1] == 0
+
+
+def test_persistent_and_multilaunch_cg_agree(ob, oracle):
+    m, _ = cases.box_model(8, 4, 4, mat="neo", jitter=0.1)
+    U = cases.random_U(m, 0.02)
+    b = np.random.default_rng(1).standard_normal(m.n_dofs)
+    out = []
+    for mode in (0, 1):
+        ctx = _ctx(ob, m)
+        ctx.set_option(ob._lib.OPT_CG_MODE, mode)
+        ctx.set_U(U)
+        ctx.assemble()
+        out.append(ctx.pcg(b, ob.PRECOND_JACOBI, 1e-12))
+    assert abs(out[0][1] - out[1][1]) <= 1 and cases.rel_err(out[0][0], out[1][0]) < 1e-9

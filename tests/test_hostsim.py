@@ -1,0 +1,111 @@
+"""CPU checks of the DEVICE-side arithmetic (onsas.jl_b200/csrc/element_math.cuh compiled with g++) and of the
+host-built tables, by walking the kernels' control flow serially (tests/hostsim).  The real kernels are checked
+on the GPU in test_gpu_*.py; this catches arithmetic / indexing mistakes before a GPU box is spent on them."""
+import numpy as np
+import pytest
+
+from tests import cases
+
+
+@pytest.mark.parametrize("mat", ["svk", "neo", "iso"])
+def test_element_rows_match_oracle(oracle, hostsim, mat):
+    m, U = cases.random_tet_model(2000, mat)
+    f, K, s, e = oracle.eval_tets(m, U)
+    f2, K2, s2, e2 = hostsim.eval_tets(m, U)
+    # north star: per-element f_int and K_t within 1e-10 relative
+    for a, b in ((f2, f), (K2, K), (s2, s), (e2, e)):
+        scale = np.abs(b).max(axis=1, keepdims=True)
+        assert (np.abs(a - b) / scale).max() < 1e-10
+
+
+@pytest.mark.parametrize("strain", [0, 1])
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_truss_rows_match_oracle(oracle, hostsim, strain, dim):
+    rng = np.random.default_rng(11)
+    n = 300
+    xyz = rng.uniform(0, 1, (2 * n, dim))
+    xyz[1::2] += 0.5
+    bars = np.arange(2 * n, dtype=np.int32).reshape(n, 2)
+    m = oracle.FlatModel(xyz=xyz, dim=dim, trusses=bars, truss_area=rng.uniform(0.5, 2, n), truss_strain=strain,
+                         mat_kind=[0, 1], mat_params=[[0.4, 1.1], [2.0, 0.7]], truss_mat=rng.integers(0, 2, n),
+                         free_dofs=np.arange(2 * n * dim))
+    U = rng.uniform(-0.2, 0.2, 2 * n * dim)
+    f, K, s, e = oracle.eval_trusses(m, U)
+    f2, K2, s2, e2 = hostsim.eval_trusses(m, U)
+    for a, b in ((f2, f), (K2, K), (s2, s), (e2, e)):
+        assert cases.rel_err(a, b) < 1e-12
+
+
+@pytest.mark.parametrize("mat,grid", [("svk", (5, 3, 4)), ("neo", (3, 3, 3)), ("iso", (9, 2, 1))])
+def test_row_owner_assembly_matches_reference_order(oracle, hostsim, mat, grid):
+    m, _ = cases.box_model(*grid, mat=mat, jitter=0.15)
+    U = cases.random_U(m)
+    ref = oracle.Assembly(m).assemble(U)
+    sim = hostsim.HostSim(m)
+    out = [sim.assemble(U, threads=t) for t in (192, 64, 256)]
+    rp, ci, v, Fi, to, _ = out[0]
+    np.testing.assert_array_equal(rp, ref.rowptr)
+    np.testing.assert_array_equal(ci, ref.col)
+    row_scale = np.repeat(np.maximum.reduceat(np.abs(ref.val), ref.rowptr[:-1]), np.diff(ref.rowptr))
+    assert (np.abs(v - ref.val) / row_scale).max() < 1e-13
+    assert cases.rel_err(Fi, ref.F_int) < 1e-13
+    assert cases.rel_err(to[:, :9], ref.tet_sig) < 1e-13
+    for o in out[1:]:  # the result does not depend on the launch configuration
+        np.testing.assert_array_equal(o[2], v)
+        np.testing.assert_array_equal(o[3], Fi)
+
+
+def test_mixed_materials_and_families(oracle, hostsim):
+    """tets of three materials + trusses sharing nodes in one structure (ACCUM path of the second family)."""
+    m, mesh = cases.box_model(3, 2, 2, jitter=0.1)
+    rng = np.random.default_rng(2)
+    bars = np.stack([np.arange(0, mesh.n_nodes - 1), np.arange(1, mesh.n_nodes)], axis=1).astype(np.int32)
+    mm = oracle.FlatModel(xyz=m.xyz, tets=m.tets, tet_mat=rng.integers(0, 3, len(m.tets)), trusses=bars,
+                          truss_mat=rng.integers(0, 2, len(bars)), truss_area=rng.uniform(0.1, 0.3, len(bars)),
+                          truss_strain=1, mat_kind=[0, 1, 2], mat_params=[[0.58, 0.38], [0.83, 0.38], [1.0, 0.3]],
+                          free_dofs=m.free_dofs)
+    U = cases.random_U(mm, 0.03)
+    ref = oracle.Assembly(mm).assemble(U)
+    rp, ci, v, Fi, to, tr = hostsim.HostSim(mm).assemble(U)
+    np.testing.assert_array_equal(ci, ref.col)
+    assert cases.rel_err(v, ref.val) < 1e-13 and cases.rel_err(Fi, ref.F_int) < 1e-13
+    assert cases.rel_err(tr[:, 0], ref.truss_sig[:, 0]) < 1e-13
+
+
+def test_partial_ownership_rows(oracle, hostsim):
+    """Multi-GPU layout: only the first n_owned nodes are rows; halo nodes appear as columns only."""
+    m, _ = cases.box_model(4, 2, 2, jitter=0.1)
+    U = cases.random_U(m)
+    ref = oracle.Assembly(m).assemble(U).csr()
+    n_own = 20
+    sim = hostsim.HostSim(m, n_rows=n_own)
+    rp, ci, v, Fi, _, _ = sim.assemble(U)
+    import scipy.sparse as sp
+    got = sp.csr_matrix((v, ci, rp), shape=(3 * n_own, m.n_dofs)).toarray()
+    np.testing.assert_allclose(got, ref[:3 * n_own].toarray(), rtol=1e-13, atol=1e-15)
+
+
+def test_bsell_spmv_and_pcg_phase_order(oracle, hostsim):
+    m, _ = cases.box_model(5, 3, 3, jitter=0.1)
+    ref = oracle.Assembly(m).assemble(cases.random_U(m, 0.02))
+    sim = hostsim.HostSim(m)
+    sim.assemble(cases.random_U(m, 0.02))
+    mask = m.free_mask()
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(m.n_dofs) * mask
+    assert cases.rel_err(sim.spmv(mask, x), (ref.csr() @ x) * mask) < 1e-13
+    b = rng.standard_normal(m.n_dofs)
+    d = np.where(mask, ref.csr().diagonal(), 1.0)
+    for pre, diag in ((0, None), (1, d)):
+        xs, its, _ = sim.pcg(mask, b, pre, 1e-10)
+        xo, ito, _ = oracle.cg(ref.rowptr, ref.col, ref.val, mask, b, diag=diag, reltol=1e-10)
+        assert abs(its - ito) <= 2 and cases.rel_err(xs, xo) < 1e-8
+
+
+def test_table_limits(hostsim, oracle):
+    m, _ = cases.box_model(2, 2, 2)
+    st = hostsim.HostSim(m).stats()
+    assert st[0] == -(-m.n_nodes // 8) and st[2] <= st[1] and st[3] <= 8 * 24
+    bad = oracle.FlatModel(xyz=m.xyz, tets=np.array([[0, 1, 2, 999]], np.int32), free_dofs=[0])
+    with pytest.raises(ValueError):
+        hostsim.HostSim(bad)
