@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ONSAS.jl Newton-Raphson hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells C]
+
+Metric (BASELINE.json): tet f_int + K_t ASSEMBLED elements/s (one "step" = one assemble! pass over the whole
+mesh: element evaluation + deterministic assembly of K, F_int, stress, strain) with the Newton-step time
+(assemble + Jacobi-PCG + update) reported beside it.
+Workload at N = 1 (configs[1]): examples/uniaxial_compression -- NeoHookean tet cube, synthetic structured mesh
+of 55^3 cells = 998 250 tetrahedra, evaluated at the analytic homogeneous state of load factor 0.5.
+N > 1: weak scaling -- a box of N x 55^3 cells partitioned by recursive coordinate bisection into N slabs,
+one rank per GPU, halo exchange of U inside every assembly (NCCL send/recv); value = all tets / max-over-ranks time.
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the stream the kernels run on, W >= 3 warm-up steps,
+inputs larger than L2 (K values + element records + tables ~ 0.4 GB per pass vs 126 MB L2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_TET = 1600  # 16 conn + 96 X + 96 U + 1152 K_e + 96 f_e + 72 P + 72 C
+E_MOD, NU = 1.0, 0.3
+MU, KBULK = E_MOD / (2 * (1 + NU)), E_MOD / (3 * (1 - 2 * NU))
+
+
+def _neo_state(load: float):
+    """alpha, beta with P11 = -load, P22 = 0 for the compressible NeoHookean of NeoHookeanMaterial.jl:94-102."""
+    a, b = 1.0, 1.0
+    for _ in range(60):
+        f = np.array([MU * a - MU / a + KBULK * b ** 2 * (a * b ** 2 - 1) + load,
+                      MU * b - MU / b + KBULK * b * (a ** 2 * b ** 2 - a)])
+        J = np.array([[MU + MU / a ** 2 + KBULK * b ** 4, KBULK * (4 * a * b ** 3 - 2 * b)],
+                      [KBULK * b * (2 * a * b ** 2 - 1), MU + MU / b ** 2 + KBULK * (3 * a ** 2 * b ** 2 - a)]])
+        d = np.linalg.solve(J, -f)
+        a, b = a + d[0], b + d[1]
+        if np.abs(d).max() < 1e-15:
+            break
+    return float(a), float(b)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem(cells: int, n_ranks: int):
+    """Global mesh (box of n_ranks x cells^3 hexes, unit cells), BCs of the uniaxial example, states."""
+    from onsas_jl_b200 import meshgen as mg
+    mesh = mg.box_tet_mesh(cells * n_ranks, cells, cells, float(n_ranks), 1.0, 1.0)
+    free = mg.free_dofs_from_fixed(mesh.n_nodes, 3, mg.uniaxial_fixed(mesh))
+    a0, b0 = _neo_state(4.0 / 9.0)
+    a1, b1 = _neo_state(0.5)
+    U_half = mg.homogeneous_field(mesh.xyz, a1, b1)        # state the assembly is timed at (F != I everywhere)
+    U_prev = mg.homogeneous_field(mesh.xyz, a0, b0)        # start of the timed Newton step (previous load step)
+    Fext = mg.global_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["x1"], (-0.5, 0.0, 0.0))
+    return mesh, free, U_half, U_prev, Fext
+
+
+def pinned(n):
+    import torch
+    return torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+
+
+def run_ours(args):
+    import torch
+    import onsas_jl_b200 as ob
+    from onsas_jl_b200 import partition as pt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    N = world
+    assert N == args.gpus or world == 1, "--gpus must match the torchrun world size"
+
+    mesh, free, U_half, U_prev, Fext = build_problem(args.cells, N)
+    kind, params = [ob.MAT_NEOHOOKEAN], [[KBULK, MU]]
+    n_tets_total = mesh.n_tets
+    if N == 1:
+        ctx = ob.context_from_flat(mesh.xyz, tets=mesh.tets, mat_kind=kind, mat_params=params, free_dofs=free, device=local_rank)
+        loc = lambda v: v  # noqa: E731
+        n_tets_local = mesh.n_tets
+    else:
+        order, ranges = pt.rcb_order(mesh.xyz, N)
+        xyz, tets, inv = pt.renumber(order, mesh.xyz, mesh.tets)
+        gfree = np.sort(inv[free // 3] * 3 + free % 3)
+        part = pt.build_local_part(rank, ranges, xyz, tets=tets, free_dofs=gfree)
+        ctx = ob.DeviceContext(local_rank)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(ob.DeviceContext.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(N, rank, bytes(uid.cpu().numpy().tobytes()))
+        ctx.set_nodes(part.xyz, part.n_owned)
+        ctx.set_materials(kind, params)
+        ctx.set_tets(part.tets)
+        ctx.set_free_dofs(part.free_dofs, part.n_free_global)
+        ctx.set_halo(part.nbr_rank, part.send_ptr, part.send_nodes, part.recv_ptr)
+        ctx.finalize()
+        perm = lambda v: v.reshape(-1, 3)[order].ravel()  # noqa: E731  (global vector in the partition numbering)
+        loc = lambda v: part.scatter_global(perm(v), 3)   # noqa: E731
+        n_tets_local = len(part.tets)
+    stream = torch.cuda.Stream(device=local_rank)   # the library launches on this stream; events are recorded on it
+    ctx.set_stream(stream.cuda_stream)
+    stats = ctx.table_stats()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    K, W = args.steps, max(args.warmup, 3)
+    ctx.set_U(loc(U_half))
+    ctx.set_Fext(loc(Fext))
+    for _ in range(W):
+        ctx.assemble()
+    ctx.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # ---- (1) device-resident assembly throughput: K launches of the fused assembly kernel
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(K):
+        ctx.assemble()
+    ev1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ctx.synchronize()
+    ms_step = ms_total / K
+    value = n_tets_total / (ms_step * 1e-3)
+
+    # ---- (2) end to end through the C ABI with pinned host buffers: H2D of U, assemble, D2H of F_int
+    hU, hF = pinned(ctx.n_dofs), pinned(ctx.n_dofs)
+    hU[:] = loc(U_half)
+    lib, h = ctx._lib, ctx._h
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        assert lib.onsas_set_U(h, hU) == 0
+        assert lib.onsas_assemble(h) == 0
+        assert lib.onsas_get_Fint(h, hF) == 0
+    barrier()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
+    e2e_value = n_tets_total / (ms_e2e * 1e-3)
+
+    # ---- (3) Newton-step time: assemble! + step! (Jacobi-PCG at the reference's default tolerance sqrt(eps))
+    newton = []
+    for _ in range(max(1, min(K, 3))):
+        ctx.set_U(loc(U_prev))
+        barrier()
+        info = ctx.newton_step(ob.PRECOND_JACOBI)
+        newton.append((max_over_ranks(info.ms_assemble + info.ms_solve), info.ms_assemble, info.ms_solve, int(info.cg_iters),
+                       info.norm_r / info.norm_Fext, info.norm_dU / max(info.norm_U, 1e-300)))
+    newton.sort()
+    nw = newton[len(newton) // 2]
+
+    # ---- (4) SpMV alone (secondary roofline)
+    for _ in range(3):
+        ctx.spmv_resident()
+    barrier()
+    ev0.record(stream)
+    for _ in range(20):
+        ctx.spmv_resident()
+    ev1.record(stream)
+    barrier()
+    ms_spmv = max_over_ranks(ev0.elapsed_time(ev1)) / 20
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = _peaks()
+    achieved = ALGO_BYTES_PER_TET * n_tets_local / (ms_step * 1e-3) / 1e9   # per GPU: its own tets per its launch
+    nnzb = stats["nnz_blocks"]
+    n_own_dofs = ctx.n_owned * 3
+    spmv_bytes = 72 * nnzb + 4 * nnzb + 8 * (stats["n_slices"] + 1) + 16 * n_own_dofs + n_own_dofs  # BSR-3x3 + mask
+    out = {
+        "metric": "tet_fint_Kt_assembled_elements_per_s", "value": value, "unit": "tets/s", "n_gpus": N, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"examples/uniaxial_compression NeoHookean tet cube, structured {args.cells}^3 cells per GPU "
+                               f"({n_tets_total} tets total), state = analytic homogeneous field at load factor 0.5",
+                   "n_tets": n_tets_total, "n_dofs": mesh.n_nodes * 3, "l2": "inputs larger than L2 (~0.4 GB touched per pass)",
+                   "partition": "single GPU" if N == 1 else f"RCB slabs, {N} ranks, NCCL halo exchange of U per assembly"},
+        "newton_step_ms": nw[0], "newton_step": {"ms_assemble": nw[1], "ms_solve": nw[2], "cg_iters": nw[3], "precond": "jacobi",
+                                                  "cg_reltol": float(np.sqrt(np.finfo(np.float64).eps)), "rel_residual_in": nw[4],
+                                                  "rel_dU": nw[5]},
+        "e2e": {"value": e2e_value, "unit": "tets/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(ctx.n_dofs * 8),
+                "d2h_bytes_per_step": int(ctx.n_dofs * 8), "what": "onsas_set_U(pinned host) + onsas_assemble + onsas_get_Fint(pinned host)"},
+        "gpu_launches": K * (1 if N == 1 else 2),
+        "roofline": {"bound": "hbm", "kernel": "k_assemble<tet,NeoHookean>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_tet": ALGO_BYTES_PER_TET,
+                     "note": "algorithmic bytes count K_e/f_e once per element; the fused kernel writes each K entry once "
+                             "(compulsory DRAM traffic ~0.45 KB/tet), so frac > 1 is on-chip reuse, not extra bandwidth"},
+        "roofline_spmv": {"bound": "hbm", "kernel": "k_spmv_dot<3>", "achieved": spmv_bytes / (ms_spmv * 1e-3) / 1e9, "peak": peak,
+                          "unit": "GB/s", "frac": spmv_bytes / (ms_spmv * 1e-3) / 1e9 / peak, "ms": ms_spmv,
+                          "bytes": int(spmv_bytes)},
+        "tables": stats, "clocks": clocks,
+    }
+    if N == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.cells, threads=1)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cells: int, threads: int, reps: int = 1):
+    """The oracle (CPU restatement of the reference's algorithm: serial element loop, COO triplets, per-entry sparse
+    insertion) timed on the host cores on the same mesh.  kind = "port": the reference is Julia and cannot run here."""
+    from oracle import oracle as O
+    mesh, free, U_half, _, _ = build_problem(cells, 1)
+    m = O.FlatModel(xyz=mesh.xyz, tets=mesh.tets, mat_kind=[O.MAT_NEOHOOKEAN], mat_params=[[KBULK, MU]], free_dofs=free)
+    if threads == 1:
+        os.environ["OMP_NUM_THREADS"] = "1"
+        asm = O.Assembly(m)
+    else:
+        asm = O.AssemblyMT(m)
+    asm.assemble(U_half)  # warm-up (page faults, pattern)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        asm.assemble(U_half)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": mesh.n_tets / dt, "unit": "tets/s", "cores": threads if threads == 1 else O.lib().orc_num_threads(),
+            "kind": "port", "seconds_per_pass": dt,
+            "sample": f"{reps} full assembly pass(es) of the same {mesh.n_tets}-tet mesh (oracle/onsas_oracle.c, gcc -O2)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm on the host cores (oracle port, all threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    cells = min(args.cells, 55)
+    from oracle import oracle as O
+    mesh, free, U_half, _, _ = build_problem(cells, 1)
+    m = O.FlatModel(xyz=mesh.xyz, tets=mesh.tets, mat_kind=[O.MAT_NEOHOOKEAN], mat_params=[[KBULK, MU]], free_dofs=free)
+    asm = O.AssemblyMT(m)
+    for _ in range(max(1, min(W, 2))):
+        asm.assemble(U_half)
+    Kb = max(1, min(K, 5))
+    t0 = time.perf_counter()
+    for _ in range(Kb):
+        asm.assemble(U_half)
+    dt = (time.perf_counter() - t0) / Kb
+    val = mesh.n_tets / dt
+    cores = O.lib().orc_num_threads()
+    out = {"impl": "reference", "metric": "tet_fint_Kt_assembled_elements_per_s", "value": val, "unit": "tets/s",
+           "n_gpus": args.gpus, "steps": Kb, "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"examples/uniaxial_compression NeoHookean tet cube, structured {cells}^3 cells ({mesh.n_tets} tets), "
+                                  "reference algorithm restated in C (ONSAS.jl is Julia; no Julia toolchain in this image)"},
+           "cpu_baseline": {"value": val, "unit": "tets/s", "cores": cores, "kind": "port",
+                            "sample": f"{Kb} full assembly passes, OpenMP over elements + row-parallel gather"},
+           "e2e": {"value": val, "unit": "tets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=55, help="hexes per edge per GPU (55 -> 998 250 tets)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
