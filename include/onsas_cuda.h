@@ -65,6 +65,7 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_ASM_MINBLOCKS 2 /* 1, 2 or 3 resident CTAs per SM the assembly kernel is compiled for (default 2) */
 #define ONSAS_OPT_CG_CHECK_EVERY 3 /* multi-launch CG: iterations enqueued between host convergence checks (default 16) */
 #define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: CTAs per SM (0 = occupancy maximum) */
+#define ONSAS_OPT_CG_PROFILE 5       /* 1 = the persistent CG kernel records per-phase SM-clock cycles (onsas_get_cg_profile) */
 
 /* ---------------------------------------------------------------- life cycle */
 
@@ -173,6 +174,10 @@ int32_t onsas_get_stress_strain(onsas_ctx* ctx, int32_t family, double* sig, dou
  * [2]=true nonzero blocks, [3]=tet pairs, [4]=truss pairs, [5]=max pairs per slice, [6]=bytes of K values,
  * [7]=persistent CG grid size. */
 int32_t onsas_get_table_stats(onsas_ctx* ctx, int64_t out[8]);
+
+/* Diagnostics: cycles block 0 of the last persistent CG solve spent in [0] p update, [1] grid sync, [2] SpMV + dot,
+ * [3] grid sync, [4] x/r update + dots, [5] grid sync, [6] scalar reductions (needs ONSAS_OPT_CG_PROFILE = 1). */
+int32_t onsas_get_cg_profile(onsas_ctx* ctx, int64_t out[8]);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU) */
 

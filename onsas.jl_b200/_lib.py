@@ -20,7 +20,7 @@ MAT_SVK, MAT_NEOHOOKEAN, MAT_ISOLINEAR = 0, 1, 2
 STRAIN_ROTATED_ENGINEERING, STRAIN_GREEN = 0, 1
 FAMILY_TET, FAMILY_TRUSS = 0, 1
 PRECOND_NONE, PRECOND_JACOBI = 0, 1
-OPT_CG_MODE, OPT_ASM_MINBLOCKS, OPT_CG_CHECK_EVERY, OPT_CG_BLOCKS_PER_SM = 1, 2, 3, 4
+OPT_CG_MODE, OPT_ASM_MINBLOCKS, OPT_CG_CHECK_EVERY, OPT_CG_BLOCKS_PER_SM, OPT_CG_PROFILE = 1, 2, 3, 4, 5
 
 
 class StepInfo(C.Structure):
@@ -66,6 +66,7 @@ SIGNATURES = {
     "onsas_get_csr": (C.c_int32, [_vp, _i64p, _i32p, _dp]),
     "onsas_get_stress_strain": (C.c_int32, [_vp, C.c_int32, _dp, _dp]),
     "onsas_get_table_stats": (C.c_int32, [_vp, _i64p]),
+    "onsas_get_cg_profile": (C.c_int32, [_vp, _i64p]),
     "onsas_comm_unique_id": (C.c_int32, [_vp]),
     "onsas_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp]),
     "onsas_set_halo": (C.c_int32, [_vp, C.c_int32, _vp, _vp, _vp, _vp]),

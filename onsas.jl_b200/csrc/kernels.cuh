@@ -15,6 +15,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include <cstdint>
+#include <type_traits>
 
 #include "element_math.cuh"
 #include "tables.hpp"
@@ -28,37 +29,36 @@ struct IC {
 };
 
 constexpr int C = SLICE_ROWS;
-constexpr int TET_REC = 39;  // 4 blocks * 9 + 3 force entries per (row, element) pair; odd -> conflict-free smem
 
 // ------------------------------------------------------------------------------------------------
 // assembly
 // ------------------------------------------------------------------------------------------------
 struct AsmArgs {
-    int64_t n_rows;
     const double* X;  // dim per node
     const double* U;  // dim per node
-    const int32_t* conn;
-    const int32_t* mat_id;  // may be null (all elements use material 0)
+    const SliceHdr* hdr;        // one 48-byte header per slice
+    const int32_t* pair_nodes;  // npe node ids per pair
+    const int32_t* pair_code;   // e*npe + a per pair
+    const int32_t* mat_id;      // may be null (all elements use material 0)
     const int32_t* mat_kind;
     const double* mat_params;  // 2 per material
     const double* area;        // trusses
     int strain_model;          // trusses
-    const int64_t* pair_ptr;
-    const int32_t* pair_code;
     const uint32_t* cptr;
     const uint16_t* ccode;
-    const int64_t* slice_ptr;
     double* val;
     double* F_int;
     double* elem_out;  // tets: 16 doubles per element; trusses: 2 per element
     int* err_flag;     // set to 1 when an element has non-positive volume
+    int max_pairs;     // sizes of the shared-memory regions
+    int max_width;
+    int64_t n_rows_guard;  // number of owned rows (the last slice may be partial)
 };
 
 template <int KIND>
-__device__ __forceinline__ void tet_pair(const AsmArgs& A, int32_t code, double* rec) {
+__device__ __forceinline__ void tet_pair(const AsmArgs& A, const int4 cn, int32_t code, double* rec) {
     const int64_t e = code >> 2;
     const int a = code & 3;
-    const int4 cn = __ldg(reinterpret_cast<const int4*>(A.conn) + e);
     const int nd[4] = {cn.x, cn.y, cn.z, cn.w};
     double X[4][3], U[4][3];
 #pragma unroll
@@ -101,17 +101,16 @@ __device__ __forceinline__ void tet_pair(const AsmArgs& A, int32_t code, double*
 }
 
 template <int DIM>
-__device__ __forceinline__ void truss_pair(const AsmArgs& A, int32_t code, double* rec) {
+__device__ __forceinline__ void truss_pair(const AsmArgs& A, const int2 cn, int32_t code, double* rec) {
     const int64_t e = code >> 1;
     const int a = code & 1;
-    const int n0 = __ldg(A.conn + 2 * e), n1 = __ldg(A.conn + 2 * e + 1);
     double X[2][3], U[2][3];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) {
-        X[0][c] = __ldg(A.X + DIM * (int64_t)n0 + c);
-        X[1][c] = __ldg(A.X + DIM * (int64_t)n1 + c);
-        U[0][c] = __ldg(A.U + DIM * (int64_t)n0 + c);
-        U[1][c] = __ldg(A.U + DIM * (int64_t)n1 + c);
+        X[0][c] = __ldg(A.X + DIM * (int64_t)cn.x + c);
+        X[1][c] = __ldg(A.X + DIM * (int64_t)cn.y + c);
+        U[0][c] = __ldg(A.U + DIM * (int64_t)cn.x + c);
+        U[1][c] = __ldg(A.U + DIM * (int64_t)cn.y + c);
     }
     const int m = A.mat_id ? __ldg(A.mat_id + e) : 0;
     const double Emod = truss_modulus(__ldg(A.mat_kind + m), __ldg(A.mat_params + 2 * m), __ldg(A.mat_params + 2 * m + 1));
@@ -129,66 +128,127 @@ __device__ __forceinline__ void truss_pair(const AsmArgs& A, int32_t code, doubl
     }
 }
 
-constexpr __host__ __device__ int truss_rec(int dim) { return (2 * dim * dim + dim) | 1; }
+// shared memory of one assembly CTA: [stage: max_pairs*REC doubles][scode: max_pairs*NPE u16][scp: max_width*C+1 u16]
+__host__ __device__ constexpr size_t asm_smem_bytes(int max_pairs, int max_width, int rec, int npe) {
+    return (size_t)max_pairs * rec * 8 + (((size_t)max_pairs * npe * 2 + ((size_t)max_width * SLICE_ROWS + 1) * 2 + 15) / 16) * 16;
+}
 
-// One CTA per BSELL slice (8 block rows).  Phase A: one thread per (row, element) pair evaluates
-// its block-row into shared memory.  Phase B: one thread per matrix entry of the slice sums its
-// contributions in ascending element order and writes K exactly once, fully coalesced; the last
-// 8*DIM items do the same for F_int.  ACCUM adds onto what a previous family already wrote.
-template <int FAMILY, int KIND, int DIM, bool ACCUM, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_assemble(AsmArgs A) {
+// One CTA per BSELL slice (8 block rows).
+//  Phase A: one thread per (row, element) pair.  Loads are arranged in three dependent levels only:
+//           slice header -> {pair node ids, pair code, contribution codes, slot ranges} -> {X, U gathers};
+//           the thread evaluates block-row a of K_e and f_a straight into its shared-memory record and
+//           stages the slice's contribution lists in shared memory on the way.
+//  Phase B: one thread per (block slot, block row r): sums the DIM entries of that row of the block over the
+//           slot's contributions in ascending element order (register accumulators, indices from shared memory)
+//           and writes K exactly once in 64-byte segments; the last C*DIM items do the same for F_int.
+//  ACCUM adds onto what a previous family already wrote.
+template <int FAMILY, int KIND, int DIM, bool ACCUM>
+__device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     extern __shared__ double stage[];
     constexpr int BB = DIM * DIM;
+    constexpr int NPE = FAMILY == 0 ? 4 : 2;
     constexpr int REC = FAMILY == 0 ? TET_REC : truss_rec(DIM);
-    constexpr int FOFF = FAMILY == 0 ? 36 : 2 * BB;
-    constexpr int SHIFT = 2;  // ccode = local_pair*4 + b for both families
-    const int64_t sl = blockIdx.x;
-    const int64_t r0 = sl * C;
-    const int64_t r1 = (r0 + C < A.n_rows) ? r0 + C : A.n_rows;
-    const int64_t p0 = A.pair_ptr[r0];
-    const int np = (int)(A.pair_ptr[r1] - p0);
+    constexpr int FOFF = NPE * BB;
+    uint16_t* scode = reinterpret_cast<uint16_t*>(stage + (size_t)A.max_pairs * REC);
+    uint16_t* scp = scode + (size_t)A.max_pairs * NPE;
+    const int tid = threadIdx.x, nth = blockDim.x;
 
-    for (int t = threadIdx.x; t < np; t += blockDim.x) {
-        const int32_t code = __ldg(A.pair_code + p0 + t);
-        if (FAMILY == 0)
-            tet_pair<KIND>(A, code, stage + (size_t)t * REC);
+    // ---- level 1: the slice header (same address for every thread: one sector, broadcast)
+    const int4* hp = reinterpret_cast<const int4*>(A.hdr + blockIdx.x);
+    const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2);
+    const int64_t p0 = (int64_t)(uint32_t)h0.x | ((int64_t)h0.y << 32);
+    const int64_t base = (int64_t)(uint32_t)h0.z | ((int64_t)h0.w << 32);
+    const int np = h1.x, width = h1.y;
+    const uint32_t cbase = (uint32_t)(p0 * NPE);
+    const int nscp = width * C + 1;
+    auto row_off = [&](int l) -> int {
+        const uint32_t w = l < 2 ? (uint32_t)h1.z : l < 4 ? (uint32_t)h1.w : l < 6 ? (uint32_t)h2.x : l < 8 ? (uint32_t)h2.y : (uint32_t)h2.z;
+        return (int)((w >> (16 * (l & 1))) & 0xffffu);
+    };
+
+    // ---- level 2 (independent loads, issued together): pair records, contribution codes, slot ranges
+    using NodeVec = typename std::conditional<FAMILY == 0, int4, int2>::type;
+    using CodeVec = typename std::conditional<FAMILY == 0, uint2, uint32_t>::type;  // NPE u16 codes of "pair t's chunk"
+    const NodeVec* pn = reinterpret_cast<const NodeVec*>(A.pair_nodes) + p0;
+    const CodeVec* cc = reinterpret_cast<const CodeVec*>(A.ccode + cbase);
+    int t = tid;
+    NodeVec nodes = NodeVec();
+    CodeVec chunk = CodeVec();
+    int32_t code = 0;
+    if (t < np) {
+        nodes = __ldg(pn + t);
+        code = __ldg(A.pair_code + p0 + t);
+        chunk = __ldg(cc + t);
+    }
+    for (int i = tid; i < nscp; i += nth) scp[i] = (uint16_t)(__ldg(A.cptr + base * C + i) - cbase);
+
+    // ---- phase A
+    while (t < np) {
+        reinterpret_cast<CodeVec*>(scode)[t] = chunk;
+        if constexpr (FAMILY == 0)
+            tet_pair<KIND>(A, nodes, code, stage + (size_t)t * REC);
         else
-            truss_pair<DIM>(A, code, stage + (size_t)t * REC);
+            truss_pair<DIM>(A, nodes, code, stage + (size_t)t * REC);
+        t += nth;
+        if (t < np) {  // slices with more pairs than threads (high-valence meshes)
+            nodes = __ldg(pn + t);
+            code = __ldg(A.pair_code + p0 + t);
+            chunk = __ldg(cc + t);
+        }
     }
     __syncthreads();
 
-    const int64_t base = A.slice_ptr[sl];
-    const int width = (int)(A.slice_ptr[sl + 1] - base);
-    const int nK = width * BB * C;
+    // ---- phase B
+    const int nK = width * DIM * C;
     const int nF = C * DIM;
-    for (int w = threadIdx.x; w < nK + nF; w += blockDim.x) {
+    double* const vout = A.val + base * BB * C;
+    for (int w = tid; w < nK + nF; w += nth) {
         if (w < nK) {
             const int lane = w % C;
-            const int k = (w / C) % BB;
-            const int s = w / (C * BB);
-            const int64_t gs = (base + s) * C + lane;
-            const uint32_t q0 = __ldg(A.cptr + gs), q1 = __ldg(A.cptr + gs + 1);
-            double acc = 0.0;
-            for (uint32_t q = q0; q < q1; ++q) {
-                const int cc = __ldg(A.ccode + q);
-                acc += stage[(cc >> SHIFT) * REC + (cc & 3) * BB + k];
+            const int r = (w / C) % DIM;
+            const int s = w / (C * DIM);
+            const int slot = s * C + lane;
+            const int q0 = scp[slot], q1 = scp[slot + 1];
+            double acc[DIM];
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) acc[j] = 0.0;
+            for (int q = q0; q < q1; ++q) {
+                const double* src = stage + scode[q] + r * DIM;
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) acc[j] += src[j];
             }
-            const int64_t idx = base * BB * C + w;
-            if (ACCUM) acc += A.val[idx];
-            A.val[idx] = acc;
+            double* dst = vout + ((size_t)s * BB + r * DIM) * C + lane;
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) {
+                if (ACCUM) acc[j] += dst[j * C];
+                dst[j * C] = acc[j];
+            }
         } else {
             const int j = w - nK;
             const int lane = j / DIM, r = j % DIM;
-            const int64_t row = r0 + lane;
-            if (row < r1) {
-                const int t0 = (int)(A.pair_ptr[row] - p0), t1 = (int)(A.pair_ptr[row + 1] - p0);
+            const int t0 = row_off(lane), t1 = row_off(lane + 1);
+            const int64_t row = (int64_t)blockIdx.x * C + lane;
+            if (t1 > t0 || !ACCUM) {
                 double acc = 0.0;
-                for (int t = t0; t < t1; ++t) acc += stage[t * REC + FOFF + r];
-                if (ACCUM) acc += A.F_int[row * DIM + r];
-                A.F_int[row * DIM + r] = acc;
+                for (int tt = t0; tt < t1; ++tt) acc += stage[tt * REC + FOFF + r];
+                if (row < A.n_rows_guard) {
+                    if (ACCUM) acc += A.F_int[row * DIM + r];
+                    A.F_int[row * DIM + r] = acc;
+                }
             }
         }
     }
+}
+
+// Register-budget variants of the same body (ONSAS_OPT_ASM_MINBLOCKS): launch bounds (256,1) / (256,2), or an
+// explicit cap of 112 registers = 3 resident CTAs of 192 threads (the structured-mesh slice size).
+template <int FAMILY, int KIND, int DIM, bool ACCUM, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_assemble(AsmArgs A) {
+    assemble_body<FAMILY, KIND, DIM, ACCUM>(A);
+}
+template <int FAMILY, int KIND, int DIM, bool ACCUM, int REGS>
+__global__ void __maxnreg__(REGS) k_assemble_reg(AsmArgs A) {
+    assemble_body<FAMILY, KIND, DIM, ACCUM>(A);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -336,6 +396,7 @@ struct CgArgs {
     double* partials;   // [P_COUNT][part_stride]
     int part_stride;
     CgState* st;
+    long long* prof;    // optional [8]: SM-clock cycles block 0 spent per phase of the persistent kernel (diagnostics)
 };
 
 // fixed-order block reduction; result valid in every thread
@@ -370,38 +431,37 @@ __device__ __forceinline__ double diag_entry(const CgArgs& A, int64_t i) {
     return A.val[((base + s) * BS * BS + c * BS + c) * C + (row % C)];
 }
 
-// y = (M K M p)[row]; returns p[row] . y
+// One scalar row of y = M K M p.  Work item t = (slice, block-row component r, lane): the 8 lanes of a
+// (slice, r) group read one 64-byte segment of K per (block, q) -- full sectors -- and the 3 components
+// of a node sit in consecutive groups, so a warp covers 32 scalar rows of at most 2 slices.
+// Returns p[i] * y[i] (0 for padded rows).
 template <int BS>
-__device__ __forceinline__ double spmv_row(const CgArgs& A, int64_t row) {
-    const int64_t sl = row / C;
-    const int lane = (int)(row % C);
+__device__ __forceinline__ double spmv_item(const CgArgs& A, int64_t t) {
+    const int64_t sl = t / (C * BS);
+    const int r = (int)((t / C) % BS);
+    const int lane = (int)(t % C);
+    const int64_t row = sl * C + lane;
+    if (row >= A.n_rows) return 0.0;
     const int64_t base = A.slice_ptr[sl];
     const int width = (int)(A.slice_ptr[sl + 1] - base);
-    double acc[BS];
-#pragma unroll
-    for (int r = 0; r < BS; ++r) acc[r] = 0.0;
     const int32_t* cp = A.col + base * C + lane;
-    const double* vp = A.val + base * BS * BS * C + lane;
-#pragma unroll 2
+    const double* vp = A.val + (base * BS * BS + r * BS) * C + lane;
+    double acc = 0.0;
+#pragma unroll 4
     for (int s = 0; s < width; ++s) {
         const int64_t cnode = __ldg(cp + (int64_t)s * C);
-        double xv[BS];
 #pragma unroll
-        for (int q = 0; q < BS; ++q) xv[q] = A.p[cnode * BS + q];
-#pragma unroll
-        for (int r = 0; r < BS; ++r)
-#pragma unroll
-            for (int q = 0; q < BS; ++q) acc[r] += __ldcs(vp + ((int64_t)s * BS * BS + r * BS + q) * C) * xv[q];
+        for (int q = 0; q < BS; ++q) acc += __ldcs(vp + ((int64_t)s * BS * BS + q) * C) * A.p[cnode * BS + q];
     }
-    double d = 0.0;
-#pragma unroll
-    for (int r = 0; r < BS; ++r) {
-        const int64_t i = row * BS + r;
-        const double y = A.mask[i] ? acc[r] : 0.0;
-        A.Ap[i] = y;
-        d += A.p[i] * y;
-    }
-    return d;
+    const int64_t i = row * BS + r;
+    const double y = A.mask[i] ? acc : 0.0;
+    A.Ap[i] = y;
+    return A.p[i] * y;
+}
+
+template <int BS>
+__device__ __forceinline__ int64_t spmv_items(const CgArgs& A) {
+    return ((A.n_rows + C - 1) / C) * (int64_t)(C * BS);
 }
 
 // ---- phase bodies shared by the persistent and the multi-launch drivers (grid-stride)
@@ -457,8 +517,8 @@ constexpr int CG_THREADS = 256;
 // residual r = (F_ext - F_int)[free] (StaticStates.jl:113-116), PCG exactly as IterativeSolvers'
 // (P)CGIterable runs it (tolerance = max(reltol*||r0||, abstol), stop when ||r|| <= tol or
 // it >= maxiter), then dU norms and U[free] += dU (NonLinearStaticAnalyses.jl:136-144).
-template <int BS>
-__global__ void __launch_bounds__(CG_THREADS) cg_persistent(CgArgs A) {
+template <int BS, bool PROF, int MINB>
+__global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[CG_THREADS / 32];
     const int64_t gtid = blockIdx.x * (int64_t)CG_THREADS + threadIdx.x;
@@ -484,15 +544,30 @@ __global__ void __launch_bounds__(CG_THREADS) cg_persistent(CgArgs A) {
     double rho_prev = 1.0;
     long long it = 0;
 
+    const bool profiling = PROF && A.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tprev = profiling ? clock64() : 0;
+    long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};
+#define CG_PROF(k)                         \
+    if constexpr (PROF) {                  \
+        if (profiling) {                   \
+            const long long tn = clock64(); \
+            tacc[k] += tn - tprev;         \
+            tprev = tn;                    \
+        }                                  \
+    }
     while (!(it >= A.maxiter || res <= tol)) {
         const double beta = rho / rho_prev;
         cg_update_p_body(A, gtid, gsz, beta);
+        CG_PROF(0)
         grid.sync();
+        CG_PROF(1)
         double d = 0.0;
-        for (int64_t row = gtid; row < A.n_rows; row += gsz) d += spmv_row<BS>(A, row);
+        for (int64_t t = gtid, nt = spmv_items<BS>(A); t < nt; t += gsz) d += spmv_item<BS>(A, t);
         d = block_sum<CG_THREADS>(d, sh);
         if (threadIdx.x == 0) part[P_PAP * ps + blockIdx.x] = d;
+        CG_PROF(2)
         grid.sync();
+        CG_PROF(3)
         const double pAp = sum_partials<CG_THREADS>(part + P_PAP * ps, nb, sh);
         const double alpha = rho / pAp;
         double s2[2];
@@ -503,12 +578,20 @@ __global__ void __launch_bounds__(CG_THREADS) cg_persistent(CgArgs A) {
             part[P_RR * ps + blockIdx.x] = b0;
             part[P_RZ * ps + blockIdx.x] = b1;
         }
+        CG_PROF(4)
         grid.sync();
+        CG_PROF(5)
         const double rr = sum_partials<CG_THREADS>(part + P_RR * ps, nb, sh);
         rho_prev = rho;
         rho = sum_partials<CG_THREADS>(part + P_RZ * ps, nb, sh);
         res = sqrt(rr);
         ++it;
+        CG_PROF(6)
+    }
+#undef CG_PROF
+    if constexpr (PROF) {
+        if (profiling)
+            for (int k = 0; k < 7; ++k) A.prof[k] = tacc[k];
     }
 
     double dd = cg_epilogue_body(A, gtid, gsz);
@@ -590,7 +673,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_spmv_dot(CgArgs A, int gate) {
     const int64_t gtid = blockIdx.x * (int64_t)CG_THREADS + threadIdx.x;
     const int64_t gsz = gridDim.x * (int64_t)CG_THREADS;
     double d = 0.0;
-    for (int64_t row = gtid; row < A.n_rows; row += gsz) d += spmv_row<BS>(A, row);
+    for (int64_t t = gtid, nt = spmv_items<BS>(A); t < nt; t += gsz) d += spmv_item<BS>(A, t);
     d = block_sum<CG_THREADS>(d, sh);
     if (threadIdx.x == 0) A.partials[P_PAP * A.part_stride + blockIdx.x] = d;
 }

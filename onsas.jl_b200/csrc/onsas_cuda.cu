@@ -137,14 +137,17 @@ struct onsas_ctx {
 
     // device
     DevBuf<double> X, U, Fext, Fint, val, x, r, p, Ap, dinv, rhs, partials, red, tet_out, truss_out, area, mat_params;
-    DevBuf<int32_t> tets, tet_mat, trusses, truss_mat, mat_kind, col, diag_slot, pair_code[2], send_nodes;
-    DevBuf<int64_t> slice_ptr, pair_ptr[2];
+    DevBuf<int32_t> tets, tet_mat, trusses, truss_mat, mat_kind, col, diag_slot, pair_code[2], pair_nodes[2], send_nodes;
+    DevBuf<int64_t> slice_ptr;
+    DevBuf<SliceHdr> hdr[2];
     DevBuf<uint32_t> cptr[2];
     DevBuf<uint16_t> ccode[2];
     DevBuf<uint8_t> mask;
     DevBuf<int> err_flag;
     DevBuf<CgState> st;
     DevBuf<double> sendbuf;
+    DevBuf<long long> prof;
+    int cg_profile = 0;
     CgState* h_st = nullptr;  // pinned
     int* h_flag = nullptr;    // pinned
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -207,30 +210,43 @@ void launch_asm_inst(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
     CUDA_CHECK(cudaGetLastError());
 }
 
+template <int FAMILY, int KIND, int DIM, bool ACCUM, int REGS>
+void launch_asm_reg(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
+    auto kern = k_assemble_reg<FAMILY, KIND, DIM, ACCUM, REGS>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    kern<<<(unsigned)c->tab.n_slices, threads, smem, c->stream>>>(A);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 template <int KIND>
 void launch_asm_tets_kind(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
-    // register budget variants: 1 -> unconstrained, 2 -> 128 regs (2 CTAs of 256), 3 -> 112 regs (3 CTAs of 192)
+    // register budget variants: 1 -> unconstrained, 2 -> 128 regs (launch bounds 256 x 2), 3 -> 112 regs (3 CTAs of 192)
     if (c->asm_minb == 1) launch_asm_inst<0, KIND, 3, false, 256, 1>(c, A, threads, smem);
-    else if (c->asm_minb == 3 && threads <= 192) launch_asm_inst<0, KIND, 3, false, 192, 3>(c, A, threads, smem);
+    else if (c->asm_minb == 3 && threads <= 192) launch_asm_reg<0, KIND, 3, false, 112>(c, A, threads, smem);
     else launch_asm_inst<0, KIND, 3, false, 256, 2>(c, A, threads, smem);
 }
 
 AsmArgs make_asm_args(onsas_ctx* c, int family) {
     AsmArgs A{};
-    A.n_rows = c->n_owned;
+    A.n_rows_guard = c->n_owned;
     A.X = c->X.p;
     A.U = c->U.p;
-    A.conn = family == 0 ? c->tets.p : c->trusses.p;
+    A.hdr = c->hdr[family].p;
+    A.pair_nodes = c->pair_nodes[family].p;
+    A.max_pairs = std::max(c->tab.fam[family].max_pairs_per_slice, 1);
+    A.max_width = std::max(c->tab.max_width, 1);
     A.mat_id = family == 0 ? (c->tet_has_mat ? c->tet_mat.p : nullptr) : (c->truss_has_mat ? c->truss_mat.p : nullptr);
     A.mat_kind = c->mat_kind.p;
     A.mat_params = c->mat_params.p;
     A.area = c->area.p;
     A.strain_model = c->strain_model;
-    A.pair_ptr = c->pair_ptr[family].p;
     A.pair_code = c->pair_code[family].p;
     A.cptr = c->cptr[family].p;
     A.ccode = c->ccode[family].p;
-    A.slice_ptr = c->slice_ptr.p;
     A.val = c->val.p;
     A.F_int = c->Fint.p;
     A.elem_out = family == 0 ? c->tet_out.p : c->truss_out.p;
@@ -253,7 +269,7 @@ void launch_assemble(onsas_ctx* c) {
         AsmArgs A = make_asm_args(c, 0);
         const int mp = c->tab.fam[0].max_pairs_per_slice;
         const int threads = round_threads(mp);
-        const size_t smem = (size_t)std::max(mp, 1) * TET_REC * sizeof(double);
+        const size_t smem = asm_smem_bytes(A.max_pairs, A.max_width, TET_REC, 4);
         switch (c->tet_kind) {
             case MAT_SVK: launch_asm_tets_kind<MAT_SVK>(c, A, threads, smem); break;
             case MAT_NEOHOOKEAN: launch_asm_tets_kind<MAT_NEOHOOKEAN>(c, A, threads, smem); break;
@@ -266,7 +282,7 @@ void launch_assemble(onsas_ctx* c) {
         AsmArgs A = make_asm_args(c, 1);
         const int mp = c->tab.fam[1].max_pairs_per_slice;
         const int threads = round_threads(mp);
-        const size_t smem = (size_t)std::max(mp, 1) * truss_rec(c->dim) * sizeof(double);
+        const size_t smem = asm_smem_bytes(A.max_pairs, A.max_width, truss_rec(c->dim), 2);
         if (wrote) {
             if (c->dim == 3) launch_asm_inst<1, 0, 3, true, 256, 2>(c, A, threads, smem);
             else if (c->dim == 2) launch_asm_inst<1, 0, 2, true, 256, 2>(c, A, threads, smem);
@@ -335,15 +351,31 @@ CgArgs make_cg_args(onsas_ctx* c, int precond, double reltol, double abstol, int
     A.partials = c->partials.p;
     A.part_stride = c->part_stride;
     A.st = c->st.p;
+    A.prof = c->cg_profile ? c->prof.p : nullptr;
     return A;
+}
+
+// grid of the stand-alone SpMV: one thread per scalar row of the padded slices, capped to the partial-sum stride
+int spmv_grid(onsas_ctx* c) {
+    const int64_t items = c->tab.n_slices * (int64_t)(SLICE_ROWS * c->dim);
+    return (int)std::max<int64_t>(1, std::min<int64_t>((items + CG_THREADS - 1) / CG_THREADS, (int64_t)c->part_stride));
+}
+
+// The persistent CG kernel is compiled for 4, 5 or 6 resident CTAs per SM (64 / 48 / 40 registers);
+// ONSAS_OPT_CG_BLOCKS_PER_SM picks the variant (default 4).
+template <int BS>
+void* persistent_kernel(onsas_ctx* c) {
+    const int v = c->cg_bps >= 6 ? 6 : c->cg_bps == 5 ? 5 : 4;
+    if (c->cg_profile) return v == 6 ? (void*)cg_persistent<BS, true, 6> : v == 5 ? (void*)cg_persistent<BS, true, 5> : (void*)cg_persistent<BS, true, 4>;
+    return v == 6 ? (void*)cg_persistent<BS, false, 6> : v == 5 ? (void*)cg_persistent<BS, false, 5> : (void*)cg_persistent<BS, false, 4>;
 }
 
 template <int BS>
 int persistent_grid(onsas_ctx* c) {
     int bps = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, cg_persistent<BS>, CG_THREADS, 0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, persistent_kernel<BS>(c), CG_THREADS, 0));
     require(bps > 0, ONSAS_ERR_CUDA, "persistent CG kernel does not fit on an SM");
-    if (c->cg_bps > 0) bps = std::min(bps, c->cg_bps);
+    if (c->cg_bps > 0 && c->cg_bps < 4) bps = std::min(bps, c->cg_bps);
     int g = bps * c->n_sm;
     return std::min(g, c->part_stride);
 }
@@ -354,12 +386,12 @@ void run_cg_bs(onsas_ctx* c, CgArgs A) {
     if (c->cg_mode == 0 && c->n_ranks == 1) {
         if (c->cg_grid == 0) c->cg_grid = persistent_grid<BS>(c);
         void* args[] = {&A};
-        CUDA_CHECK(cudaLaunchCooperativeKernel((void*)cg_persistent<BS>, dim3(c->cg_grid), dim3(CG_THREADS), args, 0, c->stream));
+        CUDA_CHECK(cudaLaunchCooperativeKernel(persistent_kernel<BS>(c), dim3(c->cg_grid), dim3(CG_THREADS), args, 0, c->stream));
         return;
     }
     // one launch per phase; collectives in-stream between them
     const int G = (int)std::max<int64_t>(1, std::min<int64_t>((n + CG_THREADS - 1) / CG_THREADS, (int64_t)c->n_sm * 8));
-    const int Gr = (int)std::max<int64_t>(1, std::min<int64_t>((A.n_rows + CG_THREADS - 1) / CG_THREADS, (int64_t)c->n_sm * 8));
+    const int Gr = spmv_grid(c);
     cudaStream_t s = c->stream;
     double* red = c->red.p;
     k_cg_prologue<BS><<<G, CG_THREADS, 0, s>>>(A);
@@ -476,6 +508,8 @@ int32_t onsas_create(int32_t device, onsas_ctx** out) {
         c->partials.zero(c->stream);
         c->red.alloc(8);
         c->red.zero(c->stream);
+        c->prof.alloc(8);
+        c->prof.zero(c->stream);
     });
     if (st != ONSAS_OK) {
         delete c;
@@ -514,6 +548,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_CG_MODE: require(value == 0 || value == 1, ONSAS_ERR_INVALID_ARG, "cg mode must be 0 or 1"); c->cg_mode = (int)value; break;
             case ONSAS_OPT_ASM_MINBLOCKS: require(value >= 1 && value <= 3, ONSAS_ERR_INVALID_ARG, "min blocks must be 1..3"); c->asm_minb = (int)value; break;
             case ONSAS_OPT_CG_CHECK_EVERY: require(value >= 1 && value <= 4096, ONSAS_ERR_INVALID_ARG, "check_every out of range"); c->check_every = (int)value; break;
+            case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
         }
@@ -660,8 +695,8 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
             if (bad) throw OnsasError(ONSAS_ERR_NEGATIVE_VOLUME, "Element with negative volume, check connectivity.");
         }
         const size_t max_smem = 227 * 1024;
-        require((size_t)c->tab.fam[0].max_pairs_per_slice * TET_REC * 8 <= max_smem &&
-                    (size_t)c->tab.fam[1].max_pairs_per_slice * truss_rec(c->dim) * 8 <= max_smem,
+        require(asm_smem_bytes(std::max(c->tab.fam[0].max_pairs_per_slice, 1), std::max(c->tab.max_width, 1), TET_REC, 4) <= max_smem &&
+                    asm_smem_bytes(std::max(c->tab.fam[1].max_pairs_per_slice, 1), std::max(c->tab.max_width, 1), truss_rec(c->dim), 2) <= max_smem,
                 ONSAS_ERR_UNSUPPORTED, "node valence too high: a slice of 8 nodes has more element pairs than fit in shared memory");
 
         // diagonal block position per row
@@ -689,8 +724,9 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->col.upload(c->tab.col, s);
         c->diag_slot.upload(dslot, s);
         for (int f = 0; f < 2; ++f) {
-            c->pair_ptr[f].upload(c->tab.fam[f].pair_ptr, s);
             c->pair_code[f].upload(c->tab.fam[f].pair_code, s);
+            c->pair_nodes[f].upload(c->tab.fam[f].pair_nodes, s);
+            c->hdr[f].upload(c->tab.fam[f].hdr, s);
             c->cptr[f].upload(c->tab.fam[f].cptr, s);
             c->ccode[f].upload(c->tab.fam[f].ccode, s);
         }
@@ -855,7 +891,7 @@ int32_t onsas_spmv(onsas_ctx* c, const double* x, double* y) {
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         CUDA_CHECK(cudaMemcpyAsync(c->p.p, x, c->n_local_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CgArgs A = make_cg_args(c, 0, 0, 0, 1, false, 0);
-        const int Gr = (int)std::max<int64_t>(1, std::min<int64_t>((A.n_rows + CG_THREADS - 1) / CG_THREADS, (int64_t)c->n_sm * 8));
+        const int Gr = spmv_grid(c);
         if (c->n_ranks > 1) halo_exchange(c, A.p, 0);
         switch (c->dim) {
             case 1: k_spmv_dot<1><<<Gr, CG_THREADS, 0, c->stream>>>(A, 0); break;
@@ -874,7 +910,7 @@ int32_t onsas_spmv_resident(onsas_ctx* c) {
     return guard(c, [&] {
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         CgArgs A = make_cg_args(c, 0, 0, 0, 1, false, 0);
-        const int Gr = (int)std::max<int64_t>(1, std::min<int64_t>((A.n_rows + CG_THREADS - 1) / CG_THREADS, (int64_t)c->n_sm * 8));
+        const int Gr = spmv_grid(c);
         switch (c->dim) {
             case 1: k_spmv_dot<1><<<Gr, CG_THREADS, 0, c->stream>>>(A, 0); break;
             case 2: k_spmv_dot<2><<<Gr, CG_THREADS, 0, c->stream>>>(A, 0); break;
@@ -944,6 +980,16 @@ int32_t onsas_get_stress_strain(onsas_ctx* c, int32_t family, double* sig, doubl
                 eps[9 * e] = h[2 * e + 1];
             }
         }
+    });
+}
+
+int32_t onsas_get_cg_profile(onsas_ctx* c, int64_t out[8]) {
+    if (!c || !out) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        long long h[8];
+        CUDA_CHECK(cudaMemcpy(h, c->prof.p, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 8; ++k) out[k] = h[k];
     });
 }
 

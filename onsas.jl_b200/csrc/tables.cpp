@@ -45,6 +45,7 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
     for (int f = 0; f < 2; ++f) {
         FamilyTables& F = t.fam[f];
         F.npe = npe[f];
+        F.rec = f == 0 ? TET_REC : truss_rec(dim);
         F.n_elem = ne[f];
         F.pair_ptr.assign(n_rows + 1, 0);
         if (ne[f] == 0) continue;
@@ -60,6 +61,12 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
         for (int64_t q = 0; q < ne[f] * npe[f]; ++q) {
             int32_t nd = conn[f][q];
             if (nd < n_rows) F.pair_code[fill[nd]++] = (int32_t)q;  // q = e*npe + a
+        }
+        F.pair_nodes.resize(F.pair_code.size() * (size_t)npe[f]);
+#pragma omp parallel for schedule(static)
+        for (int64_t p = 0; p < (int64_t)F.pair_code.size(); ++p) {
+            const int64_t e = F.pair_code[p] / npe[f];
+            for (int b = 0; b < npe[f]; ++b) F.pair_nodes[p * npe[f] + b] = conn[f][e * npe[f] + b];
         }
     }
 
@@ -85,6 +92,7 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
             }
         }
         t.slice_ptr[sl + 1] = t.slice_ptr[sl] + w;
+        t.max_width = std::max(t.max_width, w);
     }
     if (t.slice_ptr[t.n_slices] * C * (int64_t)dim * dim > (int64_t)0x7fffffff * 8) return "matrix too large";
     t.col.assign((size_t)t.slice_ptr[t.n_slices] * C, 0);
@@ -115,6 +123,8 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
         if (n_contrib >= (int64_t)0xffffffffu) return "too many contributions for 32-bit offsets";
         F.cptr.assign(n_slots + 1, 0);
         F.ccode.assign(n_contrib, 0);
+        F.hdr.assign(t.n_slices, SliceHdr());
+        const int BB = dim * dim;
         int32_t max_pairs = 0;
         bool overflow = false;
 #pragma omp parallel for schedule(static) reduction(max : max_pairs) reduction(|| : overflow)
@@ -125,10 +135,16 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
             int w = (int)(t.slice_ptr[sl + 1] - base);
             int32_t np = (int32_t)(p1 - p0);
             max_pairs = std::max(max_pairs, np);
-            if ((int64_t)np * 4 > 65535) {
+            if ((int64_t)np * F.rec > 65535) {  // contribution codes are 16-bit shared-memory offsets
                 overflow = true;
                 continue;
             }
+            SliceHdr& H = F.hdr[sl];
+            H.pair_base = p0;
+            H.slot_base = base;
+            H.n_pairs = np;
+            H.width = w;
+            for (int l = 0; l <= C; ++l) H.row_off[l] = (uint16_t)(F.pair_ptr[std::min<int64_t>(r0 + l, r1)] - p0);
             std::vector<uint32_t> cnt((size_t)w * C + 1, 0);
             std::vector<uint16_t> slot_of((size_t)np * F.npe);
             for (int64_t i = r0; i < r1; ++i) {
@@ -164,7 +180,7 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
             for (int32_t lp = 0; lp < np; ++lp)
                 for (int b = 0; b < F.npe; ++b) {
                     uint16_t slot = slot_of[(size_t)lp * F.npe + b];
-                    F.ccode[gbase + fill[slot]++] = (uint16_t)(lp * 4 + b);
+                    F.ccode[gbase + fill[slot]++] = (uint16_t)(lp * F.rec + b * BB);
                 }
         }
         if (overflow) return "too many element pairs in one 8-row slice (node valence too high)";

@@ -24,14 +24,30 @@
 namespace onsas {
 
 constexpr int SLICE_ROWS = 8;
+constexpr int TET_REC = 39;  // shared-memory record of one (row, tet) pair: 4 blocks * 9 + 3 force entries (odd stride)
+constexpr inline int truss_rec(int dim) { return (2 * dim * dim + dim) | 1; }
+
+// Everything a CTA needs to know about its slice, fetched with one 48-byte read.
+struct alignas(16) SliceHdr {
+    int64_t pair_base;                  // first pair of the slice in pair_nodes / pair_code
+    int64_t slot_base;                  // slice_ptr[sl]: first block column of the slice
+    int32_t n_pairs;
+    int32_t width;                      // blocks per row of the slice (padded)
+    uint16_t row_off[SLICE_ROWS + 1];   // pair range of each row, relative to pair_base
+    uint16_t pad[3];
+};
+static_assert(sizeof(SliceHdr) == 48, "SliceHdr must be 48 bytes");
 
 struct FamilyTables {
     int npe = 0;                     // nodes per element (4 tets, 2 trusses)
+    int rec = 0;                     // doubles per pair record in shared memory
     int64_t n_elem = 0;
     std::vector<int64_t> pair_ptr;   // [n_rows+1] pairs of row i
     std::vector<int32_t> pair_code;  // [n_pairs] e*npe + a, ascending e within a row
+    std::vector<int32_t> pair_nodes; // [n_pairs*npe] the element's node ids, copied next to the pair (one load level less)
+    std::vector<SliceHdr> hdr;       // [n_slices]
     std::vector<uint32_t> cptr;      // [n_slots+1] contribution ranges per block slot (slot = slice_ptr*C + s*C + lane)
-    std::vector<uint16_t> ccode;     // [n_pairs*npe] (pair index local to the slice)*4 + b
+    std::vector<uint16_t> ccode;     // [n_pairs*npe] shared-memory offset of the contributing block: local_pair*rec + b*dim*dim
     int32_t max_pairs_per_slice = 0;
 };
 
@@ -40,6 +56,7 @@ struct MeshTables {
     int64_t n_nodes = 0;  // local nodes (owned + halo)
     int64_t n_rows = 0;   // owned nodes = block rows of K
     int64_t n_slices = 0;
+    int32_t max_width = 0;           // widest slice (blocks per row)
     std::vector<int64_t> slice_ptr;  // [n_slices+1]
     std::vector<int32_t> col;        // [slice_ptr.back()*C]
     std::vector<int32_t> row_nblk;   // [n_rows] true number of blocks per row

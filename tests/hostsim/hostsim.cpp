@@ -19,8 +19,6 @@ using namespace onsas;
 
 namespace {
 constexpr int C = SLICE_ROWS;
-constexpr int TET_REC = 39;
-int truss_rec(int dim) { return (2 * dim * dim + dim) | 1; }
 
 template <int K>
 void tet_pair_k(const double X[4][3], const double U[4][3], double p0, double p1, int a, double* rec, double* out16) {
@@ -161,13 +159,21 @@ int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const i
         const int FOFF = fam == 0 ? 36 : 2 * BB;
         const bool ACCUM = wrote;
         std::vector<double> stage((size_t)std::max(F.max_pairs_per_slice, 1) * REC);
+        const int NPE = F.npe;
+        std::vector<uint16_t> scode((size_t)std::max(F.max_pairs_per_slice, 1) * NPE), scp((size_t)t.max_width * C + 1);
         for (int64_t sl = 0; sl < t.n_slices; ++sl) {  // one CTA per slice
-            const int64_t r0 = sl * C, r1 = std::min<int64_t>(r0 + C, t.n_rows);
-            const int64_t p0 = F.pair_ptr[r0];
-            const int np = (int)(F.pair_ptr[r1] - p0);
+            const SliceHdr& H = F.hdr[sl];
+            const int64_t p0 = H.pair_base, base = H.slot_base;
+            const int np = H.n_pairs, width = H.width;
+            const uint32_t cbase = (uint32_t)(p0 * NPE);
+            const int nscp = width * C + 1;
+            for (int tid = 0; tid < threads; ++tid)  // level-2 staging of the slot ranges
+                for (int i = tid; i < nscp; i += threads) scp[i] = (uint16_t)(F.cptr[base * C + i] - cbase);
             for (int tid = 0; tid < threads; ++tid)  // phase A
                 for (int tt = tid; tt < np; tt += threads) {
+                    for (int b = 0; b < NPE; ++b) scode[(size_t)tt * NPE + b] = F.ccode[cbase + (size_t)tt * NPE + b];
                     const int32_t code = F.pair_code[p0 + tt];
+                    const int32_t* nd = &F.pair_nodes[(p0 + tt) * NPE];
                     double* rec = stage.data() + (size_t)tt * REC;
                     if (fam == 0) {
                         const int64_t e = code >> 2;
@@ -175,8 +181,8 @@ int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const i
                         double X[4][3], U[4][3];
                         for (int k = 0; k < 4; ++k)
                             for (int c = 0; c < 3; ++c) {
-                                X[k][c] = xyz[3 * (int64_t)tets[4 * e + k] + c];
-                                U[k][c] = Uv[3 * (int64_t)tets[4 * e + k] + c];
+                                X[k][c] = xyz[3 * (int64_t)nd[k] + c];
+                                U[k][c] = Uv[3 * (int64_t)nd[k] + c];
                             }
                         const int mm = tet_mat ? tet_mat[e] : 0;
                         tet_pair(kind[mm], X, U, params[2 * mm], params[2 * mm + 1], a, rec,
@@ -187,8 +193,8 @@ int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const i
                         double X[2][3] = {{0}}, U[2][3] = {{0}};
                         for (int k = 0; k < 2; ++k)
                             for (int c = 0; c < dim; ++c) {
-                                X[k][c] = xyz[dim * (int64_t)trusses[2 * e + k] + c];
-                                U[k][c] = Uv[dim * (int64_t)trusses[2 * e + k] + c];
+                                X[k][c] = xyz[dim * (int64_t)nd[k] + c];
+                                U[k][c] = Uv[dim * (int64_t)nd[k] + c];
                             }
                         const int mm = truss_mat ? truss_mat[e] : 0;
                         const double Emod = truss_modulus(kind[mm], params[2 * mm], params[2 * mm + 1]);
@@ -202,32 +208,33 @@ int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const i
                         }
                     }
                 }
-            // phase B
-            const int64_t base = t.slice_ptr[sl];
-            const int width = (int)(t.slice_ptr[sl + 1] - base);
-            const int nK = width * BB * C, nF = C * dim;
+            // phase B: one item per (slot, block row r)
+            const int nK = width * dim * C, nF = C * dim;
+            double* vout = m->val.data() + base * BB * C;
             for (int tid = 0; tid < threads; ++tid)
                 for (int w = tid; w < nK + nF; w += threads) {
                     if (w < nK) {
-                        const int lane = w % C, k = (w / C) % BB, s = w / (C * BB);
-                        const int64_t gs = (base + s) * C + lane;
-                        double acc = 0.0;
-                        for (uint32_t q = F.cptr[gs]; q < F.cptr[gs + 1]; ++q) {
-                            const int cc = F.ccode[q];
-                            acc += stage[(size_t)(cc >> 2) * REC + (cc & 3) * BB + k];
+                        const int lane = w % C, r = (w / C) % dim, s = w / (C * dim);
+                        const int slot = s * C + lane;
+                        double acc[3] = {0, 0, 0};
+                        for (int q = scp[slot]; q < scp[slot + 1]; ++q)
+                            for (int j = 0; j < dim; ++j) acc[j] += stage[(size_t)scode[q] + r * dim + j];
+                        double* dst = vout + ((size_t)s * BB + r * dim) * C + lane;
+                        for (int j = 0; j < dim; ++j) {
+                            if (ACCUM) acc[j] += dst[j * C];
+                            dst[j * C] = acc[j];
                         }
-                        const int64_t idx = base * BB * C + w;
-                        if (ACCUM) acc += m->val[idx];
-                        m->val[idx] = acc;
                     } else {
                         const int j = w - nK, lane = j / dim, r = j % dim;
-                        const int64_t row = r0 + lane;
-                        if (row < r1) {
+                        const int t0 = H.row_off[lane], t1 = H.row_off[lane + 1];
+                        const int64_t row = sl * C + lane;
+                        if (t1 > t0 || !ACCUM) {
                             double acc = 0.0;
-                            for (int64_t tt = F.pair_ptr[row] - p0; tt < F.pair_ptr[row + 1] - p0; ++tt)
-                                acc += stage[(size_t)tt * REC + FOFF + r];
-                            if (ACCUM) acc += m->Fint[row * dim + r];
-                            m->Fint[row * dim + r] = acc;
+                            for (int tt = t0; tt < t1; ++tt) acc += stage[(size_t)tt * REC + FOFF + r];
+                            if (row < t.n_rows) {
+                                if (ACCUM) acc += m->Fint[row * dim + r];
+                                m->Fint[row * dim + r] = acc;
+                            }
                         }
                     }
                 }

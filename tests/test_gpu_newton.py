@@ -167,7 +167,7 @@ def test_million_tet_cube_size_independent_properties(ob):
     ctx.assemble()
     np.testing.assert_array_equal(ctx.get_Fint(), Fint)
     np.testing.assert_array_equal(ctx.spmv(x), Kx)
-    ctx.set_U(U + 1e-3 * rng.standard_normal(U.size) * mask)
+    ctx.set_U(U + 2e-5 * rng.standard_normal(U.size) * mask)   # ~1e-3 strain noise at h = 1/55
     for _ in range(4):
         info = ctx.newton_step(ob.PRECOND_JACOBI, 1e-10)
     assert np.abs(ctx.get_U() - U).max() < 1e-8 and info.norm_r / info.norm_Fext < 1e-8
