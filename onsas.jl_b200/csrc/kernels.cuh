@@ -130,7 +130,7 @@ __device__ __forceinline__ void truss_pair(const AsmArgs& A, const int2 cn, int3
 
 // shared memory of one assembly CTA: [stage: max_pairs*REC doubles][scode: max_pairs*NPE u16][scp: max_width*C+1 u16]
 __host__ __device__ constexpr size_t asm_smem_bytes(int max_pairs, int max_width, int rec, int npe) {
-    return (size_t)max_pairs * rec * 8 + (((size_t)max_pairs * npe * 2 + ((size_t)max_width * SLICE_ROWS + 1) * 2 + 15) / 16) * 16;
+    return ((size_t)max_pairs * rec + SLICE_ROWS) * 8 + (((size_t)max_pairs * npe * 2 + ((size_t)max_width * SLICE_ROWS + 1) * 2 + 15) / 16) * 16;
 }
 
 // One CTA per BSELL slice (8 block rows).
@@ -149,7 +149,7 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     constexpr int NPE = FAMILY == 0 ? 4 : 2;
     constexpr int REC = FAMILY == 0 ? TET_REC : truss_rec(DIM);
     constexpr int FOFF = NPE * BB;
-    uint16_t* scode = reinterpret_cast<uint16_t*>(stage + (size_t)A.max_pairs * REC);
+    uint16_t* scode = reinterpret_cast<uint16_t*>(stage + (size_t)A.max_pairs * REC + C);
     uint16_t* scp = scode + (size_t)A.max_pairs * NPE;
     const int tid = threadIdx.x, nth = blockDim.x;
 
@@ -180,15 +180,21 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
         code = __ldg(A.pair_code + p0 + t);
         chunk = __ldg(cc + t);
     }
-    for (int i = tid; i < nscp; i += nth) scp[i] = (uint16_t)(__ldg(A.cptr + base * C + i) - cbase);
+    uint32_t cp0 = 0;
+    if (tid < nscp) cp0 = __ldg(A.cptr + base * C + tid);
+    if (tid < nscp) scp[tid] = (uint16_t)(cp0 - cbase);
+    for (int i = tid + nth; i < nscp; i += nth) scp[i] = (uint16_t)(__ldg(A.cptr + base * C + i) - cbase);
 
     // ---- phase A
     while (t < np) {
         reinterpret_cast<CodeVec*>(scode)[t] = chunk;
+        int l = 0;  // row of this pair inside the slice: its record is skewed by l doubles (bank spreading)
+#pragma unroll
+        for (int k = 1; k < C; ++k) l += (t >= row_off(k)) ? 1 : 0;
         if constexpr (FAMILY == 0)
-            tet_pair<KIND>(A, nodes, code, stage + (size_t)t * REC);
+            tet_pair<KIND>(A, nodes, code, stage + (size_t)t * REC + l);
         else
-            truss_pair<DIM>(A, nodes, code, stage + (size_t)t * REC);
+            truss_pair<DIM>(A, nodes, code, stage + (size_t)t * REC + l);
         t += nth;
         if (t < np) {  // slices with more pairs than threads (high-valence meshes)
             nodes = __ldg(pn + t);
@@ -230,7 +236,7 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
             const int64_t row = (int64_t)blockIdx.x * C + lane;
             if (t1 > t0 || !ACCUM) {
                 double acc = 0.0;
-                for (int tt = t0; tt < t1; ++tt) acc += stage[tt * REC + FOFF + r];
+                for (int tt = t0; tt < t1; ++tt) acc += stage[tt * REC + lane + FOFF + r];
                 if (row < A.n_rows_guard) {
                     if (ACCUM) acc += A.F_int[row * DIM + r];
                     A.F_int[row * DIM + r] = acc;
@@ -241,7 +247,7 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
 }
 
 // Register-budget variants of the same body (ONSAS_OPT_ASM_MINBLOCKS): launch bounds (256,1) / (256,2), or an
-// explicit cap of 112 registers = 3 resident CTAs of 192 threads (the structured-mesh slice size).
+// explicit register cap (96 = 3 resident CTAs of 192 threads (the structured-mesh slice size).
 template <int FAMILY, int KIND, int DIM, bool ACCUM, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_assemble(AsmArgs A) {
     assemble_body<FAMILY, KIND, DIM, ACCUM>(A);

@@ -224,9 +224,9 @@ void launch_asm_reg(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
 
 template <int KIND>
 void launch_asm_tets_kind(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
-    // register budget variants: 1 -> unconstrained, 2 -> 128 regs (launch bounds 256 x 2), 3 -> 112 regs (3 CTAs of 192)
+    // register budget variants: 1 -> unconstrained, 2 -> 128 regs (launch bounds 256 x 2), 3 -> 96 regs (3 CTAs of 192: 18 warps need <= 102 regs each, the register file is split per SM sub-partition)
     if (c->asm_minb == 1) launch_asm_inst<0, KIND, 3, false, 256, 1>(c, A, threads, smem);
-    else if (c->asm_minb == 3 && threads <= 192) launch_asm_reg<0, KIND, 3, false, 112>(c, A, threads, smem);
+    else if (c->asm_minb == 3 && threads <= 192) launch_asm_reg<0, KIND, 3, false, 96>(c, A, threads, smem);
     else launch_asm_inst<0, KIND, 3, false, 256, 2>(c, A, threads, smem);
 }
 

@@ -1,0 +1,109 @@
+"""Multi-GPU parity check, run under torchrun (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 scripts/multi_gpu_check.py
+Every rank builds the same small global problem, keeps its RCB part, and the distributed assembly / SpMV / PCG /
+Newton solve are compared with the oracle on the global mesh (F_int, K rows, U within the north-star tolerances)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import onsas_jl_b200 as ob  # noqa: E402
+from onsas_jl_b200 import meshgen as mg  # noqa: E402
+from onsas_jl_b200 import partition as pt  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from tests import cases  # noqa: E402
+
+
+def make_ctx(part, kind, params, rank, world, local_rank):
+    ctx = ob.DeviceContext(local_rank)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(ob.DeviceContext.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    ctx.set_nodes(part.xyz, part.n_owned)
+    ctx.set_materials(kind, params)
+    ctx.set_tets(part.tets)
+    ctx.set_free_dofs(part.free_dofs, part.n_free_global)
+    ctx.set_halo(part.nbr_rank, part.send_ptr, part.send_nodes, part.recv_ptr)
+    ctx.finalize()
+    return ctx
+
+
+def main():
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    m, mesh = cases.box_model(12, 6, 6, mat="neo", jitter=0.1)
+    order, ranges = pt.rcb_order(m.xyz, world)
+    xyz, tets, inv = pt.renumber(order, m.xyz, m.tets)
+    free = np.sort(inv[m.free_dofs // 3] * 3 + m.free_dofs % 3)
+    gm = O.FlatModel(xyz=xyz, tets=tets, mat_kind=m.mat_kind, mat_params=m.mat_params, free_dofs=free)
+    part = pt.build_local_part(rank, ranges, xyz, tets=tets, free_dofs=free)
+    ctx = make_ctx(part, m.mat_kind, m.mat_params, rank, world, local_rank)
+    own = part.owned_global_dofs(3)
+
+    # ---- assembly: owned rows of F_int and K equal the global oracle rows
+    U = cases.random_U(gm, 0.02)
+    ref = O.Assembly(gm).assemble(U)
+    ctx.set_U(part.scatter_global(U, 3))
+    ctx.assemble()
+    Fl = ctx.get_Fint()[:len(own)]
+    e_f = cases.rel_err(Fl, ref.F_int[own])
+    rp, ci, v = ctx.get_csr()
+    import scipy.sparse as sp
+    Kl = sp.csr_matrix((v, ci, rp), shape=(len(own), part.n_local * 3)).tocoo()
+    gcols = part.local_to_global[Kl.col // 3] * 3 + Kl.col % 3
+    Kg = sp.csr_matrix((Kl.data, (Kl.row, gcols)), shape=(len(own), gm.n_dofs))
+    e_k = abs(Kg - ref.csr()[own]).max() / abs(ref.csr()).max()
+
+    # ---- distributed SpMV and PCG against the oracle
+    mask = gm.free_mask()
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(gm.n_dofs) * mask
+    yl = ctx.spmv(part.scatter_global(x, 3))[:len(own)]
+    e_y = cases.rel_err(yl, ((ref.csr() @ x) * mask)[own])
+    b = rng.standard_normal(gm.n_dofs)
+    xs, its, res = ctx.pcg(part.scatter_global(b, 3), ob.PRECOND_JACOBI, 1e-12)
+    d = np.where(mask, ref.csr().diagonal(), 1.0)
+    xo, ito, _ = O.cg(ref.rowptr, ref.col, ref.val, mask, b, diag=d, reltol=1e-12)
+    e_x = np.abs(xs[:len(own)] - xo[own]).max() / np.abs(xo).max()
+
+    # ---- distributed Newton solve of the compression example vs the oracle's direct-solve Newton
+    unit = np.zeros(gm.n_dofs)
+    Fg = mg.global_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["x1"], (-1.0, 0.0, 0.0)).reshape(-1, 3)[order].ravel()
+    tols = O.ConvergenceSettings(1e-10, 1e-10, 20)
+    lfs = np.linspace(1 / 3, 1.0, 3)
+    refn = O.newton_solve(gm, lfs, lambda t: Fg * t, tols)
+    ctx.set_U(np.zeros(part.n_local * 3))
+    iters = []
+    import math
+    for t in lfs:
+        ctx.set_Fext(part.scatter_global(Fg * t, 3))
+        dU_rel = dr_rel = 1e12
+        it = 0
+        while O.criterion(dU_rel, dr_rel, it, tols) == "NotConvergedYet":
+            info = ctx.newton_step(ob.PRECOND_JACOBI, 1e-13)
+            dU_rel = info.norm_dU / info.norm_U if info.norm_U > 0 else math.inf
+            dr_rel = info.norm_r / info.norm_Fext
+            it += 1
+        iters.append(it)
+    Ul = ctx.get_U()[:len(own)]
+    e_u = np.abs(Ul - refn.U[-1][own]).max() / np.abs(refn.U[-1]).max()
+    errs = torch.tensor([e_f, e_k, e_y, e_x, e_u], dtype=torch.float64, device="cuda")
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        e_f, e_k, e_y, e_x, e_u = errs.tolist()
+        print(f"multi-gpu check world={world}: F_int {e_f:.2e}  K {e_k:.2e}  spmv {e_y:.2e}  pcg x {e_x:.2e} (its {its} vs {ito})  "
+              f"newton U {e_u:.2e} iters {iters} vs {refn.iterations}", flush=True)
+        assert e_f < 1e-12 and e_k < 1e-12 and e_y < 1e-12 and e_x < 1e-8 and e_u < 1e-8 and iters == refn.iterations
+        print("MULTI_GPU_CHECK_OK", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
