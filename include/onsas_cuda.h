@@ -62,9 +62,9 @@ typedef struct onsas_ctx onsas_ctx;
 
 /* tuning keys for onsas_set_option */
 #define ONSAS_OPT_CG_MODE 1      /* 0 = one persistent cooperative kernel (default, 1 GPU), 1 = one launch per phase */
-#define ONSAS_OPT_ASM_MINBLOCKS 2 /* 1, 2 or 3 resident CTAs per SM the assembly kernel is compiled for (default 2) */
+#define ONSAS_OPT_ASM_MINBLOCKS 2 /* register budget of the assembly kernel: 1 = unconstrained, 2 = 128, 3 = 96 registers (default 3 = 3 resident CTAs of 192 threads) */
 #define ONSAS_OPT_CG_CHECK_EVERY 3 /* multi-launch CG: iterations enqueued between host convergence checks (default 16) */
-#define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: CTAs per SM (0 = occupancy maximum) */
+#define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: resident CTAs per SM the kernel is compiled for: 4, 5 or 6 (default 6); 1-3 shrink the grid */
 #define ONSAS_OPT_CG_PROFILE 5       /* 1 = the persistent CG kernel records per-phase SM-clock cycles (onsas_get_cg_profile) */
 
 /* ---------------------------------------------------------------- life cycle */

@@ -153,7 +153,7 @@ struct onsas_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 
     // options
-    int cg_mode = 0, asm_minb = 2, check_every = 16, cg_bps = 0;
+    int cg_mode = 0, asm_minb = 3, check_every = 16, cg_bps = 6;
     int cg_grid = 0, part_stride = 4096;
 
     // comm
