@@ -148,18 +148,8 @@ def run_ours(args):
         xyz, tets, inv = pt.renumber(order, mesh.xyz, mesh.tets)
         gfree = np.sort(inv[free // 3] * 3 + free % 3)
         part = pt.build_local_part(rank, ranges, xyz, tets=tets, free_dofs=gfree)
-        ctx = ob.DeviceContext(local_rank)
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(ob.DeviceContext.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        ctx.comm_init(N, rank, bytes(uid.cpu().numpy().tobytes()))
-        ctx.set_nodes(part.xyz, part.n_owned)
-        ctx.set_materials(kind, params)
-        ctx.set_tets(part.tets)
-        ctx.set_free_dofs(part.free_dofs, part.n_free_global)
-        ctx.set_halo(part.nbr_rank, part.send_ptr, part.send_nodes, part.recv_ptr)
-        ctx.finalize()
+        from onsas_jl_b200 import multigpu
+        ctx = multigpu.make_distributed_context(part, kind, params, dist, local_rank, p2p=not args.no_p2p)
         perm = lambda v: v.reshape(-1, 3)[order].ravel()  # noqa: E731  (global vector in the partition numbering)
         loc = lambda v: part.scatter_global(perm(v), 3)   # noqa: E731
         n_tets_local = len(part.tets)
@@ -253,7 +243,8 @@ def run_ours(args):
         "config": {"workload": f"examples/uniaxial_compression NeoHookean tet cube, structured {args.cells}^3 cells per GPU "
                                f"({n_tets_total} tets total), state = analytic homogeneous field at load factor 0.5",
                    "n_tets": n_tets_total, "n_dofs": mesh.n_nodes * 3, "l2": "inputs larger than L2 (~0.4 GB touched per pass)",
-                   "partition": "single GPU" if N == 1 else f"RCB slabs, {N} ranks, NCCL halo exchange of U per assembly"},
+                   "partition": "single GPU" if N == 1 else f"RCB slabs, {N} ranks, NCCL halo exchange of U per assembly; CG: " +
+                                ("NCCL per phase" if args.no_p2p else "persistent kernel, halo + all-reduce over NVLink peer memory")},
         "newton_step_ms": nw[0], "newton_step": {"ms_assemble": nw[1], "ms_solve": nw[2], "cg_iters": nw[3], "precond": "jacobi",
                                                   "cg_reltol": float(np.sqrt(np.finfo(np.float64).eps)), "rel_residual_in": nw[4],
                                                   "rel_dU": nw[5]},
@@ -337,6 +328,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=55, help="hexes per edge per GPU (55 -> 998 250 tets)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL multi-launch CG instead of the peer-memory persistent kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -191,6 +191,16 @@ int32_t onsas_comm_init(onsas_ctx* ctx, int32_t n_ranks, int32_t rank, const voi
 int32_t onsas_set_halo(onsas_ctx* ctx, int32_t n_nbr, const int32_t* nbr_rank, const int64_t* send_ptr,
                        const int32_t* send_nodes, const int64_t* recv_ptr);
 
+/* Peer-memory path of the multi-GPU linear solve (one persistent kernel per GPU; halo values and scalar partial
+ * sums are stored straight into the other ranks' memory over NVLink, no NCCL call inside the solve).
+ * After onsas_comm_init + onsas_set_halo + onsas_finalize_mesh every rank exports its window (a 64-byte CUDA IPC
+ * handle + the offset of the window inside that allocation); the host all-gathers them and calls onsas_p2p_import
+ * with all handles / offsets (indexed by rank) and, per neighbour k, the node index inside THAT neighbour's
+ * vector where this rank's values go (its n_owned + its receive offset for this rank).  Without the import the
+ * solve uses the NCCL multi-launch path. */
+int32_t onsas_p2p_export(onsas_ctx* ctx, void* handle64, int64_t* offset);
+int32_t onsas_p2p_import(onsas_ctx* ctx, const void* handles, const int64_t* offsets, const int64_t* remote_halo_node_off);
+
 #ifdef __cplusplus
 }
 #endif

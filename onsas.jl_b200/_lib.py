@@ -70,6 +70,8 @@ SIGNATURES = {
     "onsas_comm_unique_id": (C.c_int32, [_vp]),
     "onsas_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp]),
     "onsas_set_halo": (C.c_int32, [_vp, C.c_int32, _vp, _vp, _vp, _vp]),
+    "onsas_p2p_export": (C.c_int32, [_vp, _vp, C.POINTER(C.c_int64)]),
+    "onsas_p2p_import": (C.c_int32, [_vp, _vp, _i64p, _vp]),
 }
 
 

@@ -441,7 +441,7 @@ __device__ __forceinline__ double diag_entry(const CgArgs& A, int64_t i) {
 // (slice, r) group read one 64-byte segment of K per (block, q) -- full sectors -- and the 3 components
 // of a node sit in consecutive groups, so a warp covers 32 scalar rows of at most 2 slices.
 // Returns p[i] * y[i] (0 for padded rows).
-template <int BS>
+template <int BS, bool HALO_CG = false>
 __device__ __forceinline__ double spmv_item(const CgArgs& A, int64_t t) {
     const int64_t sl = t / (C * BS);
     const int r = (int)((t / C) % BS);
@@ -456,8 +456,13 @@ __device__ __forceinline__ double spmv_item(const CgArgs& A, int64_t t) {
 #pragma unroll 4
     for (int s = 0; s < width; ++s) {
         const int64_t cnode = __ldg(cp + (int64_t)s * C);
+        // halo entries of p are written by peer GPUs (P2P): read them through L2 only in the multi-GPU kernel
+        const bool halo = HALO_CG && cnode >= A.n_rows;
 #pragma unroll
-        for (int q = 0; q < BS; ++q) acc += __ldcs(vp + ((int64_t)s * BS * BS + q) * C) * A.p[cnode * BS + q];
+        for (int q = 0; q < BS; ++q) {
+            const double pv = halo ? __ldcg(A.p + cnode * BS + q) : A.p[cnode * BS + q];
+            acc += __ldcs(vp + ((int64_t)s * BS * BS + q) * C) * pv;
+        }
     }
     const int64_t i = row * BS + r;
     const double y = A.mask[i] ? acc : 0.0;
@@ -618,6 +623,165 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A) {
         st->dd = dd;
         st->it = it;
         st->done = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU persistent PCG over NVLink peer memory (one process per GPU, CUDA IPC)
+// ------------------------------------------------------------------------------------------------
+// Every rank runs the same persistent kernel on its own GPU.  Per iteration the only cross-GPU traffic is
+//   * the halo of p: each rank stores the values its neighbours need straight into THEIR p vector (peer
+//     pointers, P2P stores over NVLink), then raises a flag in the neighbour's memory;
+//   * the scalars p.Ap and (r.r, r.z): each rank stores its partial into a slot of every peer and raises a
+//     flag; every rank then sums the slots in rank order, so all ranks (and all CTAs) get bitwise the same value.
+// No NCCL call, no host round trip inside the solve; flags are monotonically increasing epochs kept in device
+// memory across launches.  A spin that exceeds ~2 s of SM clock aborts the wait and raises *err (peer died).
+constexpr int P2P_MAXR = 16;
+struct P2PArgs {
+    int n_ranks, rank, n_nbr;
+    const int* nbr_rank;             // [n_nbr]
+    const long long* send_ptr;       // [n_nbr+1] into send_nodes
+    const int* send_nodes;           // owned node ids to push, grouped by neighbour
+    double* const* peer_halo;        // [n_nbr] where my values go inside neighbour k's p vector
+    double* slots;                   // local [2][P2P_MAXR][4]
+    double* const* peer_slots;       // [n_ranks] the same array on every rank (self included)
+    unsigned long long* flags;       // local [0..MAXR): reduction epochs by source rank, [MAXR..2MAXR): halo epochs by source rank
+    unsigned long long* const* peer_flags;  // [n_ranks]
+    unsigned long long* epochs;      // local [2]: reduction epoch, halo epoch (persist across launches)
+    int* err;
+};
+
+__device__ __forceinline__ bool p2p_wait(volatile unsigned long long* f, unsigned long long epoch, int* err) {
+    const long long t0 = clock64();
+    while (*f < epoch) {
+        if (clock64() - t0 > 4000000000LL || *(volatile int*)err == 2) {
+            *err = 2;
+            return false;
+        }
+    }
+    return true;
+}
+
+// all-reduce of nv <= 4 doubles across ranks; v[] holds this rank's value (identical in all its CTAs) on entry
+template <int NT>
+__device__ __forceinline__ void p2p_allreduce(const P2PArgs& P, double* v, int nv, unsigned long long& epoch) {
+    ++epoch;
+    const int par = (int)(epoch & 1);
+    if (blockIdx.x == 0 && threadIdx.x < P.n_ranks) {
+        double* dst = P.peer_slots[threadIdx.x] + (size_t)(par * P2P_MAXR + P.rank) * 4;
+        for (int k = 0; k < nv; ++k) *(volatile double*)(dst + k) = v[k];
+        __threadfence_system();
+        *(volatile unsigned long long*)(P.peer_flags[threadIdx.x] + P.rank) = epoch;
+    }
+    if (threadIdx.x < P.n_ranks) p2p_wait(P.flags + threadIdx.x, epoch, P.err);
+    __syncthreads();
+    for (int k = 0; k < nv; ++k) {
+        double s = 0.0;
+        for (int r = 0; r < P.n_ranks; ++r) s += __ldcv(P.slots + (size_t)(par * P2P_MAXR + r) * 4 + k);
+        v[k] = s;
+    }
+    __syncthreads();
+}
+
+template <int BS, int MINB>
+__global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P2PArgs P) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[CG_THREADS / 32];
+    const int64_t gtid = blockIdx.x * (int64_t)CG_THREADS + threadIdx.x;
+    const int64_t gsz = gridDim.x * (int64_t)CG_THREADS;
+    const int nb = gridDim.x;
+    double* part = A.partials;
+    const int ps = A.part_stride;
+    unsigned long long repoch = P.epochs[0], hepoch = P.epochs[1];
+
+    double s4[4];
+    cg_prologue_body<BS>(A, gtid, gsz, s4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double b = block_sum<CG_THREADS>(s4[k], sh);
+        if (threadIdx.x == 0) part[k * ps + blockIdx.x] = b;
+    }
+    grid.sync();
+    double g4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g4[k] = sum_partials<CG_THREADS>(part + k * ps, nb, sh);
+    p2p_allreduce<CG_THREADS>(P, g4, 4, repoch);
+    const double rr0 = g4[P_RR], ff = g4[P_FF], uu = g4[P_UU];
+    double rho = g4[P_RZ];
+    double res = sqrt(rr0);
+    const double tol = fmax(A.reltol * res, A.abstol);
+    double rho_prev = 1.0;
+    long long it = 0;
+
+    while (!(it >= A.maxiter || res <= tol)) {
+        const double beta = rho / rho_prev;
+        cg_update_p_body(A, gtid, gsz, beta);
+        grid.sync();  // all of p is final on this GPU before anything is pushed
+        // ---- halo push: my owned values into the neighbours' p vectors
+        for (int k = 0; k < P.n_nbr; ++k) {
+            const long long s0 = P.send_ptr[k], cnt = (P.send_ptr[k + 1] - s0) * BS;
+            double* dst = P.peer_halo[k];
+            for (long long i = gtid; i < cnt; i += gsz) dst[i] = A.p[(int64_t)P.send_nodes[s0 + i / BS] * BS + (i % BS)];
+        }
+        __threadfence_system();
+        grid.sync();
+        ++hepoch;
+        if (blockIdx.x == 0 && threadIdx.x < P.n_nbr) {
+            __threadfence_system();
+            *(volatile unsigned long long*)(P.peer_flags[P.nbr_rank[threadIdx.x]] + P2P_MAXR + P.rank) = hepoch;
+        }
+        if (threadIdx.x < P.n_nbr) p2p_wait(P.flags + P2P_MAXR + P.nbr_rank[threadIdx.x], hepoch, P.err);
+        if (threadIdx.x == 0) __threadfence();  // drop stale L1 lines of the halo part of p
+        __syncthreads();
+
+        double d = 0.0;
+        for (int64_t t = gtid, nt = spmv_items<BS>(A); t < nt; t += gsz) d += spmv_item<BS, true>(A, t);
+        d = block_sum<CG_THREADS>(d, sh);
+        if (threadIdx.x == 0) part[P_PAP * ps + blockIdx.x] = d;
+        grid.sync();
+        double pAp = sum_partials<CG_THREADS>(part + P_PAP * ps, nb, sh);
+        p2p_allreduce<CG_THREADS>(P, &pAp, 1, repoch);
+        const double alpha = rho / pAp;
+        double s2[2];
+        cg_update_xr_body(A, gtid, gsz, alpha, s2);
+        const double b0 = block_sum<CG_THREADS>(s2[0], sh);
+        const double b1 = block_sum<CG_THREADS>(s2[1], sh);
+        if (threadIdx.x == 0) {
+            part[P_RR * ps + blockIdx.x] = b0;
+            part[P_RZ * ps + blockIdx.x] = b1;
+        }
+        grid.sync();
+        double g2[2];
+        g2[0] = sum_partials<CG_THREADS>(part + P_RR * ps, nb, sh);
+        g2[1] = sum_partials<CG_THREADS>(part + P_RZ * ps, nb, sh);
+        p2p_allreduce<CG_THREADS>(P, g2, 2, repoch);
+        rho_prev = rho;
+        rho = g2[1];
+        res = sqrt(g2[0]);
+        ++it;
+    }
+
+    double dd = cg_epilogue_body(A, gtid, gsz);
+    dd = block_sum<CG_THREADS>(dd, sh);
+    if (threadIdx.x == 0) part[P_DD * ps + blockIdx.x] = dd;
+    grid.sync();
+    dd = sum_partials<CG_THREADS>(part + P_DD * ps, nb, sh);
+    p2p_allreduce<CG_THREADS>(P, &dd, 1, repoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        CgState* st = A.st;
+        st->rho = rho;
+        st->rho_prev = rho_prev;
+        st->res = res;
+        st->tol = tol;
+        st->pAp = 0.0;
+        st->rr0 = rr0;
+        st->ff = ff;
+        st->uu = uu;
+        st->dd = dd;
+        st->it = it;
+        st->done = 1;
+        P.epochs[0] = repoch;
+        P.epochs[1] = hepoch;
     }
 }
 

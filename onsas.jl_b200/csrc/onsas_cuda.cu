@@ -38,6 +38,13 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool owned = true;
+    void alias(T* ptr, size_t count) {  // view into memory owned elsewhere (the P2P window)
+        release();
+        p = ptr;
+        n = count;
+        owned = false;
+    }
     void alloc(size_t count) {
         release();
         n = count;
@@ -60,9 +67,10 @@ struct DevBuf {
     }
     void upload(const std::vector<T>& v, cudaStream_t s) { upload(v.data(), v.size(), s); }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         n = 0;
+        owned = true;
     }
     ~DevBuf() { release(); }
 };
@@ -161,6 +169,15 @@ struct onsas_ctx {
     int n_ranks = 1, rank = 0;
     std::vector<int32_t> nbr_rank;
     std::vector<int64_t> send_ptr, recv_ptr;
+    // peer-memory window (multi-GPU persistent CG): [slots][flags][epochs][p]
+    DevBuf<unsigned char> window;
+    std::vector<void*> ipc_opened;
+    bool p2p_ready = false;
+    DevBuf<int> d_nbr_rank;
+    DevBuf<long long> d_send_ptr;
+    DevBuf<double*> d_peer_halo, d_peer_slots;
+    DevBuf<unsigned long long*> d_peer_flags;
+    int cg_grid_mg = 0;
 
     int64_t n_local_dofs() const { return n_nodes * dim; }
     int64_t n_own_dofs() const { return n_owned * dim; }
@@ -324,6 +341,15 @@ void allreduce(onsas_ctx* c, double* d, int count) {
     NCCL_CHECK(g_nccl.AllReduce(d, d, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
 }
 
+// ---------------------------------------------------------------- P2P window layout
+constexpr size_t P2P_SLOTS_BYTES = 2 * P2P_MAXR * 4 * sizeof(double);
+constexpr size_t P2P_FLAGS_BYTES = 2 * P2P_MAXR * sizeof(unsigned long long);
+constexpr size_t P2P_HDR_BYTES = ((P2P_SLOTS_BYTES + P2P_FLAGS_BYTES + 2 * sizeof(unsigned long long) + 255) / 256) * 256;
+inline double* win_slots(unsigned char* w) { return reinterpret_cast<double*>(w); }
+inline unsigned long long* win_flags(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_SLOTS_BYTES); }
+inline unsigned long long* win_epochs(unsigned char* w) { return win_flags(w) + 2 * P2P_MAXR; }
+inline double* win_p(unsigned char* w) { return reinterpret_cast<double*>(w + P2P_HDR_BYTES); }
+
 // ---------------------------------------------------------------- CG drivers
 CgArgs make_cg_args(onsas_ctx* c, int precond, double reltol, double abstol, int64_t maxiter, bool use_rhs, int update_U) {
     CgArgs A{};
@@ -389,6 +415,33 @@ void run_cg_bs(onsas_ctx* c, CgArgs A) {
         CUDA_CHECK(cudaLaunchCooperativeKernel(persistent_kernel<BS>(c), dim3(c->cg_grid), dim3(CG_THREADS), args, 0, c->stream));
         return;
     }
+    if (c->cg_mode == 0 && c->n_ranks > 1 && c->p2p_ready) {
+        // multi-GPU: the same persistent solve with halo pushes and scalar all-reduces over NVLink peer memory
+        void* kern = c->cg_bps >= 6 ? (void*)cg_persistent_mg<BS, 6> : (void*)cg_persistent_mg<BS, 4>;
+        if (c->cg_grid_mg == 0) {
+            int bps = 0;
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, CG_THREADS, 0));
+            require(bps > 0, ONSAS_ERR_CUDA, "multi-GPU persistent CG kernel does not fit on an SM");
+            c->cg_grid_mg = std::min(bps * c->n_sm, c->part_stride);
+        }
+        P2PArgs P{};
+        P.n_ranks = c->n_ranks;
+        P.rank = c->rank;
+        P.n_nbr = (int)c->nbr_rank.size();
+        P.nbr_rank = c->d_nbr_rank.p;
+        P.send_ptr = c->d_send_ptr.p;
+        P.send_nodes = c->send_nodes.p;
+        P.peer_halo = c->d_peer_halo.p;
+        P.slots = win_slots(c->window.p);
+        P.peer_slots = c->d_peer_slots.p;
+        P.flags = win_flags(c->window.p);
+        P.peer_flags = c->d_peer_flags.p;
+        P.epochs = win_epochs(c->window.p);
+        P.err = c->err_flag.p;
+        void* args[] = {&A, &P};
+        CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(c->cg_grid_mg), dim3(CG_THREADS), args, 0, c->stream));
+        return;
+    }
     // one launch per phase; collectives in-stream between them
     const int G = (int)std::max<int64_t>(1, std::min<int64_t>((n + CG_THREADS - 1) / CG_THREADS, (int64_t)c->n_sm * 8));
     const int Gr = spmv_grid(c);
@@ -440,8 +493,10 @@ void fetch_state(onsas_ctx* c) {
 
 void check_deferred(onsas_ctx* c) {
     if (*c->h_flag != 0) {
+        const int f = *c->h_flag;
         c->err_flag.zero(c->stream);
         *c->h_flag = 0;
+        if (f == 2) throw OnsasError(ONSAS_ERR_COMM, "peer-memory CG: timed out waiting for another rank");
         throw OnsasError(ONSAS_ERR_NEGATIVE_VOLUME, "Element with negative volume, check connectivity.");
     }
 }
@@ -523,6 +578,7 @@ int32_t onsas_destroy(onsas_ctx* c) {
     if (!c) return ONSAS_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    for (void* b : c->ipc_opened) cudaIpcCloseMemHandle(b);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -735,7 +791,16 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->U.alloc(nl); c->U.zero(s);
         c->Fext.alloc(nl); c->Fext.zero(s);
         c->Fint.alloc(nl); c->Fint.zero(s);
-        c->p.alloc(nl); c->p.zero(s);
+        if (c->n_ranks > 1) {
+            // P2P window: fixed-size header (slots, flags, epochs) then p, so that peers can address every part
+            c->window.alloc(P2P_HDR_BYTES + nl * sizeof(double));
+            c->window.zero(s);
+            c->p.alias(reinterpret_cast<double*>(c->window.p + P2P_HDR_BYTES), nl);
+            c->p2p_ready = false;
+        } else {
+            c->p.alloc(nl);
+            c->p.zero(s);
+        }
         c->rhs.alloc(nl); c->rhs.zero(s);
         c->x.alloc(no); c->x.zero(s);
         c->r.alloc(no); c->r.zero(s);
@@ -1062,6 +1127,71 @@ int32_t onsas_set_halo(onsas_ctx* c, int32_t n_nbr, const int32_t* nbr_rank, con
         c->send_nodes.upload(send_nodes, (size_t)ns, c->stream);
         c->sendbuf.alloc((size_t)std::max<int64_t>(ns, 1) * c->dim);
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int32_t onsas_p2p_export(onsas_ctx* c, void* handle64, int64_t* offset) {
+    if (!c || !handle64 || !offset) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized && c->n_ranks > 1 && c->window.p, ONSAS_ERR_NOT_READY,
+                "onsas_comm_init and onsas_finalize_mesh must precede onsas_p2p_export");
+        cudaIpcMemHandle_t h;
+        CUDA_CHECK(cudaIpcGetMemHandle(&h, c->window.p));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::memcpy(handle64, &h, 64);
+        // the handle names the whole underlying allocation: report where the window starts inside it
+        *offset = 0;
+        void* drv = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (drv) {
+            using Fn = int (*)(unsigned long long*, size_t*, unsigned long long);
+            Fn f = (Fn)dlsym(drv, "cuMemGetAddressRange_v2");
+            unsigned long long base = 0;
+            size_t size = 0;
+            if (f && f(&base, &size, (unsigned long long)(uintptr_t)c->window.p) == 0)
+                *offset = (int64_t)((unsigned long long)(uintptr_t)c->window.p - base);
+        }
+    });
+}
+
+int32_t onsas_p2p_import(onsas_ctx* c, const void* handles, const int64_t* offsets, const int64_t* remote_halo_node_off) {
+    if (!c || !handles || !offsets) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized && c->n_ranks > 1 && c->window.p, ONSAS_ERR_NOT_READY, "window not allocated");
+        require(c->n_ranks <= P2P_MAXR, ONSAS_ERR_UNSUPPORTED, "peer-memory CG supports at most 16 ranks");
+        const int nn = (int)c->nbr_rank.size();
+        require(nn == 0 || remote_halo_node_off, ONSAS_ERR_INVALID_ARG, "NULL remote halo offsets");
+        std::vector<unsigned char*> win(c->n_ranks, nullptr);
+        for (int r = 0; r < c->n_ranks; ++r) {
+            if (r == c->rank) {
+                win[r] = c->window.p;
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, (const unsigned char*)handles + 64 * r, 64);
+            void* base = nullptr;
+            CUDA_CHECK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(base);
+            win[r] = (unsigned char*)base + offsets[r];
+        }
+        std::vector<double*> slots(c->n_ranks), halo(nn);
+        std::vector<unsigned long long*> flags(c->n_ranks);
+        for (int r = 0; r < c->n_ranks; ++r) {
+            slots[r] = win_slots(win[r]);
+            flags[r] = win_flags(win[r]);
+        }
+        for (int k = 0; k < nn; ++k) halo[k] = win_p(win[c->nbr_rank[k]]) + remote_halo_node_off[k] * c->dim;
+        std::vector<int> nbr(c->nbr_rank.begin(), c->nbr_rank.end());
+        std::vector<long long> sp(c->send_ptr.begin(), c->send_ptr.end());
+        if (sp.empty()) sp.push_back(0);
+        cudaStream_t s = c->stream;
+        c->d_nbr_rank.upload(nbr, s);
+        c->d_send_ptr.upload(sp, s);
+        c->d_peer_halo.upload(halo, s);
+        c->d_peer_slots.upload(slots, s);
+        c->d_peer_flags.upload(flags, s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        c->p2p_ready = true;
+        c->cg_grid_mg = 0;
     });
 }
 

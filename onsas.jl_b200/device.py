@@ -239,6 +239,19 @@ class DeviceContext:
         self._check(self._lib.onsas_set_halo(self._h, len(nbr), _ptr(nbr), _ptr(sp), _ptr(sn), _ptr(rp)))
 
 
+    def p2p_export(self):
+        buf = C.create_string_buffer(64)
+        off = C.c_int64(0)
+        self._check(self._lib.onsas_p2p_export(self._h, C.cast(buf, C.c_void_p), C.byref(off)))
+        return buf.raw, off.value
+
+    def p2p_import(self, handles, offsets, remote_halo_node_off):
+        blob = C.create_string_buffer(b"".join(handles), 64 * len(handles))
+        offs = _as(offsets, np.int64)
+        rem = _as(remote_halo_node_off, np.int64)
+        self._check(self._lib.onsas_p2p_import(self._h, C.cast(blob, C.c_void_p), offs, _ptr(rem) if len(rem) else None))
+
+
 def context_from_flat(xyz, tets=None, trusses=None, truss_area=None, truss_strain=0, mat_kind=(0,), mat_params=((1.0, 1.0),),
                       tet_mat=None, truss_mat=None, free_dofs=None, device: int = 0, n_owned=None,
                       n_free_global: int = 0) -> DeviceContext:

@@ -1,0 +1,42 @@
+"""One-process-per-GPU setup of a distributed DeviceContext: NCCL communicator bootstrap
+through torch.distributed (plumbing), halo plan upload, and the CUDA-IPC window exchange that lets the persistent
+CG kernel push halo values / partial sums straight into the peers' memory over NVLink."""
+from __future__ import annotations
+
+import numpy as np
+
+from .device import DeviceContext
+
+
+def make_distributed_context(part, mat_kind, mat_params, dist, local_rank: int, p2p: bool = True,
+                             truss_strain: int = 0) -> DeviceContext:
+    """`part` is a partition.LocalPart; `dist` an initialised torch.distributed (NCCL backend)."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ctx = DeviceContext(local_rank)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(DeviceContext.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    ctx.set_nodes(part.xyz, part.n_owned)
+    ctx.set_materials(mat_kind, mat_params)
+    if len(part.tets):
+        ctx.set_tets(part.tets, part.tet_mat)
+    if len(part.trusses):
+        ctx.set_trusses(part.trusses, part.truss_area, part.truss_mat, truss_strain)
+    ctx.set_free_dofs(part.free_dofs, part.n_free_global)
+    ctx.set_halo(part.nbr_rank, part.send_ptr, part.send_nodes, part.recv_ptr)
+    ctx.finalize()
+    if p2p and world > 1:
+        handle, offset = ctx.p2p_export()
+        meta = [None] * world
+        dist.all_gather_object(meta, dict(handle=handle, offset=offset, n_owned=int(part.n_owned),
+                                          nbr=[int(r) for r in part.nbr_rank], recv_ptr=[int(v) for v in part.recv_ptr]))
+        remote = []
+        for r in part.nbr_rank:          # where my values go inside neighbour r's vector
+            m = meta[int(r)]
+            j = m["nbr"].index(rank)
+            remote.append(m["n_owned"] + m["recv_ptr"][j])
+        ctx.p2p_import([m["handle"] for m in meta], [m["offset"] for m in meta], np.asarray(remote, np.int64))
+    return ctx
