@@ -683,7 +683,7 @@ __device__ __forceinline__ void p2p_allreduce(const P2PArgs& P, double* v, int n
     __syncthreads();
 }
 
-template <int BS, int MINB>
+template <int BS, int MINB, bool PROF>
 __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P2PArgs P) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[CG_THREADS / 32];
@@ -712,11 +712,23 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
     const double tol = fmax(A.reltol * res, A.abstol);
     double rho_prev = 1.0;
     long long it = 0;
+    const bool profiling = PROF && A.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tprev = profiling ? clock64() : 0;
+    long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};
+#define MG_PROF(k)                          \
+    if constexpr (PROF) {                   \
+        if (profiling) {                    \
+            const long long tn = clock64(); \
+            tacc[k] += tn - tprev;          \
+            tprev = tn;                     \
+        }                                   \
+    }
 
     while (!(it >= A.maxiter || res <= tol)) {
         const double beta = rho / rho_prev;
         cg_update_p_body(A, gtid, gsz, beta);
         grid.sync();  // all of p is final on this GPU before anything is pushed
+        MG_PROF(0)
         // ---- halo push: my owned values into the neighbours' p vectors
         for (int k = 0; k < P.n_nbr; ++k) {
             const long long s0 = P.send_ptr[k], cnt = (P.send_ptr[k + 1] - s0) * BS;
@@ -725,6 +737,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
         }
         __threadfence_system();
         grid.sync();
+        MG_PROF(1)
         ++hepoch;
         if (blockIdx.x == 0 && threadIdx.x < P.n_nbr) {
             __threadfence_system();
@@ -733,14 +746,17 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
         if (threadIdx.x < P.n_nbr) p2p_wait(P.flags + P2P_MAXR + P.nbr_rank[threadIdx.x], hepoch, P.err);
         if (threadIdx.x == 0) __threadfence();  // drop stale L1 lines of the halo part of p
         __syncthreads();
+        MG_PROF(2)
 
         double d = 0.0;
         for (int64_t t = gtid, nt = spmv_items<BS>(A); t < nt; t += gsz) d += spmv_item<BS, true>(A, t);
         d = block_sum<CG_THREADS>(d, sh);
         if (threadIdx.x == 0) part[P_PAP * ps + blockIdx.x] = d;
+        MG_PROF(3)
         grid.sync();
         double pAp = sum_partials<CG_THREADS>(part + P_PAP * ps, nb, sh);
         p2p_allreduce<CG_THREADS>(P, &pAp, 1, repoch);
+        MG_PROF(4)
         const double alpha = rho / pAp;
         double s2[2];
         cg_update_xr_body(A, gtid, gsz, alpha, s2);
@@ -750,6 +766,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
             part[P_RR * ps + blockIdx.x] = b0;
             part[P_RZ * ps + blockIdx.x] = b1;
         }
+        MG_PROF(5)
         grid.sync();
         double g2[2];
         g2[0] = sum_partials<CG_THREADS>(part + P_RR * ps, nb, sh);
@@ -759,6 +776,12 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
         rho = g2[1];
         res = sqrt(g2[0]);
         ++it;
+        MG_PROF(6)
+    }
+#undef MG_PROF
+    if constexpr (PROF) {
+        if (profiling)
+            for (int k = 0; k < 7; ++k) A.prof[k] = tacc[k];
     }
 
     double dd = cg_epilogue_body(A, gtid, gsz);
