@@ -683,7 +683,7 @@ __device__ __forceinline__ void p2p_allreduce(const P2PArgs& P, double* v, int n
     __syncthreads();
 }
 
-template <int BS, int MINB, bool PROF>
+template <int BS, int MINB, bool PROF, bool HCG>
 __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P2PArgs P) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[CG_THREADS / 32];
@@ -730,12 +730,16 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
         grid.sync();  // all of p is final on this GPU before anything is pushed
         MG_PROF(0)
         // ---- halo push: my owned values into the neighbours' p vectors
+        bool pushed = false;
         for (int k = 0; k < P.n_nbr; ++k) {
             const long long s0 = P.send_ptr[k], cnt = (P.send_ptr[k + 1] - s0) * BS;
             double* dst = P.peer_halo[k];
-            for (long long i = gtid; i < cnt; i += gsz) dst[i] = A.p[(int64_t)P.send_nodes[s0 + i / BS] * BS + (i % BS)];
+            for (long long i = gtid; i < cnt; i += gsz) {
+                dst[i] = A.p[(int64_t)P.send_nodes[s0 + i / BS] * BS + (i % BS)];
+                pushed = true;
+            }
         }
-        __threadfence_system();
+        if (pushed) __threadfence_system();  // only the threads that stored to a peer need their stores ordered before the flag
         grid.sync();
         MG_PROF(1)
         ++hepoch;
@@ -749,7 +753,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
         MG_PROF(2)
 
         double d = 0.0;
-        for (int64_t t = gtid, nt = spmv_items<BS>(A); t < nt; t += gsz) d += spmv_item<BS, true>(A, t);
+        for (int64_t t = gtid, nt = spmv_items<BS>(A); t < nt; t += gsz) d += spmv_item<BS, HCG>(A, t);
         d = block_sum<CG_THREADS>(d, sh);
         if (threadIdx.x == 0) part[P_PAP * ps + blockIdx.x] = d;
         MG_PROF(3)

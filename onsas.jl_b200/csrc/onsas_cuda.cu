@@ -163,6 +163,7 @@ struct onsas_ctx {
     // options
     int cg_mode = 0, asm_minb = 3, check_every = 16, cg_bps = 6;
     int cg_grid = 0, part_stride = 4096;
+    int debug_flags = 0;
 
     // comm
     ncclComm_t comm = nullptr;
@@ -417,8 +418,13 @@ void run_cg_bs(onsas_ctx* c, CgArgs A) {
     }
     if (c->cg_mode == 0 && c->n_ranks > 1 && c->p2p_ready) {
         // multi-GPU: the same persistent solve with halo pushes and scalar all-reduces over NVLink peer memory
-        void* kern = c->cg_profile ? (void*)cg_persistent_mg<BS, 4, true>
-                                   : c->cg_bps >= 6 ? (void*)cg_persistent_mg<BS, 6, false> : (void*)cg_persistent_mg<BS, 4, false>;
+        void* kern;
+        if (c->debug_flags & 1)  // diagnostics: plain (L1-cached) loads of the halo part of p
+            kern = c->cg_profile ? (void*)cg_persistent_mg<BS, 4, true, false>
+                                 : c->cg_bps >= 6 ? (void*)cg_persistent_mg<BS, 6, false, false> : (void*)cg_persistent_mg<BS, 4, false, false>;
+        else
+            kern = c->cg_profile ? (void*)cg_persistent_mg<BS, 4, true, true>
+                                 : c->cg_bps >= 6 ? (void*)cg_persistent_mg<BS, 6, false, true> : (void*)cg_persistent_mg<BS, 4, false, true>;
         if (c->cg_grid_mg == 0) {
             int bps = 0;
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, CG_THREADS, 0));
@@ -605,6 +611,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_CG_MODE: require(value == 0 || value == 1, ONSAS_ERR_INVALID_ARG, "cg mode must be 0 or 1"); c->cg_mode = (int)value; break;
             case ONSAS_OPT_ASM_MINBLOCKS: require(value >= 1 && value <= 3, ONSAS_ERR_INVALID_ARG, "min blocks must be 1..3"); c->asm_minb = (int)value; break;
             case ONSAS_OPT_CG_CHECK_EVERY: require(value >= 1 && value <= 4096, ONSAS_ERR_INVALID_ARG, "check_every out of range"); c->check_every = (int)value; break;
+            case ONSAS_OPT_DEBUG_FLAGS: c->debug_flags = (int)value; c->cg_grid_mg = 0; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; c->cg_grid_mg = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; c->cg_grid_mg = 0; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
