@@ -65,7 +65,6 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_ASM_MINBLOCKS 2 /* register budget of the assembly kernel: 1 = unconstrained, 2 = 128, 3 = 96 registers (default 3 = 3 resident CTAs of 192 threads) */
 #define ONSAS_OPT_CG_CHECK_EVERY 3 /* multi-launch CG: iterations enqueued between host convergence checks (default 16) */
 #define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: resident CTAs per SM the kernel is compiled for: 4, 5 or 6 (default 6); 1-3 shrink the grid */
-#define ONSAS_OPT_DEBUG_FLAGS 6      /* diagnostics only; bit 0: multi-GPU CG reads halo entries of p with ordinary cached loads */
 #define ONSAS_OPT_CG_PROFILE 5       /* 1 = the persistent CG kernel records per-phase SM-clock cycles (onsas_get_cg_profile) */
 
 /* ---------------------------------------------------------------- life cycle */
@@ -192,15 +191,16 @@ int32_t onsas_comm_init(onsas_ctx* ctx, int32_t n_ranks, int32_t rank, const voi
 int32_t onsas_set_halo(onsas_ctx* ctx, int32_t n_nbr, const int32_t* nbr_rank, const int64_t* send_ptr,
                        const int32_t* send_nodes, const int64_t* recv_ptr);
 
-/* Peer-memory path of the multi-GPU linear solve (one persistent kernel per GPU; halo values and scalar partial
- * sums are stored straight into the other ranks' memory over NVLink, no NCCL call inside the solve).
+/* Peer-memory path of the multi-GPU linear solve: one persistent kernel per GPU; the z values of interface dofs and
+ * the scalar partial sums are stored straight into the other ranks' memory over NVLink (8-byte words carrying
+ * 32 data bits + a 32-bit epoch, polled by the receiver), no NCCL call inside the solve.
  * After onsas_comm_init + onsas_set_halo + onsas_finalize_mesh every rank exports its window (a 64-byte CUDA IPC
  * handle + the offset of the window inside that allocation); the host all-gathers them and calls onsas_p2p_import
- * with all handles / offsets (indexed by rank) and, per neighbour k, the node index inside THAT neighbour's
- * vector where this rank's values go (its n_owned + its receive offset for this rank).  Without the import the
- * solve uses the NCCL multi-launch path. */
+ * with all handles / offsets (indexed by rank) and, per neighbour k, the position (in nodes) inside THAT
+ * neighbour's halo where this rank's values start (its receive offset recv_ptr[j] for this rank).
+ * Without the import the solve uses the NCCL multi-launch path. */
 int32_t onsas_p2p_export(onsas_ctx* ctx, void* handle64, int64_t* offset);
-int32_t onsas_p2p_import(onsas_ctx* ctx, const void* handles, const int64_t* offsets, const int64_t* remote_halo_node_off);
+int32_t onsas_p2p_import(onsas_ctx* ctx, const void* handles, const int64_t* offsets, const int64_t* remote_halo_off);
 
 #ifdef __cplusplus
 }

@@ -441,7 +441,7 @@ __device__ __forceinline__ double diag_entry(const CgArgs& A, int64_t i) {
 // (slice, r) group read one 64-byte segment of K per (block, q) -- full sectors -- and the 3 components
 // of a node sit in consecutive groups, so a warp covers 32 scalar rows of at most 2 slices.
 // Returns p[i] * y[i] (0 for padded rows).
-template <int BS, bool HALO_CG = false>
+template <int BS>
 __device__ __forceinline__ double spmv_item(const CgArgs& A, int64_t t) {
     const int64_t sl = t / (C * BS);
     const int r = (int)((t / C) % BS);
@@ -456,13 +456,8 @@ __device__ __forceinline__ double spmv_item(const CgArgs& A, int64_t t) {
 #pragma unroll 4
     for (int s = 0; s < width; ++s) {
         const int64_t cnode = __ldg(cp + (int64_t)s * C);
-        // halo entries of p are written by peer GPUs (P2P): read them through L2 only in the multi-GPU kernel
-        const bool halo = HALO_CG && cnode >= A.n_rows;
 #pragma unroll
-        for (int q = 0; q < BS; ++q) {
-            const double pv = halo ? __ldcg(A.p + cnode * BS + q) : A.p[cnode * BS + q];
-            acc += __ldcs(vp + ((int64_t)s * BS * BS + q) * C) * pv;
-        }
+        for (int q = 0; q < BS; ++q) acc += __ldcs(vp + ((int64_t)s * BS * BS + q) * C) * A.p[cnode * BS + q];
     }
     const int64_t i = row * BS + r;
     const double y = A.mask[i] ? acc : 0.0;
@@ -629,73 +624,98 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A) {
 // ------------------------------------------------------------------------------------------------
 // multi-GPU persistent PCG over NVLink peer memory (one process per GPU, CUDA IPC)
 // ------------------------------------------------------------------------------------------------
-// Every rank runs the same persistent kernel on its own GPU.  Per iteration the only cross-GPU traffic is
-//   * the halo of p: each rank stores the values its neighbours need straight into THEIR p vector (peer
-//     pointers, P2P stores over NVLink), then raises a flag in the neighbour's memory;
-//   * the scalars p.Ap and (r.r, r.z): each rank stores its partial into a slot of every peer and raises a
-//     flag; every rank then sums the slots in rank order, so all ranks (and all CTAs) get bitwise the same value.
-// No NCCL call, no host round trip inside the solve; flags are monotonically increasing epochs kept in device
-// memory across launches.  A spin that exceeds ~2 s of SM clock aborts the wait and raises *err (peer died).
+// Every rank runs the same persistent kernel on its own GPU.  All cross-GPU traffic is one-way P2P stores in
+// the "LL" format: a double travels as two 8-byte words {32 data bits | 32-bit epoch}; an 8-byte store is atomic,
+// so the receiver just polls until both words carry the expected epoch -- no fences, no separate flags, no
+// acknowledgements on the critical path.
+//   * scalars (p.Ap ; r.r, r.z ; the Newton norms): block 0 writes its rank's partial into a slot of every peer;
+//     every CTA of every rank polls the slots and sums them in rank order -> bitwise identical everywhere;
+//   * halo: the thread that updates r_i also stores z_i = r_i / d_i into the neighbours' receive buffers, i.e.
+//     BEFORE the (r.r, r.z) all-reduce, so the exchange overlaps it; once beta is known each rank forms
+//     p = z + beta p for its owned AND its halo nodes locally.  SpMV then reads only local memory.
+// Three grid syncs per iteration, as on one GPU.  A poll that exceeds ~2 s of SM clock raises *err = 2.
 constexpr int P2P_MAXR = 16;
 struct P2PArgs {
-    int n_ranks, rank, n_nbr;
-    const int* nbr_rank;             // [n_nbr]
-    const long long* send_ptr;       // [n_nbr+1] into send_nodes
-    const int* send_nodes;           // owned node ids to push, grouped by neighbour
-    double* const* peer_halo;        // [n_nbr] where my values go inside neighbour k's p vector
-    double* slots;                   // local [2][P2P_MAXR][4]
-    double* const* peer_slots;       // [n_ranks] the same array on every rank (self included)
-    unsigned long long* flags;       // local [0..MAXR): reduction epochs by source rank, [MAXR..2MAXR): halo epochs by source rank
-    unsigned long long* const* peer_flags;  // [n_ranks]
-    unsigned long long* epochs;      // local [2]: reduction epoch, halo epoch (persist across launches)
+    int n_ranks, rank;
+    long long n_halo_dofs;
+    const long long* push_ptr;               // [n_own_dofs+1] CSR: remote LL slots that want dof i
+    unsigned long long* const* push_dst;     // remote addresses (16 bytes each) in the neighbours' zh buffers
+    unsigned long long* zh;                  // local receive buffer: n_halo_dofs LL pairs
+    unsigned long long* slots;               // local [2][P2P_MAXR][4] LL pairs
+    unsigned long long* const* peer_slots;   // [n_ranks] the same array on every rank (self included)
+    unsigned long long* epochs;              // local [2]: scalar epoch, halo epoch (persist across launches)
     int* err;
 };
 
-__device__ __forceinline__ bool p2p_wait(volatile unsigned long long* f, unsigned long long epoch, int* err) {
-    const long long t0 = clock64();
-    while (*f < epoch) {
-        if (clock64() - t0 > 4000000000LL || *(volatile int*)err == 2) {
-            *err = 2;
-            return false;
-        }
+__device__ __forceinline__ void ll_store(unsigned long long* dst, double v, unsigned int flag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long f = (unsigned long long)flag << 32;
+    // one 16-byte store = two atomic 8-byte words {32 data bits | 32-bit epoch}
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"((bits & 0xffffffffull) | f), "l"((bits >> 32) | f)
+                 : "memory");
+}
+
+__device__ __forceinline__ double ll_load(const unsigned long long* src, unsigned int flag, int* err) {
+    const volatile unsigned long long* s = src;
+    unsigned long long x = s[0], y = s[1];
+    if ((unsigned int)(x >> 32) != flag || (unsigned int)(y >> 32) != flag) {
+        const long long t0 = clock64();
+        do {
+            x = s[0];
+            y = s[1];
+            if (clock64() - t0 > 4000000000LL) {
+                *err = 2;
+                break;
+            }
+        } while ((unsigned int)(x >> 32) != flag || (unsigned int)(y >> 32) != flag);
     }
-    return true;
+    return __longlong_as_double((long long)((x & 0xffffffffull) | (y << 32)));
 }
 
 // all-reduce of nv <= 4 doubles across ranks; v[] holds this rank's value (identical in all its CTAs) on entry
-template <int NT>
-__device__ __forceinline__ void p2p_allreduce(const P2PArgs& P, double* v, int nv, unsigned long long& epoch) {
+__device__ __forceinline__ void p2p_allreduce(const P2PArgs& P, double* v, int nv, unsigned int& epoch, double* sh4) {
     ++epoch;
-    const int par = (int)(epoch & 1);
-    if (blockIdx.x == 0 && threadIdx.x < P.n_ranks) {
-        double* dst = P.peer_slots[threadIdx.x] + (size_t)(par * P2P_MAXR + P.rank) * 4;
-        for (int k = 0; k < nv; ++k) *(volatile double*)(dst + k) = v[k];
-        __threadfence_system();
-        *(volatile unsigned long long*)(P.peer_flags[threadIdx.x] + P.rank) = epoch;
+    const int par = (int)(epoch & 1u);
+    const int t = threadIdx.x;
+    if (blockIdx.x == 0 && t < P.n_ranks * nv) {
+        const int r = t / nv, k = t % nv;
+        ll_store(P.peer_slots[r] + (size_t)((par * P2P_MAXR + P.rank) * 4 + k) * 2, v[k], epoch);
     }
-    if (threadIdx.x < P.n_ranks) p2p_wait(P.flags + threadIdx.x, epoch, P.err);
-    __syncthreads();
-    for (int k = 0; k < nv; ++k) {
+    __syncthreads();  // sh4 free for reuse
+    if (t < nv) {
         double s = 0.0;
-        for (int r = 0; r < P.n_ranks; ++r) s += __ldcv(P.slots + (size_t)(par * P2P_MAXR + r) * 4 + k);
-        v[k] = s;
+        for (int r = 0; r < P.n_ranks; ++r) s += ll_load(P.slots + (size_t)((par * P2P_MAXR + r) * 4 + t) * 2, epoch, P.err);
+        sh4[t] = s;
     }
+    __syncthreads();
+    for (int k = 0; k < nv; ++k) v[k] = sh4[k];
     __syncthreads();
 }
 
-template <int BS, int MINB, bool PROF, bool HCG>
+// store z_i for every peer slot that wants owned dof i
+__device__ __forceinline__ void p2p_push(const P2PArgs& P, int64_t i, double z, unsigned int hepoch) {
+    for (long long q = P.push_ptr[i]; q < P.push_ptr[i + 1]; ++q) ll_store(P.push_dst[q], z, hepoch);
+}
+
+template <int BS, int MINB, bool PROF>
 __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P2PArgs P) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[CG_THREADS / 32];
+    __shared__ double sh4[4];
     const int64_t gtid = blockIdx.x * (int64_t)CG_THREADS + threadIdx.x;
     const int64_t gsz = gridDim.x * (int64_t)CG_THREADS;
     const int nb = gridDim.x;
     double* part = A.partials;
     const int ps = A.part_stride;
-    unsigned long long repoch = P.epochs[0], hepoch = P.epochs[1];
+    unsigned int repoch = (unsigned int)P.epochs[0], hepoch = (unsigned int)P.epochs[1];
 
+    // ---- prologue: residual, Jacobi diagonal, norms; first halo push of z = r / d
     double s4[4];
     cg_prologue_body<BS>(A, gtid, gsz, s4);
+    ++hepoch;
+    for (int64_t i = gtid; i < A.n; i += gsz)
+        if (P.push_ptr[i + 1] > P.push_ptr[i]) p2p_push(P, i, A.r[i] * A.dinv[i], hepoch);
+    for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) A.p[i] = 0.0;  // halo part of the search direction
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const double b = block_sum<CG_THREADS>(s4[k], sh);
@@ -705,7 +725,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
     double g4[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) g4[k] = sum_partials<CG_THREADS>(part + k * ps, nb, sh);
-    p2p_allreduce<CG_THREADS>(P, g4, 4, repoch);
+    p2p_allreduce(P, g4, 4, repoch, sh4);
     const double rr0 = g4[P_RR], ff = g4[P_FF], uu = g4[P_UU];
     double rho = g4[P_RZ];
     double res = sqrt(rr0);
@@ -726,56 +746,48 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
 
     while (!(it >= A.maxiter || res <= tol)) {
         const double beta = rho / rho_prev;
+        // ---- p = z + beta p on owned dofs; on halo dofs z comes from the neighbours' pushes of epoch hepoch
         cg_update_p_body(A, gtid, gsz, beta);
-        grid.sync();  // all of p is final on this GPU before anything is pushed
+        for (int64_t h = gtid; h < P.n_halo_dofs; h += gsz)
+            A.p[A.n + h] = ll_load(P.zh + 2 * h, hepoch, P.err) + beta * A.p[A.n + h];
         MG_PROF(0)
-        // ---- halo push: my owned values into the neighbours' p vectors
-        bool pushed = false;
-        for (int k = 0; k < P.n_nbr; ++k) {
-            const long long s0 = P.send_ptr[k], cnt = (P.send_ptr[k + 1] - s0) * BS;
-            double* dst = P.peer_halo[k];
-            for (long long i = gtid; i < cnt; i += gsz) {
-                dst[i] = A.p[(int64_t)P.send_nodes[s0 + i / BS] * BS + (i % BS)];
-                pushed = true;
-            }
-        }
-        if (pushed) __threadfence_system();  // only the threads that stored to a peer need their stores ordered before the flag
         grid.sync();
         MG_PROF(1)
-        ++hepoch;
-        if (blockIdx.x == 0 && threadIdx.x < P.n_nbr) {
-            __threadfence_system();
-            *(volatile unsigned long long*)(P.peer_flags[P.nbr_rank[threadIdx.x]] + P2P_MAXR + P.rank) = hepoch;
-        }
-        if (threadIdx.x < P.n_nbr) p2p_wait(P.flags + P2P_MAXR + P.nbr_rank[threadIdx.x], hepoch, P.err);
-        if (threadIdx.x == 0) __threadfence();  // drop stale L1 lines of the halo part of p
-        __syncthreads();
-        MG_PROF(2)
-
         double d = 0.0;
-        for (int64_t t = gtid, nt = spmv_items<BS>(A); t < nt; t += gsz) d += spmv_item<BS, HCG>(A, t);
+        for (int64_t t = gtid, nt = spmv_items<BS>(A); t < nt; t += gsz) d += spmv_item<BS>(A, t);
         d = block_sum<CG_THREADS>(d, sh);
         if (threadIdx.x == 0) part[P_PAP * ps + blockIdx.x] = d;
-        MG_PROF(3)
+        MG_PROF(2)
         grid.sync();
         double pAp = sum_partials<CG_THREADS>(part + P_PAP * ps, nb, sh);
-        p2p_allreduce<CG_THREADS>(P, &pAp, 1, repoch);
-        MG_PROF(4)
+        p2p_allreduce(P, &pAp, 1, repoch, sh4);
+        MG_PROF(3)
         const double alpha = rho / pAp;
-        double s2[2];
-        cg_update_xr_body(A, gtid, gsz, alpha, s2);
+        // ---- x += alpha p ; r -= alpha Ap ; push z of the interface dofs right away
+        ++hepoch;
+        double s2[2] = {0.0, 0.0};
+        for (int64_t i = gtid; i < A.n; i += gsz) {
+            A.x[i] += alpha * A.p[i];
+            const double ri = A.r[i] - alpha * A.Ap[i];
+            A.r[i] = ri;
+            const double zi = ri * A.dinv[i];
+            s2[0] += ri * ri;
+            s2[1] += ri * zi;
+            if (P.push_ptr[i + 1] > P.push_ptr[i]) p2p_push(P, i, zi, hepoch);
+        }
         const double b0 = block_sum<CG_THREADS>(s2[0], sh);
         const double b1 = block_sum<CG_THREADS>(s2[1], sh);
         if (threadIdx.x == 0) {
             part[P_RR * ps + blockIdx.x] = b0;
             part[P_RZ * ps + blockIdx.x] = b1;
         }
-        MG_PROF(5)
+        MG_PROF(4)
         grid.sync();
         double g2[2];
         g2[0] = sum_partials<CG_THREADS>(part + P_RR * ps, nb, sh);
         g2[1] = sum_partials<CG_THREADS>(part + P_RZ * ps, nb, sh);
-        p2p_allreduce<CG_THREADS>(P, g2, 2, repoch);
+        MG_PROF(5)
+        p2p_allreduce(P, g2, 2, repoch, sh4);
         rho_prev = rho;
         rho = g2[1];
         res = sqrt(g2[0]);
@@ -793,7 +805,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
     if (threadIdx.x == 0) part[P_DD * ps + blockIdx.x] = dd;
     grid.sync();
     dd = sum_partials<CG_THREADS>(part + P_DD * ps, nb, sh);
-    p2p_allreduce<CG_THREADS>(P, &dd, 1, repoch);
+    p2p_allreduce(P, &dd, 1, repoch, sh4);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         CgState* st = A.st;
         st->rho = rho;

@@ -163,7 +163,6 @@ struct onsas_ctx {
     // options
     int cg_mode = 0, asm_minb = 3, check_every = 16, cg_bps = 6;
     int cg_grid = 0, part_stride = 4096;
-    int debug_flags = 0;
 
     // comm
     ncclComm_t comm = nullptr;
@@ -174,10 +173,9 @@ struct onsas_ctx {
     DevBuf<unsigned char> window;
     std::vector<void*> ipc_opened;
     bool p2p_ready = false;
-    DevBuf<int> d_nbr_rank;
-    DevBuf<long long> d_send_ptr;
-    DevBuf<double*> d_peer_halo, d_peer_slots;
-    DevBuf<unsigned long long*> d_peer_flags;
+    std::vector<int32_t> h_send_nodes;
+    DevBuf<long long> d_push_ptr;
+    DevBuf<unsigned long long*> d_push_dst, d_peer_slots;
     int cg_grid_mg = 0;
 
     int64_t n_local_dofs() const { return n_nodes * dim; }
@@ -342,14 +340,13 @@ void allreduce(onsas_ctx* c, double* d, int count) {
     NCCL_CHECK(g_nccl.AllReduce(d, d, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
 }
 
-// ---------------------------------------------------------------- P2P window layout
-constexpr size_t P2P_SLOTS_BYTES = 2 * P2P_MAXR * 4 * sizeof(double);
-constexpr size_t P2P_FLAGS_BYTES = 2 * P2P_MAXR * sizeof(unsigned long long);
-constexpr size_t P2P_HDR_BYTES = ((P2P_SLOTS_BYTES + P2P_FLAGS_BYTES + 2 * sizeof(unsigned long long) + 255) / 256) * 256;
-inline double* win_slots(unsigned char* w) { return reinterpret_cast<double*>(w); }
-inline unsigned long long* win_flags(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_SLOTS_BYTES); }
-inline unsigned long long* win_epochs(unsigned char* w) { return win_flags(w) + 2 * P2P_MAXR; }
-inline double* win_p(unsigned char* w) { return reinterpret_cast<double*>(w + P2P_HDR_BYTES); }
+// ---------------------------------------------------------------- P2P window layout: [slots (LL)][epochs][zh (LL)]
+constexpr size_t P2P_SLOTS_BYTES = 2 * P2P_MAXR * 4 * 16;
+constexpr size_t P2P_HDR_BYTES = 4096;
+static_assert(P2P_SLOTS_BYTES + 16 <= P2P_HDR_BYTES, "window header too small");
+inline unsigned long long* win_slots(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w); }
+inline unsigned long long* win_epochs(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_SLOTS_BYTES); }
+inline unsigned long long* win_zh(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_HDR_BYTES); }
 
 // ---------------------------------------------------------------- CG drivers
 CgArgs make_cg_args(onsas_ctx* c, int precond, double reltol, double abstol, int64_t maxiter, bool use_rhs, int update_U) {
@@ -418,13 +415,8 @@ void run_cg_bs(onsas_ctx* c, CgArgs A) {
     }
     if (c->cg_mode == 0 && c->n_ranks > 1 && c->p2p_ready) {
         // multi-GPU: the same persistent solve with halo pushes and scalar all-reduces over NVLink peer memory
-        void* kern;
-        if (c->debug_flags & 1)  // diagnostics: plain (L1-cached) loads of the halo part of p
-            kern = c->cg_profile ? (void*)cg_persistent_mg<BS, 4, true, false>
-                                 : c->cg_bps >= 6 ? (void*)cg_persistent_mg<BS, 6, false, false> : (void*)cg_persistent_mg<BS, 4, false, false>;
-        else
-            kern = c->cg_profile ? (void*)cg_persistent_mg<BS, 4, true, true>
-                                 : c->cg_bps >= 6 ? (void*)cg_persistent_mg<BS, 6, false, true> : (void*)cg_persistent_mg<BS, 4, false, true>;
+        void* kern = c->cg_profile ? (void*)cg_persistent_mg<BS, 4, true>
+                                   : c->cg_bps >= 6 ? (void*)cg_persistent_mg<BS, 6, false> : (void*)cg_persistent_mg<BS, 4, false>;
         if (c->cg_grid_mg == 0) {
             int bps = 0;
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, CG_THREADS, 0));
@@ -434,15 +426,12 @@ void run_cg_bs(onsas_ctx* c, CgArgs A) {
         P2PArgs P{};
         P.n_ranks = c->n_ranks;
         P.rank = c->rank;
-        P.n_nbr = (int)c->nbr_rank.size();
-        P.nbr_rank = c->d_nbr_rank.p;
-        P.send_ptr = c->d_send_ptr.p;
-        P.send_nodes = c->send_nodes.p;
-        P.peer_halo = c->d_peer_halo.p;
+        P.n_halo_dofs = (long long)(c->n_local_dofs() - c->n_own_dofs());
+        P.push_ptr = c->d_push_ptr.p;
+        P.push_dst = c->d_push_dst.p;
+        P.zh = win_zh(c->window.p);
         P.slots = win_slots(c->window.p);
         P.peer_slots = c->d_peer_slots.p;
-        P.flags = win_flags(c->window.p);
-        P.peer_flags = c->d_peer_flags.p;
         P.epochs = win_epochs(c->window.p);
         P.err = c->err_flag.p;
         void* args[] = {&A, &P};
@@ -611,7 +600,6 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_CG_MODE: require(value == 0 || value == 1, ONSAS_ERR_INVALID_ARG, "cg mode must be 0 or 1"); c->cg_mode = (int)value; break;
             case ONSAS_OPT_ASM_MINBLOCKS: require(value >= 1 && value <= 3, ONSAS_ERR_INVALID_ARG, "min blocks must be 1..3"); c->asm_minb = (int)value; break;
             case ONSAS_OPT_CG_CHECK_EVERY: require(value >= 1 && value <= 4096, ONSAS_ERR_INVALID_ARG, "check_every out of range"); c->check_every = (int)value; break;
-            case ONSAS_OPT_DEBUG_FLAGS: c->debug_flags = (int)value; c->cg_grid_mg = 0; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; c->cg_grid_mg = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; c->cg_grid_mg = 0; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
@@ -799,15 +787,13 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->U.alloc(nl); c->U.zero(s);
         c->Fext.alloc(nl); c->Fext.zero(s);
         c->Fint.alloc(nl); c->Fint.zero(s);
+        c->p.alloc(nl);
+        c->p.zero(s);
         if (c->n_ranks > 1) {
-            // P2P window: fixed-size header (slots, flags, epochs) then p, so that peers can address every part
-            c->window.alloc(P2P_HDR_BYTES + nl * sizeof(double));
+            // P2P window: fixed-size header (scalar slots, epochs) then the LL receive buffer of the halo dofs
+            c->window.alloc(P2P_HDR_BYTES + std::max<size_t>(nl - no, 1) * 16);
             c->window.zero(s);
-            c->p.alias(reinterpret_cast<double*>(c->window.p + P2P_HDR_BYTES), nl);
             c->p2p_ready = false;
-        } else {
-            c->p.alloc(nl);
-            c->p.zero(s);
         }
         c->rhs.alloc(nl); c->rhs.zero(s);
         c->x.alloc(no); c->x.zero(s);
@@ -1132,6 +1118,7 @@ int32_t onsas_set_halo(onsas_ctx* c, int32_t n_nbr, const int32_t* nbr_rank, con
             require(send_nodes[k] >= 0 && send_nodes[k] < c->n_owned, ONSAS_ERR_INVALID_ARG, "send node is not owned");
         require((n_nbr ? recv_ptr[n_nbr] : 0) == c->n_nodes - c->n_owned, ONSAS_ERR_INVALID_ARG,
                 "receive ranges do not cover the halo nodes");
+        c->h_send_nodes.assign(send_nodes, send_nodes + ns);
         c->send_nodes.upload(send_nodes, (size_t)ns, c->stream);
         c->sendbuf.alloc((size_t)std::max<int64_t>(ns, 1) * c->dim);
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1161,13 +1148,13 @@ int32_t onsas_p2p_export(onsas_ctx* c, void* handle64, int64_t* offset) {
     });
 }
 
-int32_t onsas_p2p_import(onsas_ctx* c, const void* handles, const int64_t* offsets, const int64_t* remote_halo_node_off) {
+int32_t onsas_p2p_import(onsas_ctx* c, const void* handles, const int64_t* offsets, const int64_t* remote_halo_off) {
     if (!c || !handles || !offsets) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
         require(c->finalized && c->n_ranks > 1 && c->window.p, ONSAS_ERR_NOT_READY, "window not allocated");
         require(c->n_ranks <= P2P_MAXR, ONSAS_ERR_UNSUPPORTED, "peer-memory CG supports at most 16 ranks");
         const int nn = (int)c->nbr_rank.size();
-        require(nn == 0 || remote_halo_node_off, ONSAS_ERR_INVALID_ARG, "NULL remote halo offsets");
+        require(nn == 0 || remote_halo_off, ONSAS_ERR_INVALID_ARG, "NULL remote halo offsets");
         std::vector<unsigned char*> win(c->n_ranks, nullptr);
         for (int r = 0; r < c->n_ranks; ++r) {
             if (r == c->rank) {
@@ -1181,22 +1168,32 @@ int32_t onsas_p2p_import(onsas_ctx* c, const void* handles, const int64_t* offse
             c->ipc_opened.push_back(base);
             win[r] = (unsigned char*)base + offsets[r];
         }
-        std::vector<double*> slots(c->n_ranks), halo(nn);
-        std::vector<unsigned long long*> flags(c->n_ranks);
-        for (int r = 0; r < c->n_ranks; ++r) {
-            slots[r] = win_slots(win[r]);
-            flags[r] = win_flags(win[r]);
+        std::vector<unsigned long long*> slots(c->n_ranks);
+        for (int r = 0; r < c->n_ranks; ++r) slots[r] = win_slots(win[r]);
+        // push map: for every owned dof the LL slots (in the neighbours' receive buffers) that want its z value
+        const int bs = c->dim;
+        const int64_t nd = c->n_own_dofs();
+        std::vector<long long> pptr(nd + 1, 0);
+        for (int k = 0; k < nn; ++k)
+            for (int64_t j = c->send_ptr[k]; j < c->send_ptr[k + 1]; ++j)
+                for (int q = 0; q < bs; ++q) pptr[(int64_t)c->h_send_nodes[j] * bs + q + 1]++;
+        for (int64_t i = 0; i < nd; ++i) pptr[i + 1] += pptr[i];
+        std::vector<unsigned long long*> pdst((size_t)pptr[nd]);
+        std::vector<long long> fill(pptr.begin(), pptr.end() - 1);
+        for (int k = 0; k < nn; ++k) {
+            unsigned long long* zh = win_zh(win[c->nbr_rank[k]]);
+            for (int64_t j = c->send_ptr[k]; j < c->send_ptr[k + 1]; ++j)
+                for (int q = 0; q < bs; ++q) {
+                    const int64_t i = (int64_t)c->h_send_nodes[j] * bs + q;
+                    const int64_t remote_dof = (remote_halo_off[k] + (j - c->send_ptr[k])) * bs + q;
+                    pdst[fill[i]++] = zh + 2 * remote_dof;
+                }
         }
-        for (int k = 0; k < nn; ++k) halo[k] = win_p(win[c->nbr_rank[k]]) + remote_halo_node_off[k] * c->dim;
-        std::vector<int> nbr(c->nbr_rank.begin(), c->nbr_rank.end());
-        std::vector<long long> sp(c->send_ptr.begin(), c->send_ptr.end());
-        if (sp.empty()) sp.push_back(0);
+        if (pdst.empty()) pdst.push_back(nullptr);
         cudaStream_t s = c->stream;
-        c->d_nbr_rank.upload(nbr, s);
-        c->d_send_ptr.upload(sp, s);
-        c->d_peer_halo.upload(halo, s);
+        c->d_push_ptr.upload(pptr, s);
+        c->d_push_dst.upload(pdst, s);
         c->d_peer_slots.upload(slots, s);
-        c->d_peer_flags.upload(flags, s);
         CUDA_CHECK(cudaStreamSynchronize(s));
         c->p2p_ready = true;
         c->cg_grid_mg = 0;

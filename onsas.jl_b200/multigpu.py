@@ -34,9 +34,9 @@ def make_distributed_context(part, mat_kind, mat_params, dist, local_rank: int, 
         dist.all_gather_object(meta, dict(handle=handle, offset=offset, n_owned=int(part.n_owned),
                                           nbr=[int(r) for r in part.nbr_rank], recv_ptr=[int(v) for v in part.recv_ptr]))
         remote = []
-        for r in part.nbr_rank:          # where my values go inside neighbour r's vector
+        for r in part.nbr_rank:          # where my values start inside neighbour r's halo receive buffer
             m = meta[int(r)]
             j = m["nbr"].index(rank)
-            remote.append(m["n_owned"] + m["recv_ptr"][j])
+            remote.append(m["recv_ptr"][j])
         ctx.p2p_import([m["handle"] for m in meta], [m["offset"] for m in meta], np.asarray(remote, np.int64))
     return ctx

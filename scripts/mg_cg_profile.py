@@ -23,17 +23,16 @@ ctx = multigpu.make_distributed_context(part, [ob.MAT_NEOHOOKEAN], [[bench.KBULK
 loc = lambda v: part.scatter_global(v.reshape(-1, 3)[order].ravel(), 3)  # noqa: E731
 ctx.set_Fext(loc(Fext))
 L = ob._lib
-for bps, prof, dbg in ((6, 0, 0), (4, 1, 0), (6, 0, 1), (4, 1, 1)):
-    ctx.set_option(L.OPT_DEBUG_FLAGS, dbg)
+for bps, prof in ((6, 0), (4, 0), (4, 1)):
     ctx.set_option(L.OPT_CG_BLOCKS_PER_SM, bps)
     ctx.set_option(L.OPT_CG_PROFILE, prof)
     ctx.set_U(loc(U_prev))
     dist.barrier()
     info = ctx.newton_step(ob.PRECOND_JACOBI)
-    line = f"rank {rank} bps={bps} prof={prof} dbg={dbg} cg_iters={info.cg_iters} ms_solve={info.ms_solve:.2f} us/iter={1e3 * info.ms_solve / info.cg_iters:.2f}"
+    line = f"rank {rank} bps={bps} prof={prof} cg_iters={info.cg_iters} ms_solve={info.ms_solve:.2f} us/iter={1e3 * info.ms_solve / info.cg_iters:.2f}"
     if prof:
         p = list(ctx.cg_profile().values())
-        names = ["update_p+sync", "push+fence+sync", "halo_wait", "spmv", "sync+allreduce(pAp)", "update_xr", "sync+allreduce(rr,rz)"]
+        names = ["update_p(+halo)", "sync", "spmv", "sync+allreduce(pAp)", "update_xr+push", "sync+sums", "allreduce(rr,rz)"]
         tot = sum(p)
         line += " | " + " ".join(f"{n}={100 * v / tot:.1f}%" for n, v in zip(names, p)) + f" cycles/iter={tot / info.cg_iters:.0f}"
     print(line, flush=True)
