@@ -753,10 +753,15 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
         MG_PROF(0)
         grid.sync();
         MG_PROF(1)
+        long long tc0 = 0;
+        if constexpr (PROF) tc0 = clock64();
         double d = 0.0;
         for (int64_t t = gtid, nt = spmv_items<BS>(A); t < nt; t += gsz) d += spmv_item<BS>(A, t);
         d = block_sum<CG_THREADS>(d, sh);
         if (threadIdx.x == 0) part[P_PAP * ps + blockIdx.x] = d;
+        if constexpr (PROF) {
+            if (A.prof != nullptr && threadIdx.x == 0) A.prof[8 + blockIdx.x] += clock64() - tc0;  // per-CTA SpMV cycles
+        }
         MG_PROF(2)
         grid.sync();
         double pAp = sum_partials<CG_THREADS>(part + P_PAP * ps, nb, sh);

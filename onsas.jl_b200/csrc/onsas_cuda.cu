@@ -559,7 +559,7 @@ int32_t onsas_create(int32_t device, onsas_ctx** out) {
         c->partials.zero(c->stream);
         c->red.alloc(8);
         c->red.zero(c->stream);
-        c->prof.alloc(8);
+        c->prof.alloc(8 + 4096);
         c->prof.zero(c->stream);
     });
     if (st != ONSAS_OK) {
@@ -1046,9 +1046,14 @@ int32_t onsas_get_cg_profile(onsas_ctx* c, int64_t out[8]) {
     if (!c || !out) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        long long h[8];
-        CUDA_CHECK(cudaMemcpy(h, c->prof.p, sizeof(h), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < 8; ++k) out[k] = h[k];
+        std::vector<long long> h(8 + 4096);
+        CUDA_CHECK(cudaMemcpy(h.data(), c->prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 7; ++k) out[k] = h[k];
+        // [7]: slowest CTA's accumulated SpMV cycles (multi-GPU profiling variant), 0 otherwise
+        long long mx = 0;
+        for (size_t k = 8; k < h.size(); ++k) mx = std::max(mx, h[k]);
+        out[7] = mx;
+        c->prof.zero(c->stream);
     });
 }
 

@@ -215,8 +215,8 @@ class DeviceContext:
     def cg_profile(self) -> dict:
         out = np.zeros(8, np.int64)
         self._check(self._lib.onsas_get_cg_profile(self._h, out))
-        keys = ["update_p", "sync1", "spmv_dot", "sync2", "update_xr", "sync3", "reductions"]
-        return dict(zip(keys, (int(v) for v in out[:7])))
+        keys = ["update_p", "sync1", "spmv_dot", "sync2", "update_xr", "sync3", "reductions", "slowest_cta_spmv"]
+        return dict(zip(keys, (int(v) for v in out[:8])))
 
     # -- multi-GPU
     @staticmethod

@@ -31,10 +31,35 @@ for bps, prof in ((6, 0), (4, 0), (4, 1)):
     info = ctx.newton_step(ob.PRECOND_JACOBI)
     line = f"rank {rank} bps={bps} prof={prof} cg_iters={info.cg_iters} ms_solve={info.ms_solve:.2f} us/iter={1e3 * info.ms_solve / info.cg_iters:.2f}"
     if prof:
-        p = list(ctx.cg_profile().values())
+        pv = ctx.cg_profile()
+        slow = pv.pop("slowest_cta_spmv")
+        p = list(pv.values())
         names = ["update_p(+halo)", "sync", "spmv", "sync+allreduce(pAp)", "update_xr+push", "sync+sums", "allreduce(rr,rz)"]
         tot = sum(p)
-        line += " | " + " ".join(f"{n}={100 * v / tot:.1f}%" for n, v in zip(names, p)) + f" cycles/iter={tot / info.cg_iters:.0f}"
+        line += " | " + " ".join(f"{n}={100 * v / tot:.1f}%" for n, v in zip(names, p)) + f" cycles/iter={tot / info.cg_iters:.0f} slowest_cta_spmv_cycles/iter={slow / info.cg_iters:.0f}"
+    print(line, flush=True)
+dist.barrier()
+# the same local matrix solved by the single-GPU persistent kernel (halo columns present, no communication): isolates
+# the cost of the partition ordering from the cost of the multi-GPU machinery
+c1 = ob.DeviceContext(local_rank)
+c1.set_nodes(part.xyz, part.n_owned)
+c1.set_materials([ob.MAT_NEOHOOKEAN], [[bench.KBULK, bench.MU]])
+c1.set_tets(part.tets)
+c1.set_free_dofs(part.free_dofs, part.n_free_global)
+c1.finalize()
+c1.set_U(loc(U_prev))
+c1.set_Fext(loc(Fext))
+for bps, prof in ((6, 0), (4, 1)):
+    c1.set_option(L.OPT_CG_BLOCKS_PER_SM, bps)
+    c1.set_option(L.OPT_CG_PROFILE, prof)
+    c1.assemble()
+    info = c1.step(ob.PRECOND_JACOBI, cg_maxiter=1000, update_U=False)
+    line = f"rank {rank} LOCAL-ONLY bps={bps} prof={prof} cg_iters={info.cg_iters} us/iter={1e3 * info.ms_solve / info.cg_iters:.2f}"
+    if prof:
+        pv = c1.cg_profile()
+        pv.pop("slowest_cta_spmv")
+        tot = sum(pv.values())
+        line += " | " + " ".join(f"{k}={100 * v / tot:.1f}%" for k, v in pv.items())
     print(line, flush=True)
 dist.barrier()
 dist.destroy_process_group()
