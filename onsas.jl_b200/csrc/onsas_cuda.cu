@@ -1053,6 +1053,12 @@ int32_t onsas_get_cg_profile(onsas_ctx* c, int64_t out[8]) {
         long long mx = 0;
         for (size_t k = 8; k < h.size(); ++k) mx = std::max(mx, h[k]);
         out[7] = mx;
+        if (const char* f = getenv("ONSAS_PROF_DUMP")) {  // diagnostics: per-CTA SpMV cycles of the last profiled solve
+            if (FILE* fp = fopen(f, "w")) {
+                for (size_t k = 8; k < h.size(); ++k) fprintf(fp, "%lld\n", h[k]);
+                fclose(fp);
+            }
+        }
         c->prof.zero(c->stream);
     });
 }

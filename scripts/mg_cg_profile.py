@@ -31,7 +31,9 @@ for bps, prof in ((6, 0), (4, 0), (4, 1)):
     info = ctx.newton_step(ob.PRECOND_JACOBI)
     line = f"rank {rank} bps={bps} prof={prof} cg_iters={info.cg_iters} ms_solve={info.ms_solve:.2f} us/iter={1e3 * info.ms_solve / info.cg_iters:.2f}"
     if prof:
+        os.environ["ONSAS_PROF_DUMP"] = f"gpurun_out/mg_cta_rank{rank}.txt"
         pv = ctx.cg_profile()
+        os.environ.pop("ONSAS_PROF_DUMP")
         slow = pv.pop("slowest_cta_spmv")
         p = list(pv.values())
         names = ["update_p(+halo)", "sync", "spmv", "sync+allreduce(pAp)", "update_xr+push", "sync+sums", "allreduce(rr,rz)"]
