@@ -65,6 +65,7 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_ASM_MINBLOCKS 2 /* register budget of the assembly kernel: 1 = unconstrained, 2 = 128, 3 = 96 registers (default 3 = 3 resident CTAs of 192 threads) */
 #define ONSAS_OPT_CG_CHECK_EVERY 3 /* multi-launch CG: iterations enqueued between host convergence checks (default 16) */
 #define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: resident CTAs per SM the kernel is compiled for: 4, 5 or 6 (default 6); 1-3 shrink the grid */
+#define ONSAS_OPT_FORCE_MG 6         /* diagnostics: set before onsas_finalize_mesh to run the multi-GPU CG kernel with a single rank */
 #define ONSAS_OPT_CG_PROFILE 5       /* 1 = the persistent CG kernel records per-phase SM-clock cycles (onsas_get_cg_profile) */
 
 /* ---------------------------------------------------------------- life cycle */

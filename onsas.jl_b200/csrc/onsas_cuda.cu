@@ -163,6 +163,7 @@ struct onsas_ctx {
     // options
     int cg_mode = 0, asm_minb = 3, check_every = 16, cg_bps = 6;
     int cg_grid = 0, part_stride = 4096;
+    int force_mg = 0;  // diagnostics: run the multi-GPU kernel even with one rank
 
     // comm
     ncclComm_t comm = nullptr;
@@ -407,13 +408,13 @@ int persistent_grid(onsas_ctx* c) {
 template <int BS>
 void run_cg_bs(onsas_ctx* c, CgArgs A) {
     const int64_t n = A.n;
-    if (c->cg_mode == 0 && c->n_ranks == 1) {
+    if (c->cg_mode == 0 && c->n_ranks == 1 && !(c->force_mg && c->p2p_ready)) {
         if (c->cg_grid == 0) c->cg_grid = persistent_grid<BS>(c);
         void* args[] = {&A};
         CUDA_CHECK(cudaLaunchCooperativeKernel(persistent_kernel<BS>(c), dim3(c->cg_grid), dim3(CG_THREADS), args, 0, c->stream));
         return;
     }
-    if (c->cg_mode == 0 && c->n_ranks > 1 && c->p2p_ready) {
+    if (c->cg_mode == 0 && (c->n_ranks > 1 || c->force_mg) && c->p2p_ready) {
         // multi-GPU: the same persistent solve with halo pushes and scalar all-reduces over NVLink peer memory
         void* kern = c->cg_profile ? (void*)cg_persistent_mg<BS, 4, true>
                                    : c->cg_bps >= 6 ? (void*)cg_persistent_mg<BS, 6, false> : (void*)cg_persistent_mg<BS, 4, false>;
@@ -600,6 +601,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_CG_MODE: require(value == 0 || value == 1, ONSAS_ERR_INVALID_ARG, "cg mode must be 0 or 1"); c->cg_mode = (int)value; break;
             case ONSAS_OPT_ASM_MINBLOCKS: require(value >= 1 && value <= 3, ONSAS_ERR_INVALID_ARG, "min blocks must be 1..3"); c->asm_minb = (int)value; break;
             case ONSAS_OPT_CG_CHECK_EVERY: require(value >= 1 && value <= 4096, ONSAS_ERR_INVALID_ARG, "check_every out of range"); c->check_every = (int)value; break;
+            case ONSAS_OPT_FORCE_MG: c->force_mg = value != 0; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; c->cg_grid_mg = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; c->cg_grid_mg = 0; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
@@ -789,7 +791,7 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->Fint.alloc(nl); c->Fint.zero(s);
         c->p.alloc(nl);
         c->p.zero(s);
-        if (c->n_ranks > 1) {
+        if (c->n_ranks > 1 || c->force_mg) {
             // P2P window: fixed-size header (scalar slots, epochs) then the LL receive buffer of the halo dofs
             c->window.alloc(P2P_HDR_BYTES + std::max<size_t>(nl - no, 1) * 16);
             c->window.zero(s);
@@ -1139,7 +1141,7 @@ int32_t onsas_set_halo(onsas_ctx* c, int32_t n_nbr, const int32_t* nbr_rank, con
 int32_t onsas_p2p_export(onsas_ctx* c, void* handle64, int64_t* offset) {
     if (!c || !handle64 || !offset) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
-        require(c->finalized && c->n_ranks > 1 && c->window.p, ONSAS_ERR_NOT_READY,
+        require(c->finalized && c->window.p, ONSAS_ERR_NOT_READY,
                 "onsas_comm_init and onsas_finalize_mesh must precede onsas_p2p_export");
         cudaIpcMemHandle_t h;
         CUDA_CHECK(cudaIpcGetMemHandle(&h, c->window.p));
@@ -1162,7 +1164,7 @@ int32_t onsas_p2p_export(onsas_ctx* c, void* handle64, int64_t* offset) {
 int32_t onsas_p2p_import(onsas_ctx* c, const void* handles, const int64_t* offsets, const int64_t* remote_halo_off) {
     if (!c || !handles || !offsets) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
-        require(c->finalized && c->n_ranks > 1 && c->window.p, ONSAS_ERR_NOT_READY, "window not allocated");
+        require(c->finalized && c->window.p, ONSAS_ERR_NOT_READY, "window not allocated");
         require(c->n_ranks <= P2P_MAXR, ONSAS_ERR_UNSUPPORTED, "peer-memory CG supports at most 16 ranks");
         const int nn = (int)c->nbr_rank.size();
         require(nn == 0 || remote_halo_off, ONSAS_ERR_INVALID_ARG, "NULL remote halo offsets");
