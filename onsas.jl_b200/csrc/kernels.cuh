@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
     long long it = 0;
     const bool profiling = PROF && A.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long tprev = profiling ? clock64() : 0;
-    long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define MG_PROF(k)                          \
     if constexpr (PROF) {                   \
         if (profiling) {                    \
@@ -760,10 +760,11 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
         d = block_sum<CG_THREADS>(d, sh);
         if (threadIdx.x == 0) part[P_PAP * ps + blockIdx.x] = d;
         if constexpr (PROF) {
-            if (A.prof != nullptr && threadIdx.x == 0) A.prof[8 + blockIdx.x] += clock64() - tc0;  // per-CTA SpMV cycles
+            if (A.prof != nullptr && threadIdx.x == 0) A.prof[16 + blockIdx.x] += clock64() - tc0;  // per-CTA SpMV cycles
         }
         MG_PROF(2)
         grid.sync();
+        MG_PROF(7)
         double pAp = sum_partials<CG_THREADS>(part + P_PAP * ps, nb, sh);
         p2p_allreduce(P, &pAp, 1, repoch, sh4);
         MG_PROF(3)
@@ -802,7 +803,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
 #undef MG_PROF
     if constexpr (PROF) {
         if (profiling)
-            for (int k = 0; k < 7; ++k) A.prof[k] = tacc[k];
+            for (int k = 0; k < 8; ++k) A.prof[k] = tacc[k];
     }
 
     double dd = cg_epilogue_body(A, gtid, gsz);

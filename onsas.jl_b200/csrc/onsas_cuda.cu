@@ -560,7 +560,7 @@ int32_t onsas_create(int32_t device, onsas_ctx** out) {
         c->partials.zero(c->stream);
         c->red.alloc(8);
         c->red.zero(c->stream);
-        c->prof.alloc(8 + 4096);
+        c->prof.alloc(16 + 4096);
         c->prof.zero(c->stream);
     });
     if (st != ONSAS_OK) {
@@ -1048,16 +1048,21 @@ int32_t onsas_get_cg_profile(onsas_ctx* c, int64_t out[8]) {
     if (!c || !out) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        std::vector<long long> h(8 + 4096);
+        std::vector<long long> h(16 + 4096);
         CUDA_CHECK(cudaMemcpy(h.data(), c->prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         for (int k = 0; k < 7; ++k) out[k] = h[k];
+        if (h[7] > 0) {  // multi-GPU variant: [3] is split into the grid sync ([7]) and the reduction proper
+            out[3] = h[3];
+            out[6] += 0;
+        }
         // [7]: slowest CTA's accumulated SpMV cycles (multi-GPU profiling variant), 0 otherwise
         long long mx = 0;
-        for (size_t k = 8; k < h.size(); ++k) mx = std::max(mx, h[k]);
+        for (size_t k = 16; k < h.size(); ++k) mx = std::max(mx, h[k]);
         out[7] = mx;
+        if (getenv("ONSAS_PROF_VERBOSE")) fprintf(stderr, "[onsas prof] grid.sync after SpMV: %lld cycles, reduction after it: %lld\n", h[7], h[3]);
         if (const char* f = getenv("ONSAS_PROF_DUMP")) {  // diagnostics: per-CTA SpMV cycles of the last profiled solve
             if (FILE* fp = fopen(f, "w")) {
-                for (size_t k = 8; k < h.size(); ++k) fprintf(fp, "%lld\n", h[k]);
+                for (size_t k = 16; k < h.size(); ++k) fprintf(fp, "%lld\n", h[k]);
                 fclose(fp);
             }
         }

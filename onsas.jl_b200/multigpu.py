@@ -29,7 +29,17 @@ def make_distributed_context(part, mat_kind, mat_params, dist, local_rank: int, 
     ctx.set_halo(part.nbr_rank, part.send_ptr, part.send_nodes, part.recv_ptr)
     ctx.finalize()
     if p2p and world > 1:
-        handle, offset = ctx.p2p_export()
+        # every rank must take the same path: export first, agree on success, then import
+        try:
+            handle, offset = ctx.p2p_export()
+            ok = 1
+        except Exception as ex:  # e.g. CUDA IPC not permitted: the NCCL per-phase CG path still runs on the GPUs
+            handle, offset, ok = b"", 0, 0
+            print(f"[onsas] rank {rank}: peer-memory export failed ({ex}); using the NCCL CG path", flush=True)
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return ctx
         meta = [None] * world
         dist.all_gather_object(meta, dict(handle=handle, offset=offset, n_owned=int(part.n_owned),
                                           nbr=[int(r) for r in part.nbr_rank], recv_ptr=[int(v) for v in part.recv_ptr]))
