@@ -61,7 +61,10 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_PRECOND_JACOBI 1 /* the north-star solver */
 
 /* tuning keys for onsas_set_option */
-#define ONSAS_OPT_CG_MODE 1      /* 0 = one persistent cooperative kernel (default, 1 GPU), 1 = one launch per phase */
+#define ONSAS_OPT_CG_MODE 1      /* 0 = persistent cooperative kernel with K streamed through shared memory by TMA bulk copies (default;
+                                        on N GPUs halo values and partial sums travel over NVLink peer memory),
+                                    1 = one launch per phase (NCCL between the launches when N > 1),
+                                    2 = persistent cooperative kernel with register-fed SpMV (fallback of 0 for very wide rows) */
 #define ONSAS_OPT_ASM_MINBLOCKS 2 /* register budget of the assembly kernel: 1 = unconstrained, 2 = 128, 3 = 96 registers (default 3 = 3 resident CTAs of 192 threads) */
 #define ONSAS_OPT_CG_CHECK_EVERY 3 /* multi-launch CG: iterations enqueued between host convergence checks (default 16) */
 #define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: resident CTAs per SM the kernel is compiled for: 4, 5 or 6 (default 6); 1-3 shrink the grid */

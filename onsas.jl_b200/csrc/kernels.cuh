@@ -5,7 +5,8 @@
 //   k_eval_tets / k_eval_trusses       un-assembled f_e, K_e, sigma, eps (Entities.jl:174-218 contract)
 //   cg_persistent<BS>                  whole Jacobi-PCG solve + residual + update + norms in ONE
 //                                      cooperative launch (NonLinearStaticAnalyses.jl:107-148 and the
-//                                      IterativeSolvers.jl cg! it calls)
+//                                      IterativeSolvers.jl cg! it calls); with N GPUs the same kernel pushes
+//                                      halo values and partial sums into the peers' memory over NVLink
 //   k_cg_* / k_spmv_dot<BS>            the same phases as separate launches (multi-GPU path, where the
 //                                      halo exchange and all-reduce sit between them)
 //
@@ -385,7 +386,7 @@ struct CgArgs {
     const int32_t* col;
     const double* val;
     const int32_t* diag_slot;  // per row: position of the diagonal block in the row
-    const uint8_t* mask;       // 1 = free dof
+    const uint8_t* mask;       // bit 0: free dof; bit 1: interface dof (a neighbour rank needs its value)
     double* x;                 // solution (dU), owned dofs
     double* r;
     double* p;   // search direction, n_local dofs (owned + halo)
@@ -403,6 +404,8 @@ struct CgArgs {
     int part_stride;
     CgState* st;
     long long* prof;    // optional [8]: SM-clock cycles block 0 spent per phase of the persistent kernel (diagnostics)
+    int* err;           // device error flag (3 = a shared-memory stage never arrived)
+    double* p_pad;      // cg_stream: search direction with one 32-byte sector per node (BS = 3: stride 4), owned + halo nodes
 };
 
 // fixed-order block reduction; result valid in every thread
@@ -460,7 +463,7 @@ __device__ __forceinline__ double spmv_item(const CgArgs& A, int64_t t) {
         for (int q = 0; q < BS; ++q) acc += __ldcs(vp + ((int64_t)s * BS * BS + q) * C) * A.p[cnode * BS + q];
     }
     const int64_t i = row * BS + r;
-    const double y = A.mask[i] ? acc : 0.0;
+    const double y = (A.mask[i] & 1) ? acc : 0.0;
     A.Ap[i] = y;
     return A.p[i] * y;
 }
@@ -475,7 +478,7 @@ template <int BS>
 __device__ __forceinline__ void cg_prologue_body(const CgArgs& A, int64_t gtid, int64_t gsz, double s[4]) {
     s[0] = s[1] = s[2] = s[3] = 0.0;
     for (int64_t i = gtid; i < A.n; i += gsz) {
-        const bool m = A.mask[i] != 0;
+        const bool m = (A.mask[i] & 1) != 0;
         double ri = 0.0;
         if (m) ri = A.rhs ? A.rhs[i] : (A.Fext[i] - A.Fint[i]);
         double di = m ? 1.0 : 0.0;
@@ -486,7 +489,7 @@ __device__ __forceinline__ void cg_prologue_body(const CgArgs& A, int64_t gtid, 
         A.dinv[i] = di;
         const double fe = A.Fext ? A.Fext[i] : 0.0, u = A.U ? A.U[i] : 0.0;
         s[P_RR] += ri * ri;
-        s[P_RZ] += ri * ri * di;
+        s[P_RZ] += ri * (ri * di);
         s[P_FF] += fe * fe;
         s[P_UU] += u * u;
     }
@@ -503,7 +506,7 @@ __device__ __forceinline__ void cg_update_xr_body(const CgArgs& A, int64_t gtid,
         const double ri = A.r[i] - alpha * A.Ap[i];
         A.r[i] = ri;
         s[0] += ri * ri;
-        s[1] += ri * ri * A.dinv[i];
+        s[1] += ri * (ri * A.dinv[i]);
     }
 }
 
@@ -518,108 +521,6 @@ __device__ __forceinline__ double cg_epilogue_body(const CgArgs& A, int64_t gtid
 }
 
 constexpr int CG_THREADS = 256;
-
-// The whole linear solve of one Newton iteration in one cooperative launch:
-// residual r = (F_ext - F_int)[free] (StaticStates.jl:113-116), PCG exactly as IterativeSolvers'
-// (P)CGIterable runs it (tolerance = max(reltol*||r0||, abstol), stop when ||r|| <= tol or
-// it >= maxiter), then dU norms and U[free] += dU (NonLinearStaticAnalyses.jl:136-144).
-template <int BS, bool PROF, int MINB>
-__global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double sh[CG_THREADS / 32];
-    const int64_t gtid = blockIdx.x * (int64_t)CG_THREADS + threadIdx.x;
-    const int64_t gsz = gridDim.x * (int64_t)CG_THREADS;
-    const int nb = gridDim.x;
-    double* part = A.partials;
-    const int ps = A.part_stride;
-
-    double s4[4];
-    cg_prologue_body<BS>(A, gtid, gsz, s4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double b = block_sum<CG_THREADS>(s4[k], sh);
-        if (threadIdx.x == 0) part[k * ps + blockIdx.x] = b;
-    }
-    grid.sync();
-    const double rr0 = sum_partials<CG_THREADS>(part + P_RR * ps, nb, sh);
-    const double ff = sum_partials<CG_THREADS>(part + P_FF * ps, nb, sh);
-    const double uu = sum_partials<CG_THREADS>(part + P_UU * ps, nb, sh);
-    double rho = sum_partials<CG_THREADS>(part + P_RZ * ps, nb, sh);
-    double res = sqrt(rr0);
-    const double tol = fmax(A.reltol * res, A.abstol);
-    double rho_prev = 1.0;
-    long long it = 0;
-
-    const bool profiling = PROF && A.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-    long long tprev = profiling ? clock64() : 0;
-    long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};
-#define CG_PROF(k)                         \
-    if constexpr (PROF) {                  \
-        if (profiling) {                   \
-            const long long tn = clock64(); \
-            tacc[k] += tn - tprev;         \
-            tprev = tn;                    \
-        }                                  \
-    }
-    while (!(it >= A.maxiter || res <= tol)) {
-        const double beta = rho / rho_prev;
-        cg_update_p_body(A, gtid, gsz, beta);
-        CG_PROF(0)
-        grid.sync();
-        CG_PROF(1)
-        double d = 0.0;
-        for (int64_t t = gtid, nt = spmv_items<BS>(A); t < nt; t += gsz) d += spmv_item<BS>(A, t);
-        d = block_sum<CG_THREADS>(d, sh);
-        if (threadIdx.x == 0) part[P_PAP * ps + blockIdx.x] = d;
-        CG_PROF(2)
-        grid.sync();
-        CG_PROF(3)
-        const double pAp = sum_partials<CG_THREADS>(part + P_PAP * ps, nb, sh);
-        const double alpha = rho / pAp;
-        double s2[2];
-        cg_update_xr_body(A, gtid, gsz, alpha, s2);
-        const double b0 = block_sum<CG_THREADS>(s2[0], sh);
-        const double b1 = block_sum<CG_THREADS>(s2[1], sh);
-        if (threadIdx.x == 0) {
-            part[P_RR * ps + blockIdx.x] = b0;
-            part[P_RZ * ps + blockIdx.x] = b1;
-        }
-        CG_PROF(4)
-        grid.sync();
-        CG_PROF(5)
-        const double rr = sum_partials<CG_THREADS>(part + P_RR * ps, nb, sh);
-        rho_prev = rho;
-        rho = sum_partials<CG_THREADS>(part + P_RZ * ps, nb, sh);
-        res = sqrt(rr);
-        ++it;
-        CG_PROF(6)
-    }
-#undef CG_PROF
-    if constexpr (PROF) {
-        if (profiling)
-            for (int k = 0; k < 7; ++k) A.prof[k] = tacc[k];
-    }
-
-    double dd = cg_epilogue_body(A, gtid, gsz);
-    dd = block_sum<CG_THREADS>(dd, sh);
-    if (threadIdx.x == 0) part[P_DD * ps + blockIdx.x] = dd;
-    grid.sync();
-    dd = sum_partials<CG_THREADS>(part + P_DD * ps, nb, sh);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        CgState* st = A.st;
-        st->rho = rho;
-        st->rho_prev = rho_prev;
-        st->res = res;
-        st->tol = tol;
-        st->pAp = 0.0;
-        st->rr0 = rr0;
-        st->ff = ff;
-        st->uu = uu;
-        st->dd = dd;
-        st->it = it;
-        st->done = 1;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // multi-GPU persistent PCG over NVLink peer memory (one process per GPU, CUDA IPC)
@@ -672,23 +573,34 @@ __device__ __forceinline__ double ll_load(const unsigned long long* src, unsigne
     return __longlong_as_double((long long)((x & 0xffffffffull) | (y << 32)));
 }
 
-// all-reduce of nv <= 4 doubles across ranks; v[] holds this rank's value (identical in all its CTAs) on entry
-__device__ __forceinline__ void p2p_allreduce(const P2PArgs& P, double* v, int nv, unsigned int& epoch, double* sh4) {
+// all-reduce of NV <= 4 doubles across ranks; v[] holds this rank's value (identical in all its CTAs) on entry.
+// NV is a compile-time constant and the values pass through shared memory, so v[] stays in registers.
+template <int NV>
+__device__ __forceinline__ void p2p_allreduce(const P2PArgs& P, double (&v)[NV], unsigned int& epoch, double* sh4) {
     ++epoch;
     const int par = (int)(epoch & 1u);
     const int t = threadIdx.x;
-    if (blockIdx.x == 0 && t < P.n_ranks * nv) {
-        const int r = t / nv, k = t % nv;
-        ll_store(P.peer_slots[r] + (size_t)((par * P2P_MAXR + P.rank) * 4 + k) * 2, v[k], epoch);
+    if (blockIdx.x == 0) {
+        __syncthreads();  // sh4 free for reuse
+        if (t == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) sh4[k] = v[k];
+        }
+        __syncthreads();
+        if (t < P.n_ranks * NV) {
+            const int r = t / NV, k = t % NV;
+            ll_store(P.peer_slots[r] + (size_t)((par * P2P_MAXR + P.rank) * 4 + k) * 2, sh4[k], epoch);
+        }
     }
-    __syncthreads();  // sh4 free for reuse
-    if (t < nv) {
+    __syncthreads();
+    if (t < NV) {
         double s = 0.0;
         for (int r = 0; r < P.n_ranks; ++r) s += ll_load(P.slots + (size_t)((par * P2P_MAXR + r) * 4 + t) * 2, epoch, P.err);
         sh4[t] = s;
     }
     __syncthreads();
-    for (int k = 0; k < nv; ++k) v[k] = sh4[k];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = sh4[k];
     __syncthreads();
 }
 
@@ -697,8 +609,14 @@ __device__ __forceinline__ void p2p_push(const P2PArgs& P, int64_t i, double z, 
     for (long long q = P.push_ptr[i]; q < P.push_ptr[i + 1]; ++q) ll_store(P.push_dst[q], z, hepoch);
 }
 
-template <int BS, int MINB, bool PROF>
-__global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P2PArgs P) {
+// The whole linear solve of one Newton iteration in one cooperative launch, on 1 GPU or on N:
+// residual r = (F_ext - F_int)[free] (StaticStates.jl:113-116), PCG exactly as IterativeSolvers'
+// (P)CGIterable runs it (tolerance = max(reltol*||r0||, abstol), stop when ||r|| <= tol or
+// it >= maxiter), then dU norms and U[free] += dU (NonLinearStaticAnalyses.jl:136-144).
+// Multi-GPU (P.n_ranks > 0) is a RUN-TIME switch on purpose: the single- and the multi-GPU solve are the same
+// machine code, so the SpMV loop's instruction schedule -- what its HBM throughput lives on -- cannot differ.
+template <int BS, bool PROF, int MINB>
+__global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A, P2PArgs P) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[CG_THREADS / 32];
     __shared__ double sh4[4];
@@ -707,35 +625,42 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
     const int nb = gridDim.x;
     double* part = A.partials;
     const int ps = A.part_stride;
-    unsigned int repoch = (unsigned int)P.epochs[0], hepoch = (unsigned int)P.epochs[1];
+    const bool mg = P.n_ranks > 0;
+    unsigned int repoch = 0, hepoch = 0;
+    if (mg) {
+        repoch = (unsigned int)P.epochs[0];
+        hepoch = (unsigned int)P.epochs[1];
+    }
 
-    // ---- prologue: residual, Jacobi diagonal, norms; first halo push of z = r / d
-    double s4[4];
-    cg_prologue_body<BS>(A, gtid, gsz, s4);
-    ++hepoch;
-    for (int64_t i = gtid; i < A.n; i += gsz)
-        if (P.push_ptr[i + 1] > P.push_ptr[i]) p2p_push(P, i, A.r[i] * A.dinv[i], hepoch);
-    for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) A.p[i] = 0.0;  // halo part of the search direction
+    // ---- prologue: residual, Jacobi diagonal, norms; multi-GPU: first halo push of z = r / d
+    double g4[4];
+    cg_prologue_body<BS>(A, gtid, gsz, g4);
+    if (mg) {
+        ++hepoch;
+        for (int64_t i = gtid; i < A.n; i += gsz)
+            if (A.mask[i] & 2) p2p_push(P, i, A.r[i] * A.dinv[i], hepoch);
+        for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) A.p[i] = 0.0;  // halo part of the search direction
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const double b = block_sum<CG_THREADS>(s4[k], sh);
+        const double b = block_sum<CG_THREADS>(g4[k], sh);
         if (threadIdx.x == 0) part[k * ps + blockIdx.x] = b;
     }
     grid.sync();
-    double g4[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) g4[k] = sum_partials<CG_THREADS>(part + k * ps, nb, sh);
-    p2p_allreduce(P, g4, 4, repoch, sh4);
+    if (mg) p2p_allreduce<4>(P, g4, repoch, sh4);
     const double rr0 = g4[P_RR], ff = g4[P_FF], uu = g4[P_UU];
     double rho = g4[P_RZ];
     double res = sqrt(rr0);
     const double tol = fmax(A.reltol * res, A.abstol);
     double rho_prev = 1.0;
     long long it = 0;
+
     const bool profiling = PROF && A.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     long long tprev = profiling ? clock64() : 0;
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define MG_PROF(k)                          \
+#define CG_PROF(k)                          \
     if constexpr (PROF) {                   \
         if (profiling) {                    \
             const long long tn = clock64(); \
@@ -743,16 +668,17 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
             tprev = tn;                     \
         }                                   \
     }
-
     while (!(it >= A.maxiter || res <= tol)) {
         const double beta = rho / rho_prev;
         // ---- p = z + beta p on owned dofs; on halo dofs z comes from the neighbours' pushes of epoch hepoch
         cg_update_p_body(A, gtid, gsz, beta);
-        for (int64_t h = gtid; h < P.n_halo_dofs; h += gsz)
-            A.p[A.n + h] = ll_load(P.zh + 2 * h, hepoch, P.err) + beta * A.p[A.n + h];
-        MG_PROF(0)
+        if (mg) {
+            for (int64_t h = gtid; h < P.n_halo_dofs; h += gsz)
+                A.p[A.n + h] = ll_load(P.zh + 2 * h, hepoch, P.err) + beta * A.p[A.n + h];
+        }
+        CG_PROF(0)
         grid.sync();
-        MG_PROF(1)
+        CG_PROF(1)
         long long tc0 = 0;
         if constexpr (PROF) tc0 = clock64();
         double d = 0.0;
@@ -760,16 +686,21 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
         d = block_sum<CG_THREADS>(d, sh);
         if (threadIdx.x == 0) part[P_PAP * ps + blockIdx.x] = d;
         if constexpr (PROF) {
-            if (A.prof != nullptr && threadIdx.x == 0) A.prof[16 + blockIdx.x] += clock64() - tc0;  // per-CTA SpMV cycles
+            if (A.prof != nullptr && threadIdx.x == 0) {  // per-CTA SpMV cycles and the SM it runs on (diagnostics)
+                A.prof[16 + blockIdx.x] += clock64() - tc0;
+                unsigned int smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                A.prof[16 + 2048 + blockIdx.x] = smid;
+            }
         }
-        MG_PROF(2)
+        CG_PROF(2)
         grid.sync();
-        MG_PROF(7)
-        double pAp = sum_partials<CG_THREADS>(part + P_PAP * ps, nb, sh);
-        p2p_allreduce(P, &pAp, 1, repoch, sh4);
-        MG_PROF(3)
-        const double alpha = rho / pAp;
-        // ---- x += alpha p ; r -= alpha Ap ; push z of the interface dofs right away
+        CG_PROF(3)
+        double pAp[1] = {sum_partials<CG_THREADS>(part + P_PAP * ps, nb, sh)};
+        if (mg) p2p_allreduce<1>(P, pAp, repoch, sh4);
+        const double alpha = rho / pAp[0];
+        // ---- x += alpha p ; r -= alpha Ap ; multi-GPU: push z of the interface dofs right away, so the exchange
+        //      overlaps the (r.r, r.z) all-reduce
         ++hepoch;
         double s2[2] = {0.0, 0.0};
         for (int64_t i = gtid; i < A.n; i += gsz) {
@@ -779,7 +710,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
             const double zi = ri * A.dinv[i];
             s2[0] += ri * ri;
             s2[1] += ri * zi;
-            if (P.push_ptr[i + 1] > P.push_ptr[i]) p2p_push(P, i, zi, hepoch);
+            if (mg && (A.mask[i] & 2)) p2p_push(P, i, zi, hepoch);
         }
         const double b0 = block_sum<CG_THREADS>(s2[0], sh);
         const double b1 = block_sum<CG_THREADS>(s2[1], sh);
@@ -787,20 +718,19 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
             part[P_RR * ps + blockIdx.x] = b0;
             part[P_RZ * ps + blockIdx.x] = b1;
         }
-        MG_PROF(4)
+        CG_PROF(4)
         grid.sync();
-        double g2[2];
-        g2[0] = sum_partials<CG_THREADS>(part + P_RR * ps, nb, sh);
-        g2[1] = sum_partials<CG_THREADS>(part + P_RZ * ps, nb, sh);
-        MG_PROF(5)
-        p2p_allreduce(P, g2, 2, repoch, sh4);
+        CG_PROF(5)
+        s2[0] = sum_partials<CG_THREADS>(part + P_RR * ps, nb, sh);
+        s2[1] = sum_partials<CG_THREADS>(part + P_RZ * ps, nb, sh);
+        if (mg) p2p_allreduce<2>(P, s2, repoch, sh4);
         rho_prev = rho;
-        rho = g2[1];
-        res = sqrt(g2[0]);
+        rho = s2[1];
+        res = sqrt(s2[0]);
         ++it;
-        MG_PROF(6)
+        CG_PROF(6)
     }
-#undef MG_PROF
+#undef CG_PROF
     if constexpr (PROF) {
         if (profiling)
             for (int k = 0; k < 8; ++k) A.prof[k] = tacc[k];
@@ -810,8 +740,9 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
     dd = block_sum<CG_THREADS>(dd, sh);
     if (threadIdx.x == 0) part[P_DD * ps + blockIdx.x] = dd;
     grid.sync();
-    dd = sum_partials<CG_THREADS>(part + P_DD * ps, nb, sh);
-    p2p_allreduce(P, &dd, 1, repoch, sh4);
+    double dd1[1] = {sum_partials<CG_THREADS>(part + P_DD * ps, nb, sh)};
+    if (mg) p2p_allreduce<1>(P, dd1, repoch, sh4);
+    dd = dd1[0];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         CgState* st = A.st;
         st->rho = rho;
@@ -825,8 +756,391 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent_mg(CgArgs A, P
         st->dd = dd;
         st->it = it;
         st->done = 1;
-        P.epochs[0] = repoch;
-        P.epochs[1] = hepoch;
+        if (mg) {
+            P.epochs[0] = repoch;
+            P.epochs[1] = hepoch;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cg_stream: the persistent PCG with K streamed through shared memory by the TMA engine (cp.async.bulk)
+// ------------------------------------------------------------------------------------------------
+// Why: the register-fed SpMV above keeps only a handful of 8-byte loads in flight per thread, so its HBM
+// throughput hangs on occupancy and on how ptxas happens to schedule the loop (measured: 48..115 us per CG
+// iteration for functionally identical variants).  Here ONE CTA per SM runs N_CW consumer warps and one producer
+// warp.  A consumer warp owns a private ring of DEPTH shared-memory slots; a slot holds the contiguous BSELL image
+// of one slice (values + column ids, 9.1 KB on the structured tet mesh).  Lane w of the producer warp feeds
+// consumer warp w: it waits on the slot's "empty" mbarrier, arms the "full" mbarrier with the byte count and
+// issues two bulk copies (UBLKCP) that complete on it.  ~110-150 KB per SM are in flight whatever the compute
+// warps do, and no register is spent on it.  Consumers never meet at a block barrier inside the SpMV: each waits
+// for its own slice, reads K from shared memory (conflict-free: lane = (row of the slice, quarter of its blocks)),
+// gathers p with one 32-byte load per block column from a sector-padded copy of p, reduces the four partial row
+// sums with two xor-shuffles and releases the slot.
+//   * slices are dealt round-robin (slice = (cta + k*grid) * N_CW + warp), so every CTA sweeps all of K's range;
+//   * the rings keep running ACROSS CG iterations: the producer is always DEPTH fills ahead, so the first slices
+//     of the next SpMV land while the vector updates and reductions of this iteration execute;
+//   * K's lines carry an L2 evict_first hint: the CG vectors, which are re-read within an iteration, stay in L2;
+//   * a row's blocks are summed in 4 interleaved partial sums -- a fixed order, so the solve stays bitwise
+//     reproducible (it differs in rounding from the 1-thread-per-row order of the other drivers);
+//   * multi-GPU (P.n_ranks > 0) is a run-time switch: same machine code on 1 and on N GPUs.
+struct StreamArgs {
+    int n_cw;         // consumer warps (<= ST_MAX_CW)
+    int depth;        // ring slots per consumer warp (2..4)
+    int slot_blocks;  // capacity of a slot in blocks (widest slice)
+    long long n_slices;
+};
+
+constexpr int ST_MAX_CW = 12;
+constexpr int ST_MAX_DEPTH = 4;
+
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// wait with a watchdog: a lost copy / a stuck consumer raises *err = 3 instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
+    if (mbar_try_wait(bar, parity)) return;
+    if (*(volatile int*)err == 3) return;  // already failing: do not wait again
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) {
+            *(volatile int*)err = 3;
+            return;
+        }
+    }
+}
+// K is read once per CG iteration and is larger than L2: its lines are marked evict_first so that the CG vectors
+// (which ARE re-read within an iteration) keep their place in L2
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// p of one node from the padded search direction: a single sector, a single load instruction
+template <int BS>
+__device__ __forceinline__ void ld_node(const double* pn, double (&v)[BS]) {
+    if constexpr (BS == 3) {
+        double pad;
+        asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(pad) : "l"(pn));
+    } else if constexpr (BS == 2) {
+        asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(pn));
+    } else {
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(v[0]) : "l"(pn));
+    }
+}
+
+// CW = consumer warps the instantiation is compiled for (8: 288 threads, 224 registers; 12: 416 threads, 152 registers)
+template <int BS, int CW>
+__global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamArgs S, P2PArgs P) {
+    constexpr int ST_THREADS = (CW + 1) * 32;
+    constexpr int VB = CW > 8 ? 5 : 8;  // dofs per thread and batch in the vector phases (register budget: 152 vs 224)
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ double sh[ST_THREADS / 32];
+    __shared__ double sh4[4];
+    __shared__ __align__(8) uint64_t full[ST_MAX_CW][ST_MAX_DEPTH], empty[ST_MAX_CW][ST_MAX_DEPTH];
+    __shared__ int s_width[ST_MAX_CW][ST_MAX_DEPTH];  // blocks per row of the slice sitting in a slot
+    constexpr int BB = BS * BS;
+    constexpr int PS = BS == 3 ? 4 : BS;  // stride of a node in the padded search direction
+    const int tid = threadIdx.x;
+    const int64_t gtid = blockIdx.x * (int64_t)ST_THREADS + tid;
+    const int64_t gsz = gridDim.x * (int64_t)ST_THREADS;
+    const int nb = gridDim.x;
+    double* part = A.partials;
+    const int ps = A.part_stride;
+    const bool mg = P.n_ranks > 0;
+    unsigned int repoch = 0, hepoch = 0;
+    if (mg) {
+        repoch = (unsigned int)P.epochs[0];
+        hepoch = (unsigned int)P.epochs[1];
+    }
+    auto pad_of = [](int64_t i) -> int64_t { return BS == 3 ? (i / 3) * 4 + (i % 3) : i; };  // dof -> index in p_pad
+    const bool profiling = A.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long tprev = 0;
+    auto prof = [&](int k) {
+        if (profiling) {
+            const long long tn = clock64();
+            A.prof[k] += tn - tprev;
+            tprev = tn;
+        }
+    };
+
+    // ---- the rings
+    const int w = tid >> 5, lane = tid & 31;
+    const int NCW = S.n_cw, D = S.depth;
+    const bool is_producer = w == CW;                  // last warp; its lane l feeds consumer warp l
+    const int cw = is_producer ? lane : w;             // consumer warp this thread consumes for / produces for
+    const bool active = cw < NCW && (!is_producer || lane < NCW);
+    const size_t val_bytes = (size_t)S.slot_blocks * BB * C * sizeof(double);
+    const size_t slot_bytes = val_bytes + (size_t)S.slot_blocks * C * sizeof(int32_t);
+    // slices of consumer warp cw in this CTA: (blockIdx + k*grid) * NCW + cw, k = 0 .. n_my-1
+    const long long first = (long long)blockIdx.x * NCW + cw, step = (long long)gridDim.x * NCW;
+    const int n_my = active && first < S.n_slices ? (int)((S.n_slices - 1 - first) / step) + 1 : 0;
+    if (tid == 0) {
+        for (int a = 0; a < ST_MAX_CW; ++a)
+            for (int k = 0; k < ST_MAX_DEPTH; ++k) {
+                mbar_init(&full[a][k], 1);
+                mbar_init(&empty[a][k], 1);
+            }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t pol_stream = l2_policy_evict_first();
+    // producer lane: fill number f of its consumer warp -> slice first + (f mod n_my) * step, slot f mod D
+    int64_t nx_b0 = 0, nx_b1 = 0;  // producer lane: block range of the NEXT fill's slice, fetched one fill ahead
+    auto prefetch_range = [&](long long f) {
+        const long long sl = first + (f % n_my) * step;
+        nx_b0 = A.slice_ptr[sl];
+        nx_b1 = A.slice_ptr[sl + 1];
+    };
+    auto fill = [&](long long f) {
+        const int slot = (int)(f % D);
+        const int64_t b0 = nx_b0;
+        const uint32_t nblk = (uint32_t)(nx_b1 - nx_b0);
+        prefetch_range(f + 1);
+        unsigned char* dst = dyn + ((size_t)cw * D + slot) * slot_bytes;
+        s_width[cw][slot] = (int)nblk;
+        mbar_expect_tx(&full[cw][slot], nblk * (uint32_t)(BB * C * sizeof(double) + C * sizeof(int32_t)));  // release: s_width is visible to the waiters
+        if (nblk) {
+            bulk_g2s(dst, A.val + b0 * BB * C, nblk * (uint32_t)(BB * C * sizeof(double)), &full[cw][slot], pol_stream);
+            bulk_g2s(dst + val_bytes, A.col + b0 * C, nblk * (uint32_t)(C * sizeof(int32_t)), &full[cw][slot], pol_stream);
+        }
+    };
+    long long f_next = 0;   // producer lane: next fill to issue
+    long long q_done = 0;   // consumer warp: fills consumed so far
+    if (is_producer && n_my > 0) {
+        prefetch_range(0);
+        for (; f_next < D; ++f_next) fill(f_next);
+    }
+
+    // ---- prologue: residual, Jacobi diagonal, norms; multi-GPU: first halo push of z = r / d
+    double g4[4];
+    cg_prologue_body<BS>(A, gtid, gsz, g4);
+    if (mg) {
+        ++hepoch;
+        for (int64_t i = gtid; i < A.n; i += gsz)
+            if (A.mask[i] & 2) p2p_push(P, i, A.r[i] * A.dinv[i], hepoch);
+    }
+    for (int64_t i = gtid, np = ((A.n + (mg ? P.n_halo_dofs : 0)) / BS) * PS; i < np; i += gsz) A.p_pad[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double b = block_sum<ST_THREADS>(g4[k], sh);
+        if (tid == 0) part[k * ps + blockIdx.x] = b;
+    }
+    grid.sync();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g4[k] = sum_partials<ST_THREADS>(part + k * ps, nb, sh);
+    if (mg) p2p_allreduce<4>(P, g4, repoch, sh4);
+    const double rr0 = g4[P_RR], ff = g4[P_FF], uu = g4[P_UU];
+    double rho = g4[P_RZ];
+    double res = sqrt(rr0);
+    const double tol = fmax(A.reltol * res, A.abstol);
+    double rho_prev = 1.0;
+    long long it = 0;
+    if (profiling) tprev = clock64();
+
+    const int lrow = lane & 7, qpart = lane >> 3;
+    while (!(it >= A.maxiter || res <= tol)) {
+        // ---- p = z + beta p (owned dofs; halo dofs from the neighbours' pushes of epoch hepoch)
+        {
+            const double beta = rho / rho_prev;
+            const double* __restrict__ rv = A.r;
+            const double* __restrict__ dv = A.dinv;
+            double* __restrict__ pv = A.p_pad;
+            // one CTA per SM: batches of VB independent dofs per thread keep enough loads in flight
+            for (int64_t i0 = gtid; i0 < A.n; i0 += VB * gsz) {
+                double a[VB], b[VB], c[VB];
+#pragma unroll
+                for (int u = 0; u < VB; ++u) {  // loads of a batch first (tail lanes re-read the last dof: no branches)
+                    const int64_t i = i0 + u * gsz < A.n ? i0 + u * gsz : A.n - 1;
+                    a[u] = rv[i];
+                    b[u] = dv[i];
+                    c[u] = pv[pad_of(i)];
+                }
+#pragma unroll
+                for (int u = 0; u < VB; ++u) {
+                    const int64_t i = i0 + u * gsz;
+                    if (i < A.n) pv[pad_of(i)] = a[u] * b[u] + beta * c[u];
+                }
+            }
+            if (mg) {
+                for (int64_t h = gtid; h < P.n_halo_dofs; h += gsz) {
+                    const int64_t j = pad_of(A.n + h);
+                    pv[j] = ll_load(P.zh + 2 * h, hepoch, P.err) + beta * pv[j];
+                }
+            }
+        }
+        prof(0);
+        grid.sync();
+        prof(1);
+        // ---- Ap = K p from the shared-memory rings, partial p.Ap
+        double d = 0.0;
+        if (is_producer) {
+            // stay DEPTH fills ahead: n_my fills per SpMV phase, each as soon as its slot has been released
+            if (n_my > 0)
+                for (int k = 0; k < n_my; ++k, ++f_next) {
+                    mbar_wait(&empty[cw][f_next % D], (uint32_t)((f_next / D - 1) & 1), A.err);
+                    fill(f_next);
+                }
+        } else if (n_my > 0) {
+            const long long tc0 = A.prof != nullptr ? clock64() : 0;
+            for (int k = 0; k < n_my; ++k, ++q_done) {
+                const int slot = (int)(q_done % D);
+                mbar_wait(&full[cw][slot], (uint32_t)((q_done / D) & 1), A.err);
+                const int width = s_width[cw][slot];
+                const unsigned char* stg = dyn + ((size_t)cw * D + slot) * slot_bytes;
+                const double* sv = reinterpret_cast<const double*>(stg) + lrow;
+                const int32_t* sc = reinterpret_cast<const int32_t*>(stg + val_bytes) + lrow;
+                const int64_t row = (first + k * step) * C + lrow;
+                const bool own = qpart == 0 && row < A.n_rows;
+                double po[BS];  // the row's own p (for p.Ap), fetched in the same round trip as the gathers
+#pragma unroll
+                for (int r = 0; r < BS; ++r) po[r] = 0.0;
+                if (own) ld_node<BS>(A.p_pad + row * PS, po);
+                double acc[BS];
+#pragma unroll
+                for (int r = 0; r < BS; ++r) acc[r] = 0.0;
+#pragma unroll 4
+                for (int blk = qpart; blk < width; blk += 4) {
+                    const int64_t cn = sc[blk * C];
+                    double pv[BS];
+                    ld_node<BS>(A.p_pad + cn * PS, pv);
+#pragma unroll
+                    for (int r = 0; r < BS; ++r)
+#pragma unroll
+                        for (int q = 0; q < BS; ++q) acc[r] += sv[(blk * BB + r * BS + q) * C] * pv[q];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[cw][slot]);  // every lane has read its part of the slot: release it
+#pragma unroll
+                for (int r = 0; r < BS; ++r) {
+                    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 8);
+                    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 16);
+                }
+                if (own) {  // rows of fixed dofs are not masked here: p is zero there and the update phase skips them
+#pragma unroll
+                    for (int r = 0; r < BS; ++r) {
+                        A.Ap[row * BS + r] = acc[r];
+                        d += po[r] * acc[r];
+                    }
+                }
+            }
+            if (A.prof != nullptr && lane == 0) A.prof[16 + blockIdx.x * CW + w] += clock64() - tc0;  // per-warp SpMV cycles (diagnostics)
+        }
+        d = block_sum<ST_THREADS>(d, sh);
+        if (tid == 0) part[P_PAP * ps + blockIdx.x] = d;
+        prof(2);
+        grid.sync();
+        prof(3);
+        if (*(volatile int*)A.err == 3) break;  // a stage never arrived (set before the barrier, so every CTA sees it)
+        double pAp[1] = {sum_partials<ST_THREADS>(part + P_PAP * ps, nb, sh)};
+        if (mg) p2p_allreduce<1>(P, pAp, repoch, sh4);
+        const double alpha = rho / pAp[0];
+        // ---- x += alpha p ; r -= alpha Ap ; multi-GPU: push z of the interface dofs right away
+        ++hepoch;
+        double s2[2] = {0.0, 0.0};
+        {
+            double* __restrict__ xv = A.x;
+            double* __restrict__ rv = A.r;
+            const double* __restrict__ pv = A.p_pad;
+            const double* __restrict__ av = A.Ap;
+            const double* __restrict__ dv = A.dinv;
+            for (int64_t i0 = gtid; i0 < A.n; i0 += VB * gsz) {
+                double x[VB], pp[VB], rr[VB], ap[VB], di[VB];
+#pragma unroll
+                for (int u = 0; u < VB; ++u) {
+                    const int64_t i = i0 + u * gsz < A.n ? i0 + u * gsz : A.n - 1;
+                    x[u] = xv[i];
+                    pp[u] = pv[pad_of(i)];
+                    rr[u] = rv[i];
+                    ap[u] = av[i];
+                    di[u] = dv[i];
+                }
+#pragma unroll
+                for (int u = 0; u < VB; ++u) {
+                    const int64_t i = i0 + u * gsz;
+                    if (i < A.n) {
+                        xv[i] = x[u] + alpha * pp[u];
+                        const double ri = di[u] != 0.0 ? rr[u] - alpha * ap[u] : 0.0;  // fixed dofs: d = 0 (the SpMV does not mask)
+                        rv[i] = ri;
+                        const double zi = ri * di[u];
+                        s2[0] += ri * ri;
+                        s2[1] += ri * zi;
+                        if (mg && (A.mask[i] & 2)) p2p_push(P, i, zi, hepoch);
+                    }
+                }
+            }
+        }
+        const double b0 = block_sum<ST_THREADS>(s2[0], sh);
+        const double b1 = block_sum<ST_THREADS>(s2[1], sh);
+        if (tid == 0) {
+            part[P_RR * ps + blockIdx.x] = b0;
+            part[P_RZ * ps + blockIdx.x] = b1;
+        }
+        prof(4);
+        grid.sync();
+        prof(5);
+        s2[0] = sum_partials<ST_THREADS>(part + P_RR * ps, nb, sh);
+        s2[1] = sum_partials<ST_THREADS>(part + P_RZ * ps, nb, sh);
+        if (mg) p2p_allreduce<2>(P, s2, repoch, sh4);
+        rho_prev = rho;
+        rho = s2[1];
+        res = sqrt(s2[0]);
+        ++it;
+        prof(6);
+    }
+    // drain the copies that are still in flight before the shared memory goes away
+    if (!is_producer && n_my > 0)
+        for (int k = 0; k < D; ++k, ++q_done) mbar_wait(&full[cw][q_done % D], (uint32_t)((q_done / D) & 1), A.err);
+
+    double dd = cg_epilogue_body(A, gtid, gsz);
+    dd = block_sum<ST_THREADS>(dd, sh);
+    if (tid == 0) part[P_DD * ps + blockIdx.x] = dd;
+    grid.sync();
+    double dd1[1] = {sum_partials<ST_THREADS>(part + P_DD * ps, nb, sh)};
+    if (mg) p2p_allreduce<1>(P, dd1, repoch, sh4);
+    if (blockIdx.x == 0 && tid == 0) {
+        CgState* st = A.st;
+        st->rho = rho;
+        st->rho_prev = rho_prev;
+        st->res = res;
+        st->tol = tol;
+        st->pAp = 0.0;
+        st->rr0 = rr0;
+        st->ff = ff;
+        st->uu = uu;
+        st->dd = dd1[0];
+        st->it = it;
+        st->done = 1;
+        if (mg) {
+            P.epochs[0] = repoch;
+            P.epochs[1] = hepoch;
+        }
     }
 }
 

@@ -144,7 +144,7 @@ struct onsas_ctx {
     MeshTables tab;
 
     // device
-    DevBuf<double> X, U, Fext, Fint, val, x, r, p, Ap, dinv, rhs, partials, red, tet_out, truss_out, area, mat_params;
+    DevBuf<double> X, U, Fext, Fint, val, x, r, p, p_pad, Ap, dinv, rhs, partials, red, tet_out, truss_out, area, mat_params;
     DevBuf<int32_t> tets, tet_mat, trusses, truss_mat, mat_kind, col, diag_slot, pair_code[2], pair_nodes[2], send_nodes;
     DevBuf<int64_t> slice_ptr;
     DevBuf<SliceHdr> hdr[2];
@@ -163,6 +163,12 @@ struct onsas_ctx {
     // options
     int cg_mode = 0, asm_minb = 3, check_every = 16, cg_bps = 6;
     int cg_grid = 0, part_stride = 4096;
+    struct StreamPlan {
+        bool built = false, ok = false;
+        int n_cw = 0, depth = 0, grid = 0, threads = 0;
+        void* kern = nullptr;
+        size_t smem = 0;
+    } st_plan;
     int force_mg = 0;  // diagnostics: run the multi-GPU kernel even with one rank
 
     // comm
@@ -175,9 +181,10 @@ struct onsas_ctx {
     std::vector<void*> ipc_opened;
     bool p2p_ready = false;
     std::vector<int32_t> h_send_nodes;
+    std::vector<uint8_t> h_iface;  // per owned dof: 1 = a neighbour rank needs its value (mask bit 1 on the device)
     DevBuf<long long> d_push_ptr;
     DevBuf<unsigned long long*> d_push_dst, d_peer_slots;
-    int cg_grid_mg = 0;
+
 
     int64_t n_local_dofs() const { return n_nodes * dim; }
     int64_t n_own_dofs() const { return n_owned * dim; }
@@ -212,6 +219,15 @@ int32_t guard(onsas_ctx* ctx, F&& f) {
 
 void require(bool cond, int code, const char* msg) {
     if (!cond) throw OnsasError(code, msg);
+}
+
+// device mask = bit 0: free dof (onsas_set_free_dofs), bit 1: interface dof (onsas_p2p_import)
+void upload_mask(onsas_ctx* c) {
+    std::vector<uint8_t> m(c->h_mask);
+    for (size_t i = 0; i < c->h_iface.size() && i < m.size(); ++i)
+        if (c->h_iface[i]) m[i] |= 2;
+    c->mask.upload(m, c->stream);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
 // ---------------------------------------------------------------- assembly launch
@@ -377,6 +393,8 @@ CgArgs make_cg_args(onsas_ctx* c, int precond, double reltol, double abstol, int
     A.part_stride = c->part_stride;
     A.st = c->st.p;
     A.prof = c->cg_profile ? c->prof.p : nullptr;
+    A.err = c->err_flag.p;
+    A.p_pad = c->p_pad.p;
     return A;
 }
 
@@ -405,26 +423,10 @@ int persistent_grid(onsas_ctx* c) {
     return std::min(g, c->part_stride);
 }
 
-template <int BS>
-void run_cg_bs(onsas_ctx* c, CgArgs A) {
-    const int64_t n = A.n;
-    if (c->cg_mode == 0 && c->n_ranks == 1 && !(c->force_mg && c->p2p_ready)) {
-        if (c->cg_grid == 0) c->cg_grid = persistent_grid<BS>(c);
-        void* args[] = {&A};
-        CUDA_CHECK(cudaLaunchCooperativeKernel(persistent_kernel<BS>(c), dim3(c->cg_grid), dim3(CG_THREADS), args, 0, c->stream));
-        return;
-    }
-    if (c->cg_mode == 0 && (c->n_ranks > 1 || c->force_mg) && c->p2p_ready) {
-        // multi-GPU: the same persistent solve with halo pushes and scalar all-reduces over NVLink peer memory
-        void* kern = c->cg_profile ? (void*)cg_persistent_mg<BS, 4, true>
-                                   : c->cg_bps >= 6 ? (void*)cg_persistent_mg<BS, 6, false> : (void*)cg_persistent_mg<BS, 4, false>;
-        if (c->cg_grid_mg == 0) {
-            int bps = 0;
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, CG_THREADS, 0));
-            require(bps > 0, ONSAS_ERR_CUDA, "multi-GPU persistent CG kernel does not fit on an SM");
-            c->cg_grid_mg = std::min(bps * c->n_sm, c->part_stride);
-        }
-        P2PArgs P{};
+// ---------------------------------------------------------------- streamed persistent CG (cg_stream): plan + launch
+P2PArgs make_p2p_args(onsas_ctx* c) {
+    P2PArgs P{};  // n_ranks = 0: single GPU
+    if ((c->n_ranks > 1 || c->force_mg) && c->p2p_ready) {
         P.n_ranks = c->n_ranks;
         P.rank = c->rank;
         P.n_halo_dofs = (long long)(c->n_local_dofs() - c->n_own_dofs());
@@ -435,8 +437,81 @@ void run_cg_bs(onsas_ctx* c, CgArgs A) {
         P.peer_slots = c->d_peer_slots.p;
         P.epochs = win_epochs(c->window.p);
         P.err = c->err_flag.p;
+    }
+    return P;
+}
+
+// Ring geometry of cg_stream: a slot holds the widest slice.  Preferred: 12 consumer warps x 2 slots (one slice per
+// warp in flight while it computes on the other); fewer warps for wide rows.  Returns false when not even
+// one warp with two slots fits: the register-fed kernel runs then.
+template <int BS>
+bool plan_stream(onsas_ctx* c) {
+    if (c->st_plan.built) return c->st_plan.ok;
+    c->st_plan.built = true;
+    c->st_plan.ok = false;
+    if (c->tab.n_slices == 0 || c->tab.max_width <= 0) return false;
+    int optin = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    const size_t budget = (size_t)optin - 3072;  // static shared memory of the kernel + slack
+    const size_t slot_bytes = (size_t)(BS * BS * 8 + 4) * SLICE_ROWS * (size_t)c->tab.max_width;
+    const int slots = (int)(budget / slot_bytes);
+    if (slots < 2) return false;
+    // measured on the 1 M-tet cube (scripts/cg_stream_probe.py): 12 warps x 2 slots 47.8 us / CG iteration, 8 x 3 52.8 us
+    int cw_max = 12, want_depth = 2;
+    if (const char* e = getenv("ONSAS_STREAM_CW")) cw_max = atoi(e) >= 12 ? 12 : 8;  // experiment knobs
+    if (const char* e = getenv("ONSAS_STREAM_DEPTH")) want_depth = std::max(2, std::min(ST_MAX_DEPTH, atoi(e)));
+    int depth = std::min(want_depth, slots);
+    int n_cw = std::min(cw_max, slots / depth);
+    if (n_cw < cw_max && depth > 2) {  // wide rows: rather keep the warps and give each two slots
+        depth = 2;
+        n_cw = std::min(cw_max, slots / 2);
+    }
+    const size_t smem = slot_bytes * (size_t)n_cw * depth;
+    void* kern = cw_max == 12 ? (void*)cg_stream<BS, 12> : (void*)cg_stream<BS, 8>;
+    const int threads = (cw_max + 1) * 32;
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) return false;
+    c->st_plan.kern = kern;
+    c->st_plan.threads = threads;
+    c->st_plan.n_cw = n_cw;
+    c->st_plan.depth = depth;
+    c->st_plan.smem = smem;
+    c->st_plan.grid = std::min(c->n_sm, c->part_stride);
+    c->st_plan.ok = true;
+    if (getenv("ONSAS_VERBOSE"))
+        fprintf(stderr, "[onsas] streamed CG: %d CTAs x (%d consumer warps + 1 producer warp), %d slots of %.1f KB per warp, %.1f KB of shared memory\n",
+                c->st_plan.grid, n_cw, depth, slot_bytes / 1024.0, smem / 1024.0);
+    return true;
+}
+
+template <int BS>
+void launch_stream(onsas_ctx* c, CgArgs A) {
+    StreamArgs S{};
+    S.n_cw = c->st_plan.n_cw;
+    S.depth = c->st_plan.depth;
+    S.slot_blocks = c->tab.max_width;
+    S.n_slices = c->tab.n_slices;
+    P2PArgs P = make_p2p_args(c);
+    void* args[] = {&A, &S, &P};
+    CUDA_CHECK(cudaLaunchCooperativeKernel(c->st_plan.kern, dim3(c->st_plan.grid), dim3(c->st_plan.threads), args, c->st_plan.smem, c->stream));
+}
+
+template <int BS>
+void run_cg_bs(onsas_ctx* c, CgArgs A) {
+    const int64_t n = A.n;
+    // persistent solver: single GPU, or N GPUs once the peer-memory window is imported; without the window a
+    // multi-rank solve runs the multi-launch driver below (NCCL between the phases)
+    if (c->cg_mode != 1 && (c->n_ranks == 1 || c->p2p_ready)) {
+        if (c->cg_mode == 0 && plan_stream<BS>(c)) {
+            launch_stream<BS>(c, A);
+            return;
+        }
+        if (c->cg_grid == 0) c->cg_grid = persistent_grid<BS>(c);
+        P2PArgs P = make_p2p_args(c);
         void* args[] = {&A, &P};
-        CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(c->cg_grid_mg), dim3(CG_THREADS), args, 0, c->stream));
+        CUDA_CHECK(cudaLaunchCooperativeKernel(persistent_kernel<BS>(c), dim3(c->cg_grid), dim3(CG_THREADS), args, 0, c->stream));
         return;
     }
     // one launch per phase; collectives in-stream between them
@@ -494,6 +569,7 @@ void check_deferred(onsas_ctx* c) {
         c->err_flag.zero(c->stream);
         *c->h_flag = 0;
         if (f == 2) throw OnsasError(ONSAS_ERR_COMM, "peer-memory CG: timed out waiting for another rank");
+        if (f == 3) throw OnsasError(ONSAS_ERR_CUDA, "streamed CG: a shared-memory stage of K never arrived");
         throw OnsasError(ONSAS_ERR_NEGATIVE_VOLUME, "Element with negative volume, check connectivity.");
     }
 }
@@ -598,12 +674,12 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
         switch (key) {
-            case ONSAS_OPT_CG_MODE: require(value == 0 || value == 1, ONSAS_ERR_INVALID_ARG, "cg mode must be 0 or 1"); c->cg_mode = (int)value; break;
+            case ONSAS_OPT_CG_MODE: require(value >= 0 && value <= 2, ONSAS_ERR_INVALID_ARG, "cg mode must be 0, 1 or 2"); c->cg_mode = (int)value; break;
             case ONSAS_OPT_ASM_MINBLOCKS: require(value >= 1 && value <= 3, ONSAS_ERR_INVALID_ARG, "min blocks must be 1..3"); c->asm_minb = (int)value; break;
             case ONSAS_OPT_CG_CHECK_EVERY: require(value >= 1 && value <= 4096, ONSAS_ERR_INVALID_ARG, "check_every out of range"); c->check_every = (int)value; break;
             case ONSAS_OPT_FORCE_MG: c->force_mg = value != 0; break;
-            case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; c->cg_grid_mg = 0; break;
-            case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; c->cg_grid_mg = 0; break;
+            case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
+            case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
         }
     });
@@ -686,10 +762,7 @@ int32_t onsas_set_free_dofs(onsas_ctx* c, int64_t n_free, const int64_t* free_do
         c->n_free = n_free;
         c->n_free_global = n_free_global > 0 ? n_free_global : n_free;
         c->have_free = true;
-        if (c->finalized) {
-            c->mask.upload(c->h_mask, c->stream);
-            CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        }
+        if (c->finalized) upload_mask(c);
     });
 }
 
@@ -773,6 +846,7 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->trusses.upload(c->h_trusses, s);
         if (c->truss_has_mat) c->truss_mat.upload(c->h_truss_mat, s);
         c->area.upload(c->h_area, s);
+        c->h_iface.clear();
         c->mask.upload(c->h_mask, s);
         c->slice_ptr.upload(c->tab.slice_ptr, s);
         c->col.upload(c->tab.col, s);
@@ -791,6 +865,8 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->Fint.alloc(nl); c->Fint.zero(s);
         c->p.alloc(nl);
         c->p.zero(s);
+        c->p_pad.alloc((size_t)c->n_nodes * 4);  // cg_stream: one 32-byte sector per node
+        c->p_pad.zero(s);
         if (c->n_ranks > 1 || c->force_mg) {
             // P2P window: fixed-size header (scalar slots, epochs) then the LL receive buffer of the halo dofs
             c->window.alloc(P2P_HDR_BYTES + std::max<size_t>(nl - no, 1) * 16);
@@ -806,6 +882,7 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->truss_out.alloc((size_t)c->n_trusses * 2); c->truss_out.zero(s);
         CUDA_CHECK(cudaStreamSynchronize(s));
         c->cg_grid = 0;
+        c->st_plan.built = false;
         c->finalized = true;
     });
 }
@@ -1057,9 +1134,10 @@ int32_t onsas_get_cg_profile(onsas_ctx* c, int64_t out[8]) {
         }
         // [7]: slowest CTA's accumulated SpMV cycles (multi-GPU profiling variant), 0 otherwise
         long long mx = 0;
-        for (size_t k = 16; k < h.size(); ++k) mx = std::max(mx, h[k]);
+        for (size_t k = 16; k < 16 + 2048; ++k) mx = std::max(mx, h[k]);
         out[7] = mx;
-        if (getenv("ONSAS_PROF_VERBOSE")) fprintf(stderr, "[onsas prof] grid.sync after SpMV: %lld cycles, reduction after it: %lld\n", h[7], h[3]);
+        if (getenv("ONSAS_PROF_VERBOSE"))
+            fprintf(stderr, "[onsas prof] aux counters: %lld %lld %lld\n", h[8], h[9], h[10]);
         if (const char* f = getenv("ONSAS_PROF_DUMP")) {  // diagnostics: per-CTA SpMV cycles of the last profiled solve
             if (FILE* fp = fopen(f, "w")) {
                 for (size_t k = 16; k < h.size(); ++k) fprintf(fp, "%lld\n", h[k]);
@@ -1213,8 +1291,12 @@ int32_t onsas_p2p_import(onsas_ctx* c, const void* handles, const int64_t* offse
         c->d_push_dst.upload(pdst, s);
         c->d_peer_slots.upload(slots, s);
         CUDA_CHECK(cudaStreamSynchronize(s));
+        // mark the interface dofs (mask bit 1): only they look the push map up inside the solver
+        c->h_iface.assign((size_t)nd, 0);
+        for (int64_t i = 0; i < nd; ++i)
+            if (pptr[i + 1] > pptr[i]) c->h_iface[i] = 1;
+        upload_mask(c);
         c->p2p_ready = true;
-        c->cg_grid_mg = 0;
     });
 }
 

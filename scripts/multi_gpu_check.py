@@ -59,7 +59,7 @@ def main():
     d = np.where(mask, ref.csr().diagonal(), 1.0)
     xo, ito, _ = O.cg(ref.rowptr, ref.col, ref.val, mask, b, diag=d, reltol=1e-12)
     e_x, its_modes = 0.0, []
-    for mode in (0, 1):   # 0 = persistent kernel over NVLink peer memory, 1 = one launch per phase + NCCL
+    for mode in (0, 1, 2):   # 0 = TMA-streamed persistent kernel over NVLink peer memory, 1 = one launch per phase + NCCL, 2 = register-fed persistent kernel
         ctx.set_option(ob._lib.OPT_CG_MODE, mode)
         xs, its, res = ctx.pcg(part.scatter_global(b, 3), ob.PRECOND_JACOBI, 1e-12)
         e_x = max(e_x, np.abs(xs[:len(own)] - xo[own]).max() / np.abs(xo).max())
