@@ -131,7 +131,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs to stdout by default: rank 0 prints ONE JSON line there
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     N = world
@@ -234,6 +235,13 @@ def run_ours(args):
         return
     peak, peak_src = _peaks()
     achieved = ALGO_BYTES_PER_TET * n_tets_local / (ms_step * 1e-3) / 1e9   # per GPU: its own tets per its launch
+    traffic = None   # DRAM bytes per launch of the assembly kernel from the committed ncu capture of the same workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_assemble"]
+        if tr["n_tets"] == n_tets_local:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     nnzb = stats["nnz_blocks"]
     n_own_dofs = ctx.n_owned * 3
     spmv_bytes = 72 * nnzb + 4 * nnzb + 8 * (stats["n_slices"] + 1) + 16 * n_own_dofs + n_own_dofs  # BSR-3x3 + mask
@@ -245,7 +253,8 @@ def run_ours(args):
                                f"({n_tets_total} tets total), state = analytic homogeneous field at load factor 0.5",
                    "n_tets": n_tets_total, "n_dofs": mesh.n_nodes * 3, "l2": "inputs larger than L2 (~0.4 GB touched per pass)",
                    "partition": "single GPU" if N == 1 else f"RCB slabs, {N} ranks, NCCL halo exchange of U per assembly; CG: " +
-                                ("NCCL per phase" if args.no_p2p else "persistent kernel, halo + all-reduce over NVLink peer memory")},
+                                ("one launch per phase, NCCL between them" if args.no_p2p else
+                                 "persistent TMA-streamed kernel, halo + all-reduce pushed over NVLink peer memory")},
         "newton_step_ms": nw[0], "newton_step": {"ms_assemble": nw[1], "ms_solve": nw[2], "cg_iters": nw[3], "precond": "jacobi",
                                                   "cg_reltol": float(np.sqrt(np.finfo(np.float64).eps)), "rel_residual_in": nw[4],
                                                   "rel_dU": nw[5]},
@@ -253,13 +262,19 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(ctx.n_dofs * 8), "what": "onsas_set_U(pinned host) + onsas_assemble + onsas_get_Fint(pinned host)"},
         "gpu_launches": K * (1 if N == 1 else 2),
         "roofline": {"bound": "hbm", "kernel": "k_assemble<tet,NeoHookean>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_tet": ALGO_BYTES_PER_TET,
                      "note": "algorithmic bytes count K_e/f_e once per element; the fused kernel writes each K entry once "
                              "(compulsory DRAM traffic ~0.45 KB/tet), so frac > 1 is on-chip reuse, not extra bandwidth"},
         "roofline_spmv": {"bound": "hbm", "kernel": "k_spmv_dot<3>", "achieved": spmv_bytes / (ms_spmv * 1e-3) / 1e9, "peak": peak,
                           "unit": "GB/s", "frac": spmv_bytes / (ms_spmv * 1e-3) / 1e9 / peak, "ms": ms_spmv,
                           "bytes": int(spmv_bytes)},
+        # one PCG iteration of the persistent solver: SpMV bytes above + 10 vector passes, over the
+        # measured time per iteration of the Newton step's solve
+        "roofline_pcg": {"bound": "hbm", "kernel": "cg_stream<3> (one CG iteration)", "bytes": int(spmv_bytes + 80 * n_own_dofs),
+                         "us_per_iteration": 1e3 * nw[2] / max(nw[3], 1),
+                         "achieved": (spmv_bytes + 80 * n_own_dofs) / (1e-3 * nw[2] / max(nw[3], 1)) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": (spmv_bytes + 80 * n_own_dofs) / (1e-3 * nw[2] / max(nw[3], 1)) / 1e9 / peak},
         "tables": stats, "clocks": clocks,
     }
     if N == 1 and not args.no_cpu_baseline:
