@@ -171,3 +171,90 @@ def test_million_tet_cube_size_independent_properties(ob):
     for _ in range(4):
         info = ctx.newton_step(ob.PRECOND_JACOBI, 1e-10)
     assert np.abs(ctx.get_U() - U).max() < 1e-8 and info.norm_r / info.norm_Fext < 1e-8
+
+
+def test_truss_lattice_1m_bars_size_independent_properties(ob):
+    """configs[4] family at 1.0 M bars (52^3-cell braced lattice, Green strain): (i) under a homogeneous stretch every
+    bar's strain / stress is the closed form of Trusses.jl:159-184 and interior nodes are in equilibrium; (ii) a rigid
+    translation is in the null space of K_t at U = 0; (iii) K is symmetric; (iv) a large-displacement Newton solve of a
+    tip-loaded lattice converges quadratically (residual drops below 1e-8 within the iteration budget)."""
+    n = 52
+    mesh = mg.truss_lattice(n, n, n, 2.0)
+    assert mesh.n_bars > 1_000_000
+    E, A, eps = 210e9, 2.5e-3, 1e-3
+    nn = mesh.n_nodes
+    ctx = ob.context_from_flat(mesh.xyz, trusses=mesh.bars, truss_area=np.full(mesh.n_bars, A), truss_strain=ob.STRAIN_GREEN,
+                               mat_kind=[ob.MAT_SVK], mat_params=[[0.0, E / 2]], free_dofs=np.arange(nn * 3, dtype=np.int64))
+    U = np.zeros((nn, 3))
+    U[:, 0] = eps * mesh.xyz[:, 0]
+    ctx.set_U(U.ravel())
+    ctx.assemble()
+    Fint = ctx.get_Fint().reshape(-1, 3)
+    g = np.rint(mesh.xyz / 2.0).astype(int)
+    interior = np.all((g > 0) & (g < n), axis=1)
+    assert np.abs(Fint[interior]).max() < 1e-9 * E * A * eps
+    s, e = ctx.get_stress_strain(ob.FAMILY_TRUSS)
+    d = mesh.xyz[mesh.bars[:, 1]] - mesh.xyz[mesh.bars[:, 0]]
+    l0 = np.linalg.norm(d, axis=1)
+    l1 = np.linalg.norm(d * np.array([1 + eps, 1, 1]), axis=1)
+    eg = (l1 ** 2 - l0 ** 2) / (2 * l0 ** 2)
+    np.testing.assert_allclose(e[:, 0], eg, rtol=1e-10, atol=1e-16)
+    np.testing.assert_allclose(s[:, 0], E * eg * l1 / l0, rtol=1e-10, atol=1e-4)
+    ctx.set_U(np.zeros(nn * 3))
+    ctx.assemble()
+    t = np.zeros((nn, 3))
+    t[:, 1] = 1.0
+    assert np.abs(ctx.spmv(t.ravel())).max() < 1e-9 * E * A / 2.0
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal(nn * 3), rng.standard_normal(nn * 3)
+    Kx, Ky = ctx.spmv(x), ctx.spmv(y)
+    assert abs(y @ Kx - x @ Ky) < 1e-11 * abs(y @ Kx)
+    ctx.close()
+    # clamped at x = 0, pulled at x = L: Newton on a smaller lattice of the same family (the 1 M-bar tangent needs ~1e4 CG
+    # iterations per step; the property, not the size, is what this part checks)
+    small = mg.truss_lattice(12, 4, 4, 2.0)
+    fixed = {c: small.node_sets["x0"] for c in range(3)}
+    free = mg.free_dofs_from_fixed(small.n_nodes, 3, fixed)
+    F = np.zeros((small.n_nodes, 3))
+    F[small.node_sets["x1"], 0] = 0.02 * E * A
+    F[small.node_sets["x1"], 2] = 0.002 * E * A
+    c2 = ob.context_from_flat(small.xyz, trusses=small.bars, truss_area=np.full(small.n_bars, A), truss_strain=ob.STRAIN_GREEN,
+                              mat_kind=[ob.MAT_SVK], mat_params=[[0.0, E / 2]], free_dofs=free)
+    c2.set_Fext(F.ravel())
+    rel = []
+    for _ in range(8):
+        info = c2.newton_step(ob.PRECOND_JACOBI, 1e-12)
+        rel.append(info.norm_r / info.norm_Fext)
+    assert rel[-1] < 1e-8 and rel[-1] < rel[2] * 1e-4
+
+
+def test_cylinder_600k_tets_linear_vs_lame(ob):
+    """configs[2] family at 0.62 M tets ((24, 288, 15) structured cylinder, IsotropicLinearElastic): the Newton step from
+    U = 0 IS the linear solve; the radial displacement matches the plane-strain Lame field to discretisation accuracy,
+    reactions balance the pressure resultant, and a second Newton step changes nothing (residual at round-off)."""
+    Ri, Re, Lz, E, nu, p = 100.0, 200.0, 30.0, 210.0, 0.3, 10.0
+    mesh = mg.cylinder_tet_mesh(24, 288, 15, Ri, Re, Lz)
+    assert mesh.n_tets == 6 * 24 * 288 * 15
+    fixed = {2: mesh.node_sets["z_caps"], 0: mesh.node_sets["outer_on_y_axis"], 1: mesh.node_sets["outer_on_x_axis"]}
+    free = mg.free_dofs_from_fixed(mesh.n_nodes, 3, fixed)
+    Fp = mg.pressure_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["inner"], p)
+    ctx = ob.context_from_flat(mesh.xyz, tets=mesh.tets, mat_kind=[ob.MAT_ISOLINEAR], mat_params=[[E, nu]], free_dofs=free)
+    ctx.set_Fext(Fp)
+    info = ctx.newton_step(ob.PRECOND_JACOBI, 1e-11)
+    assert info.cg_residual <= info.cg_tol
+    U = ctx.get_U().reshape(-1, 3)
+    r = np.linalg.norm(mesh.xyz[:, :2], axis=1)
+    ur = (U[:, :2] * mesh.xyz[:, :2] / r[:, None]).sum(axis=1)
+    A = (1 + nu) * (1 - 2 * nu) * Ri ** 2 * p / (E * (Re ** 2 - Ri ** 2))
+    B = (1 + nu) * Ri ** 2 * Re ** 2 * p / (E * (Re ** 2 - Ri ** 2))
+    lame = A * r + B / r
+    assert np.abs(ur - lame).max() < 2e-3 * lame.max()          # O(h^2) + faceted boundary at nt = 288
+    assert np.abs(U[:, 2]).max() < 1e-6 * lame.max()            # plane strain: u_z = 0 everywhere
+    info2 = ctx.newton_step(ob.PRECOND_JACOBI, 1e-11)
+    assert info2.norm_r / info2.norm_Fext < 1e-9                # linear material: the first step already solved it
+    Fint = ctx.get_Fint().reshape(-1, 3)
+    mask = np.ones(mesh.n_nodes * 3, bool)
+    mask[free] = False
+    # reactions: only at fixed dofs; their x / y resultants vanish (the pressure is self-equilibrated in the plane)
+    Rx = (Fint - Fp.reshape(-1, 3))[:, 0][mask.reshape(-1, 3)[:, 0]].sum()
+    assert abs(Rx) < 1e-6 * np.abs(Fp).sum()
