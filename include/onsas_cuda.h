@@ -111,7 +111,26 @@ int32_t onsas_set_U(onsas_ctx* ctx, const double* U);       /* displacements(sta
 int32_t onsas_get_U(onsas_ctx* ctx, double* U);
 int32_t onsas_set_Fext(onsas_ctx* ctx, const double* Fext); /* external_forces(state), :88; result of apply! :228-241 */
 int32_t onsas_get_Fint(onsas_ctx* ctx, double* Fint);       /* internal_forces(state), :85; reactions = Fint at fixed dofs */
+int32_t onsas_get_Fext(onsas_ctx* ctx, double* Fext);
 int32_t onsas_get_dU(onsas_ctx* ctx, double* dU);           /* Delta_displacements(state) scattered to a full dof vector */
+
+/* ---------------------------------------------------------------- external loads on the device
+ * The step before every Newton loop (apply!(sa, load_bcs), StructuralAnalyses.jl:228-241 with
+ * StructuralBoundaryConditions.jl:195-220): each load boundary condition becomes a unit nodal vector ("pattern")
+ * built ONCE on the device from the boundary faces; per load step only the factors p_k(t) cross the boundary and
+ * F_ext = sum_k factors[k] * pattern_k is formed on the device (fixed order: deterministic).
+ *   onsas_add_face_load  kind 0 = GlobalLoad on TriangularFaces (GlobalLoadBoundaryConditions.jl:50-68):
+ *                        values[3] * A/3 per face node; kind 1 = Pressure (LocalLoadBoundaryConditions.jl:36-56):
+ *                        -n * A/3 * values[0], n A = 1/2 (x2-x1) x (x3-x1) (TriangularFaces.jl:44-65).
+ *                        tri = 3 x n_faces local 0-based node ids.  A time-dependent direction is expressed as one
+ *                        pattern per component (values = e_x, e_y, e_z) with factors = the components of p(t).
+ *   onsas_add_nodal_load GlobalLoad on nodes (:34-48): values[dim] on every listed node, duplicates summed.
+ *   onsas_apply_loads    n_factors must equal the number of patterns added since the last finalize / clear. */
+int32_t onsas_add_face_load(onsas_ctx* ctx, int64_t n_faces, const int32_t* tri, int32_t kind, const double* values,
+                            int32_t* pattern_id);
+int32_t onsas_add_nodal_load(onsas_ctx* ctx, int64_t n, const int32_t* nodes, const double* values, int32_t* pattern_id);
+int32_t onsas_apply_loads(onsas_ctx* ctx, int32_t n_factors, const double* factors);
+int32_t onsas_clear_loads(onsas_ctx* ctx);
 
 /* ---------------------------------------------------------------- hot path */
 

@@ -52,6 +52,11 @@ SIGNATURES = {
     "onsas_get_U": (C.c_int32, [_vp, _dp]),
     "onsas_set_Fext": (C.c_int32, [_vp, _dp]),
     "onsas_get_Fint": (C.c_int32, [_vp, _dp]),
+    "onsas_get_Fext": (C.c_int32, [_vp, _dp]),
+    "onsas_add_face_load": (C.c_int32, [_vp, C.c_int64, _i32p, C.c_int32, _dp, C.POINTER(C.c_int32)]),
+    "onsas_add_nodal_load": (C.c_int32, [_vp, C.c_int64, _i32p, _dp, C.POINTER(C.c_int32)]),
+    "onsas_apply_loads": (C.c_int32, [_vp, C.c_int32, _dp]),
+    "onsas_clear_loads": (C.c_int32, [_vp]),
     "onsas_get_dU": (C.c_int32, [_vp, _dp]),
     "onsas_assemble": (C.c_int32, [_vp]),
     "onsas_eval_elements": (C.c_int32, [_vp, C.c_int32, C.c_int64, C.c_int64, _dp, _dp, _dp, _dp]),

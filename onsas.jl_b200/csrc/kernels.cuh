@@ -1241,6 +1241,55 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_epilogue(CgArgs A) {
 
 __global__ void k_cg_finish(CgArgs A, const double* red) { A.st->dd = red[P_DD]; }
 
+// ------------------------------------------------------------------------------------------------
+// external loads (the step before each Newton loop: apply!, StructuralAnalyses.jl:228-241)
+// ------------------------------------------------------------------------------------------------
+// Unit nodal load vector of one boundary condition on triangular faces, built once on the device.
+//   kind 0  GlobalLoad (GlobalLoadBoundaryConditions.jl:50-68): v * A / 3 on each face node, v = values[0..2]
+//   kind 1  Pressure   (LocalLoadBoundaryConditions.jl:36-56):  -n * A / 3 * values[0], n A = 1/2 (x2-x1) x (x3-x1)
+//           (TriangularFaces.jl:44-65)
+// One thread per node walks the node's incident (face, corner) list in ascending face order and writes the node's
+// entries once: the duplicate summation of StructuralBoundaryConditions.jl:195-220 with a fixed order, no atomics.
+__global__ void k_face_load(const double* __restrict__ X, const int32_t* __restrict__ tri, const int64_t* __restrict__ nf_ptr,
+                            const int32_t* __restrict__ nf_face, int64_t n_nodes, int kind, double v0, double v1, double v2,
+                            double* __restrict__ F) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    for (int64_t q = nf_ptr[i]; q < nf_ptr[i + 1]; ++q) {
+        const int64_t f = nf_face[q];
+        const double* a = X + 3 * (int64_t)tri[3 * f];
+        const double* b = X + 3 * (int64_t)tri[3 * f + 1];
+        const double* c = X + 3 * (int64_t)tri[3 * f + 2];
+        const double e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+        const double av[3] = {0.5 * (e1[1] * e2[2] - e1[2] * e2[1]), 0.5 * (e1[2] * e2[0] - e1[0] * e2[2]),
+                              0.5 * (e1[0] * e2[1] - e1[1] * e2[0])};
+        if (kind == 0) {
+            const double A3 = sqrt(av[0] * av[0] + av[1] * av[1] + av[2] * av[2]) / 3.0;
+            f0 += v0 * A3;
+            f1 += v1 * A3;
+            f2 += v2 * A3;
+        } else {
+            f0 += -v0 * av[0] / 3.0;
+            f1 += -v0 * av[1] / 3.0;
+            f2 += -v0 * av[2] / 3.0;
+        }
+    }
+    F[3 * i] = f0;
+    F[3 * i + 1] = f1;
+    F[3 * i + 2] = f2;
+}
+
+// F_ext = sum_k factor[k] * pattern_k, patterns stored back to back (n each), summed in pattern order
+__global__ void k_combine_loads(const double* __restrict__ patterns, const double* __restrict__ factors, int n_patterns, int64_t n,
+                                double* __restrict__ Fext) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double f = 0.0;
+    for (int k = 0; k < n_patterns; ++k) f += factors[k] * patterns[(int64_t)k * n + i];
+    Fext[i] = f;
+}
+
 // ---- halo exchange helpers (multi-GPU): pack owned values the neighbours need
 __global__ void k_pack(const double* __restrict__ v, const int32_t* __restrict__ send_nodes, int64_t n_send, int bs,
                        double* __restrict__ buf, const CgState* st, int gate) {

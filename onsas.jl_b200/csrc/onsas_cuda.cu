@@ -181,6 +181,9 @@ struct onsas_ctx {
     std::vector<void*> ipc_opened;
     bool p2p_ready = false;
     std::vector<int32_t> h_send_nodes;
+    // device-side load patterns (unit nodal vectors of the load boundary conditions), n_local_dofs each
+    DevBuf<double> patterns, factors;
+    int n_patterns = 0;
     std::vector<uint8_t> h_iface;  // per owned dof: 1 = a neighbour rank needs its value (mask bit 1 on the device)
     DevBuf<long long> d_push_ptr;
     DevBuf<unsigned long long*> d_push_dst, d_peer_slots;
@@ -883,6 +886,8 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         CUDA_CHECK(cudaStreamSynchronize(s));
         c->cg_grid = 0;
         c->st_plan.built = false;
+        c->n_patterns = 0;
+        c->patterns.release();
         c->finalized = true;
     });
 }
@@ -927,6 +932,115 @@ int32_t onsas_get_dU(onsas_ctx* c, double* dU) {
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         std::fill(dU, dU + c->n_local_dofs(), 0.0);
         download(c, dU, c->x.p, (size_t)c->n_own_dofs());
+    });
+}
+
+// ---------------------------------------------------------------- external loads on the device
+namespace {
+// appends one zero-initialised pattern to the device array and returns its device pointer
+double* append_pattern(onsas_ctx* c) {
+    const size_t n = (size_t)c->n_local_dofs();
+    DevBuf<double> grown;
+    grown.alloc((size_t)(c->n_patterns + 1) * n);
+    if (c->n_patterns > 0)
+        CUDA_CHECK(cudaMemcpyAsync(grown.p, c->patterns.p, (size_t)c->n_patterns * n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(grown.p + (size_t)c->n_patterns * n, 0, n * sizeof(double), c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    std::swap(c->patterns.p, grown.p);
+    std::swap(c->patterns.n, grown.n);
+    c->n_patterns += 1;
+    return c->patterns.p + (size_t)(c->n_patterns - 1) * n;
+}
+}  // namespace
+
+int32_t onsas_add_face_load(onsas_ctx* c, int64_t n_faces, const int32_t* tri, int32_t kind, const double* values, int32_t* pattern_id) {
+    if (!c || !pattern_id) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        require(c->dim == 3, ONSAS_ERR_UNSUPPORTED, "face loads need a 3-D mesh");
+        require(kind == 0 || kind == 1, ONSAS_ERR_INVALID_ARG, "unknown load kind");
+        require(n_faces >= 0 && (n_faces == 0 || tri) && values, ONSAS_ERR_INVALID_ARG, "bad face list");
+        const int64_t nn = c->n_nodes;
+        std::vector<int64_t> ptr((size_t)nn + 1, 0);
+        for (int64_t f = 0; f < n_faces; ++f)
+            for (int k = 0; k < 3; ++k) {
+                const int32_t nd = tri[3 * f + k];
+                require(nd >= 0 && nd < nn, ONSAS_ERR_INVALID_ARG, "face node out of range");
+                ptr[(size_t)nd + 1]++;
+            }
+        for (int64_t i = 0; i < nn; ++i) ptr[i + 1] += ptr[i];
+        std::vector<int32_t> face((size_t)ptr[nn]);
+        std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
+        for (int64_t f = 0; f < n_faces; ++f)  // ascending face order inside every node's list
+            for (int k = 0; k < 3; ++k) face[(size_t)fill[tri[3 * f + k]]++] = (int32_t)f;
+        if (face.empty()) face.push_back(0);
+        DevBuf<int64_t> d_ptr;
+        DevBuf<int32_t> d_face, d_tri;
+        d_ptr.upload(ptr, c->stream);
+        d_face.upload(face, c->stream);
+        std::vector<int32_t> htri(tri, tri + 3 * n_faces);
+        if (htri.empty()) htri.push_back(0);
+        d_tri.upload(htri, c->stream);
+        double* F = append_pattern(c);
+        if (nn > 0) {
+            k_face_load<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>(c->X.p, d_tri.p, d_ptr.p, d_face.p, nn, kind, values[0],
+                                                                              kind == 0 ? values[1] : 0.0, kind == 0 ? values[2] : 0.0, F);
+            CUDA_CHECK(cudaGetLastError());
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        *pattern_id = c->n_patterns - 1;
+    });
+}
+
+int32_t onsas_add_nodal_load(onsas_ctx* c, int64_t n, const int32_t* nodes, const double* values, int32_t* pattern_id) {
+    if (!c || !pattern_id) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        require(n >= 0 && (n == 0 || nodes) && values, ONSAS_ERR_INVALID_ARG, "bad node list");
+        std::vector<double> h((size_t)c->n_local_dofs(), 0.0);
+        for (int64_t k = 0; k < n; ++k) {  // GlobalLoad on nodes (GlobalLoadBoundaryConditions.jl:34-48), duplicates summed in list order
+            require(nodes[k] >= 0 && nodes[k] < c->n_nodes, ONSAS_ERR_INVALID_ARG, "load node out of range");
+            for (int d = 0; d < c->dim; ++d) h[(size_t)nodes[k] * c->dim + d] += values[d];
+        }
+        double* F = append_pattern(c);
+        if (!h.empty()) CUDA_CHECK(cudaMemcpyAsync(F, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        *pattern_id = c->n_patterns - 1;
+    });
+}
+
+int32_t onsas_apply_loads(onsas_ctx* c, int32_t n_factors, const double* factors) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        require(n_factors == c->n_patterns && (n_factors == 0 || factors), ONSAS_ERR_INVALID_ARG,
+                "one factor per load pattern is required");
+        const int64_t n = c->n_local_dofs();
+        if (n_factors == 0) {
+            c->Fext.zero(c->stream);
+            return;
+        }
+        c->factors.upload(factors, (size_t)n_factors, c->stream);
+        k_combine_loads<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->patterns.p, c->factors.p, n_factors, n, c->Fext.p);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));  // factors is caller-owned host memory
+    });
+}
+
+int32_t onsas_clear_loads(onsas_ctx* c) {
+    if (!c) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->n_patterns = 0;
+        c->patterns.release();
+    });
+}
+
+int32_t onsas_get_Fext(onsas_ctx* c, double* F) {
+    if (!c || !F) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] {
+        require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
+        download(c, F, c->Fext.p, (size_t)c->n_local_dofs());
     });
 }
 

@@ -125,6 +125,36 @@ class DeviceContext:
         assert F.size == self.n_dofs
         self._check(self._lib.onsas_set_Fext(self._h, F))
 
+    # -- external loads built on the device (apply!, StructuralAnalyses.jl:228-241)
+    def add_face_load(self, tri, kind: int, values) -> int:
+        """kind 0: GlobalLoad values[3] * A/3 per face node; kind 1: Pressure -n * A/3 * values[0]."""
+        tri = _as(tri, np.int32).reshape(-1, 3)
+        v = np.zeros(3)
+        v[:np.size(values)] = np.ravel(values)
+        pid = C.c_int32(-1)
+        self._check(self._lib.onsas_add_face_load(self._h, len(tri), tri.ravel() if len(tri) else np.zeros(3, np.int32), int(kind), v, C.byref(pid)))
+        return int(pid.value)
+
+    def add_nodal_load(self, nodes, values) -> int:
+        nodes = _as(nodes, np.int32).ravel()
+        v = np.zeros(3)
+        v[:np.size(values)] = np.ravel(values)
+        pid = C.c_int32(-1)
+        self._check(self._lib.onsas_add_nodal_load(self._h, len(nodes), nodes if len(nodes) else np.zeros(1, np.int32), v, C.byref(pid)))
+        return int(pid.value)
+
+    def apply_loads(self, factors):
+        f = _as(factors, np.float64).ravel()
+        self._check(self._lib.onsas_apply_loads(self._h, len(f), f if len(f) else np.zeros(1)))
+
+    def clear_loads(self):
+        self._check(self._lib.onsas_clear_loads(self._h))
+
+    def get_Fext(self):
+        out = np.empty(self.n_dofs)
+        self._check(self._lib.onsas_get_Fext(self._h, out))
+        return out
+
     def get_Fint(self):
         out = np.empty(self.n_dofs)
         self._check(self._lib.onsas_get_Fint(self._h, out))

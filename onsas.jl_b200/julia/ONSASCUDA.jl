@@ -145,6 +145,33 @@ function download!(ctx::CudaContext, state::FullStaticState, tet_elems, bar_elem
     end
 end
 
+"""
+Optional device-side `apply!` (SURVEY 8f-1): registers one load pattern per `Pressure` BC and one per component of a
+`GlobalLoad` BC whose entities are all `TriangularFace`s; returns the closures `t -> factor` in pattern order, or
+`nothing` when some load is not a face load (the host `apply!` + `onsas_set_Fext` path is used then).
+"""
+function register_loads!(ctx::CudaContext, s::AbstractStructure, node_index::AbstractDict)
+    factors = Function[]
+    for (bc, ents) in pairs(load_bcs(boundary_conditions(s)))
+        all(e -> e isa TriangularFace, ents) || return nothing
+        tri = Int32[node_index[n] - 1 for e in ents for n in nodes(e)]          # 3 x n_faces, 0-based
+        pid = Ref{Int32}(-1)
+        if bc isa Pressure
+            GC.@preserve tri check(ctx, ccall((:onsas_add_face_load, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Int32}, Int32, Ptr{Float64}, Ref{Int32}),
+                ctx.handle, length(ents), tri, Int32(1), [1.0, 0.0, 0.0], pid))
+            push!(factors, t -> bc(t))
+        else
+            for c in 1:3
+                e_c = [Float64(c == k) for k in 1:3]
+                GC.@preserve tri check(ctx, ccall((:onsas_add_face_load, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Int32}, Int32, Ptr{Float64}, Ref{Int32}),
+                    ctx.handle, length(ents), tri, Int32(0), e_c, pid))
+                push!(factors, t -> bc(t)[c])
+            end
+        end
+    end
+    factors
+end
+
 "Drop-in replacement of `_solve!(::NonLinearStaticAnalysis, ::AbstractSolver, ...)` (NonLinearStaticAnalyses.jl:70-104)."
 function _solve!(sa::NonLinearStaticAnalysis, alg::NewtonRaphsonCUDA, linear_solver::LinearSolver = nothing;
         linear_solve_inplace::Bool = false)

@@ -315,6 +315,22 @@ class FlatStructure:
     free_dofs: np.ndarray
     fext: Callable[[float], np.ndarray]
     materials: list = field(default_factory=list)
+    # device-side loads: [(builder, factor_fn)] with builder(ctx) -> pattern id and factor_fn(t) -> float;
+    # None when some load cannot be expressed as a face / nodal pattern (the host-evaluated fext(t) is uploaded then)
+    load_patterns: list | None = None
+
+    def apply_loads(self, ctx, t: float):
+        """apply!(sa, load_bcs) of one load step (StructuralAnalyses.jl:228-241) on the device when every load is a
+        face / nodal pattern: the patterns are built once per context, only the factors p_k(t) cross the boundary."""
+        if self.load_patterns is None:
+            ctx.set_Fext(self.fext(t))
+            return
+        if getattr(ctx, "_load_owner", None) is not self:
+            ctx.clear_loads()
+            for build, _ in self.load_patterns:
+                build(ctx)
+            ctx._load_owner = self
+        ctx.apply_loads([f(t) for _, f in self.load_patterns])
 
     @property
     def n_nodes(self):
@@ -432,7 +448,31 @@ class Structure:
                         F[dim * idx[id(n)]: dim * idx[id(n)] + dim] += per[:dim]
             return F
 
+        # the same loads as device patterns: one per Pressure BC, one per component of a GlobalLoad BC
+        patterns: list | None = []
+        for bc, ents in loads:
+            ents = list(ents)
+            if ents and all(isinstance(e, TriangularFace) for e in ents) and dim == 3:
+                tri = np.array([[idx[id(n)] for n in e.nodes] for e in ents], np.int32)
+                if isinstance(bc, Pressure):
+                    patterns.append((lambda ctx, tri=tri: ctx.add_face_load(tri, 1, [1.0]), lambda t, bc=bc: float(bc.values(t))))
+                else:
+                    for c in range(dim):
+                        e_c = np.eye(3)[c]
+                        patterns.append((lambda ctx, tri=tri, e_c=e_c: ctx.add_face_load(tri, 0, e_c),
+                                         lambda t, bc=bc, c=c: float(np.asarray(bc.values(t), dtype=np.float64)[c])))
+            elif ents and all(isinstance(e, Node) for e in ents) and not isinstance(bc, Pressure):
+                ids = np.array([idx[id(n)] for n in ents], np.int32)
+                for c in range(dim):
+                    e_c = np.eye(3)[c][:dim]
+                    patterns.append((lambda ctx, ids=ids, e_c=e_c: ctx.add_nodal_load(ids, e_c),
+                                     lambda t, bc=bc, c=c: float(np.asarray(bc.values(t), dtype=np.float64)[c])))
+            else:   # body loads on elements etc.: evaluated on the host
+                patterns = None
+                break
+
         return FlatStructure(
+            load_patterns=patterns,
             xyz=xyz, dim=dim, tets=np.array(tets, np.int32).reshape(-1, 4), tet_mat=np.array(tet_mat, np.int32),
             trusses=np.array(trusses, np.int32).reshape(-1, 2), truss_mat=np.array(truss_mat, np.int32),
             truss_area=np.array(areas, np.float64), truss_strain=(strain or RotatedEngineeringStrain).code,

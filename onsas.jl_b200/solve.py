@@ -290,7 +290,7 @@ def _solve_nonlinear(sa: NonLinearStaticAnalysis, alg: NewtonRaphson) -> Solutio
     sol = Solution(sa, alg)
     while not sa.is_done():
         it = sa.iter_state.reset()                       # :83
-        ctx.set_Fext(s.flat.fext(sa.current_time()))     # :86-87 external forces of this load step
+        s.flat.apply_loads(ctx, sa.current_time())       # :86-87 external forces of this load step (built on the device)
         cg_its, infos = [], []
         while isinstance(isconverged(it, alg.tol), NotConvergedYet):   # :90
             info = ctx.newton_step(alg.precond_code, alg.cg_reltol, alg.cg_abstol, alg.cg_maxiter)  # :92-95
@@ -318,7 +318,7 @@ def _solve_linear(sa: LinearStaticAnalysis, alg: NewtonRaphson) -> Solution:
     while not sa.is_done():
         ctx.set_U(np.zeros(n))
         ctx.assemble()                                   # tangent at U = 0; F_int = 0
-        ctx.set_Fext(s.flat.fext(sa.current_time()))
+        s.flat.apply_loads(ctx, sa.current_time())
         info = ctx.step(alg.precond_code, alg.cg_reltol, alg.cg_abstol, alg.cg_maxiter, update_U=True)
         ctx.assemble()                                   # stress / strain / F_int at the solved U (:123-131)
         ctx.synchronize()
