@@ -240,3 +240,40 @@ def test_persistent_and_multilaunch_cg_agree(ob, oracle):
         assert abs(out[0][1] - o[1]) <= 1 and cases.rel_err(out[0][0], o[0]) < 1e-9
 
 
+
+
+def test_high_valence_hub_falls_back_to_the_register_fed_solver(ob, oracle):
+    """A hub node with 400 bars: its slice has more (row, element) pairs than the assembly CTA has threads (the pair
+    loop wraps) and its row is 401 blocks wide -- too wide for the shared-memory ring of the streamed CG, which must
+    hand over to the register-fed persistent kernel.  Assembly, SpMV and all three solver modes still match the
+    oracle."""
+    rng = np.random.default_rng(5)
+    n_spokes = 400
+    xyz = np.vstack([np.zeros((1, 3)), rng.standard_normal((n_spokes, 3)) + np.array([0.0, 0.0, 3.0])])
+    xyz[1:] /= np.linalg.norm(xyz[1:], axis=1, keepdims=True) / rng.uniform(1.0, 2.0, (n_spokes, 1))
+    bars = np.stack([np.zeros(n_spokes, np.int32), np.arange(1, n_spokes + 1, dtype=np.int32)], axis=1)
+    ring = np.stack([np.arange(1, n_spokes, dtype=np.int32), np.arange(2, n_spokes + 1, dtype=np.int32)], axis=1)
+    bars = np.vstack([bars, ring]).astype(np.int32)
+    free = np.arange(3, dtype=np.int64)                      # only the hub moves
+    m = oracle.FlatModel(xyz=xyz, trusses=bars, truss_area=rng.uniform(0.5, 1.5, len(bars)), truss_strain=1,
+                         mat_kind=[0], mat_params=[[0.0, 50.0]], free_dofs=free)
+    U = np.zeros(m.n_dofs)
+    U[:3] = [0.05, -0.02, 0.08]
+    ref = oracle.Assembly(m).assemble(U)
+    ctx = _ctx(ob, m)
+    ctx.set_U(U)
+    ctx.assemble()
+    rp, ci, v = ctx.get_csr()
+    np.testing.assert_array_equal(ci, ref.col)
+    assert cases.rel_err(v, ref.val) < 1e-12 and cases.rel_err(ctx.get_Fint(), ref.F_int) < 1e-12
+    mask = m.free_mask()
+    x = rng.standard_normal(m.n_dofs) * mask
+    assert cases.rel_err(ctx.spmv(x), (ref.csr() @ x) * mask) < 1e-13
+    b = rng.standard_normal(m.n_dofs)
+    A = ref.csr()
+    xd = np.zeros(m.n_dofs)
+    xd[free] = np.linalg.solve(A[free][:, free].toarray(), b[free])
+    for mode in (0, 1, 2):
+        ctx.set_option(ob._lib.OPT_CG_MODE, mode)
+        xs, its, res = ctx.pcg(b, ob.PRECOND_JACOBI, 1e-13)
+        assert its <= 4 and cases.rel_err(xs, xd) < 1e-10
