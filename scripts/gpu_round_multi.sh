@@ -7,7 +7,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi -L > $OUT/gpus.txt 2>&1
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
-echo "== multi-gpu parity check (N=$N)"; timeout 300 $RUN scripts/multi_gpu_check.py > $OUT/multi_check_$N.log 2>&1; echo "rc=$?"; grep -E "multi-gpu check|MULTI_GPU_CHECK|Error|error" $OUT/multi_check_$N.log | head -20
+echo "== multi-gpu parity check (N=$N)"; timeout 300 $RUN tests/multi_gpu_check.py > $OUT/multi_check_$N.log 2>&1; echo "rc=$?"; grep -E "multi-gpu check|MULTI_GPU_CHECK|Error|error" $OUT/multi_check_$N.log | head -20
 if [ $ONLY -eq 0 ]; then
   echo "== bench N=1"; timeout 300 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline > $OUT/bench_1.json 2> $OUT/bench_1.err; cut -c1-300 $OUT/bench_1.json
 fi

@@ -1,5 +1,5 @@
 """Multi-GPU parity check, run under torchrun (one rank per GPU):
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 scripts/multi_gpu_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tests/multi_gpu_check.py
 Every rank builds the same small global problem, keeps its RCB part, and the distributed assembly / SpMV / PCG /
 Newton solve are compared with the oracle on the global mesh (F_int, K rows, U within the north-star tolerances)."""
 import os
