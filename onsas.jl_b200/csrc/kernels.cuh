@@ -377,7 +377,7 @@ struct CgState {
     int pad;
 };
 
-enum : int { P_RR = 0, P_RZ = 1, P_FF = 2, P_UU = 3, P_PAP = 4, P_DD = 5, P_COUNT = 6 };
+enum : int { P_RR = 0, P_RZ = 1, P_FF = 2, P_UU = 3, P_PAP = 4, P_DD = 5, P_COUNT = 8 };  // 8 rows: cg_stream alternates two sets of 4
 
 struct CgArgs {
     int64_t n_rows;   // owned block rows
@@ -889,6 +889,22 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         }
     };
 
+    // grid-wide reduction + barrier of NV CTA partials (identical in all threads of the CTA on entry)
+    // (a flag-word all-to-all among the CTAs instead of grid.sync + partials was measured: 50.2 vs 46.4 us per iteration)
+    unsigned int n_red = 0;
+    auto grid_reduce = [&](auto& v) {
+        constexpr int NV = sizeof(v) / sizeof(double);
+        // two row sets, alternating: a fast CTA writing reduction n+1 must not overwrite what a slow one still reads of n
+        double* pr = part + (size_t)((n_red++ & 1u) * 4) * ps;
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) pr[k * ps + blockIdx.x] = v[k];
+        }
+        grid.sync();
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = sum_partials<ST_THREADS>(pr + k * ps, nb, sh);
+    };
+
     // ---- the rings
     const int w = tid >> 5, lane = tid & 31;
     const int NCW = S.n_cw, D = S.depth;
@@ -948,13 +964,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     }
     for (int64_t i = gtid, np = ((A.n + (mg ? P.n_halo_dofs : 0)) / BS) * PS; i < np; i += gsz) A.p_pad[i] = 0.0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double b = block_sum<ST_THREADS>(g4[k], sh);
-        if (tid == 0) part[k * ps + blockIdx.x] = b;
-    }
-    grid.sync();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) g4[k] = sum_partials<ST_THREADS>(part + k * ps, nb, sh);
+    for (int k = 0; k < 4; ++k) g4[k] = block_sum<ST_THREADS>(g4[k], sh);
+    grid_reduce(g4);
     if (mg) p2p_allreduce<4>(P, g4, repoch, sh4);
     const double rr0 = g4[P_RR], ff = g4[P_FF], uu = g4[P_UU];
     double rho = g4[P_RZ];
@@ -1052,13 +1063,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
             }
             if (A.prof != nullptr && lane == 0) A.prof[16 + blockIdx.x * CW + w] += clock64() - tc0;  // per-warp SpMV cycles (diagnostics)
         }
-        d = block_sum<ST_THREADS>(d, sh);
-        if (tid == 0) part[P_PAP * ps + blockIdx.x] = d;
+        double pAp[1] = {block_sum<ST_THREADS>(d, sh)};
         prof(2);
-        grid.sync();
+        grid_reduce(pAp);
         prof(3);
         if (*(volatile int*)A.err == 3) break;  // a stage never arrived (set before the barrier, so every CTA sees it)
-        double pAp[1] = {sum_partials<ST_THREADS>(part + P_PAP * ps, nb, sh)};
         if (mg) p2p_allreduce<1>(P, pAp, repoch, sh4);
         const double alpha = rho / pAp[0];
         // ---- x += alpha p ; r -= alpha Ap ; multi-GPU: push z of the interface dofs right away
@@ -1096,17 +1105,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                 }
             }
         }
-        const double b0 = block_sum<ST_THREADS>(s2[0], sh);
-        const double b1 = block_sum<ST_THREADS>(s2[1], sh);
-        if (tid == 0) {
-            part[P_RR * ps + blockIdx.x] = b0;
-            part[P_RZ * ps + blockIdx.x] = b1;
-        }
+        s2[0] = block_sum<ST_THREADS>(s2[0], sh);
+        s2[1] = block_sum<ST_THREADS>(s2[1], sh);
         prof(4);
-        grid.sync();
+        grid_reduce(s2);
         prof(5);
-        s2[0] = sum_partials<ST_THREADS>(part + P_RR * ps, nb, sh);
-        s2[1] = sum_partials<ST_THREADS>(part + P_RZ * ps, nb, sh);
         if (mg) p2p_allreduce<2>(P, s2, repoch, sh4);
         rho_prev = rho;
         rho = s2[1];
@@ -1118,11 +1121,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     if (!is_producer && n_my > 0)
         for (int k = 0; k < D; ++k, ++q_done) mbar_wait(&full[cw][q_done % D], (uint32_t)((q_done / D) & 1), A.err);
 
-    double dd = cg_epilogue_body(A, gtid, gsz);
-    dd = block_sum<ST_THREADS>(dd, sh);
-    if (tid == 0) part[P_DD * ps + blockIdx.x] = dd;
-    grid.sync();
-    double dd1[1] = {sum_partials<ST_THREADS>(part + P_DD * ps, nb, sh)};
+    double dd1[1] = {block_sum<ST_THREADS>(cg_epilogue_body(A, gtid, gsz), sh)};
+    grid_reduce(dd1);
     if (mg) p2p_allreduce<1>(P, dd1, repoch, sh4);
     if (blockIdx.x == 0 && tid == 0) {
         CgState* st = A.st;

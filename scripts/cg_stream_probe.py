@@ -1,4 +1,5 @@
-"""Diagnostics of the streamed CG: per-phase cycles for ring geometries (ONSAS_STREAM_CW / ONSAS_STREAM_DEPTH)."""
+"""Diagnostics of the streamed CG: per-phase cycles for ring
+geometries (ONSAS_STREAM_CW / ONSAS_STREAM_DEPTH experiment knobs)."""
 import os
 import subprocess
 import sys
@@ -14,17 +15,19 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     mesh, free, U_half, U_prev, Fext = bench.build_problem(55, 1)
     ctx = ob.context_from_flat(mesh.xyz, tets=mesh.tets, mat_kind=[ob.MAT_NEOHOOKEAN], mat_params=[[bench.KBULK, bench.MU]], free_dofs=free)
     ctx.set_Fext(Fext)
-    for prof in (0, 0, 1):
-        ctx.set_option(L.OPT_CG_PROFILE, prof)
-        ctx.set_U(U_prev)
-        info = ctx.newton_step(ob.PRECOND_JACOBI)
-        line = f"cw={os.environ.get('ONSAS_STREAM_CW')} depth={os.environ.get('ONSAS_STREAM_DEPTH')} prof={prof} cg_iters={info.cg_iters} ms_solve={info.ms_solve:.2f} us/iter={1e3 * info.ms_solve / info.cg_iters:.2f}"
-        if prof:
-            pv = ctx.cg_profile()
-            slow = pv.pop("slowest_cta_spmv", 0)
-            tot = sum(pv.values())
-            line += " | " + " ".join(f"{k}={v / info.cg_iters:.0f}" for k, v in pv.items()) + f" cyc/iter={tot / info.cg_iters:.0f} slowest_warp_spmv/iter={slow / info.cg_iters:.0f}"
-        print(line, flush=True)
+    for llbar in (0,):
+        for prof in (0, 0, 1):
+            ctx.set_option(L.OPT_CG_PROFILE, prof)
+            ctx.set_U(U_prev)
+            info = ctx.newton_step(ob.PRECOND_JACOBI)
+            line = (f"cw={os.environ.get('ONSAS_STREAM_CW', '12')} depth={os.environ.get('ONSAS_STREAM_DEPTH', '2')} prof={prof} "
+                    f"cg_iters={info.cg_iters} ms_solve={info.ms_solve:.2f} us/iter={1e3 * info.ms_solve / info.cg_iters:.2f}")
+            if prof:
+                pv = ctx.cg_profile()
+                slow = pv.pop("slowest_cta_spmv", 0)
+                tot = sum(pv.values())
+                line += " | " + " ".join(f"{k}={v / info.cg_iters:.0f}" for k, v in pv.items()) + f" cyc/iter={tot / info.cg_iters:.0f} slowest_warp_spmv/iter={slow / info.cg_iters:.0f}"
+            print(line, flush=True)
 else:
     for cw, depth in ((12, 2), (8, 3)):
         env = dict(os.environ, ONSAS_STREAM_CW=str(cw), ONSAS_STREAM_DEPTH=str(depth))
