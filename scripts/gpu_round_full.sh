@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call: tests, bench (ours + reference arm), launch list, full ncu captures (assembly, streamed CG), config sweep.
-# usage (from the repo root): gpurun --timeout 2400 -- 'bash scripts/gpu_round9.sh r09'
-TAG=${1:-r09}
+# usage (from the repo root): gpurun --timeout 2400 -- 'bash scripts/gpu_round_full.sh r09'
+TAG=${1:-r11}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
@@ -13,5 +13,5 @@ echo "== cg probe"; timeout 300 python scripts/cg_stream_probe.py > $OUT/cg_stre
 echo "== ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1; echo "rc=$?"
 echo "== ncu full: streamed CG"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:cg_stream -c 1 -o $OUT/prof_cg_stream python scripts/profile_target.py 55 neo 0 0 1 > $OUT/ncu_cg.log 2>&1; echo "rc=$?"; tail -2 $OUT/ncu_cg.log
 echo "== ncu full: assembly"; ONSAS_ASM_MINB=3 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_assemble -s 2 -c 1 -o $OUT/prof_assemble python scripts/profile_target.py 55 neo 4 0 0 > $OUT/ncu_asm.log 2>&1; echo "rc=$?"
-echo "== config sweep"; timeout 1200 python scripts/config_sweep.py c2 c3 c5 c4 > $OUT/config_sweep.jsonl 2> $OUT/config_sweep.err; echo "rc=$?"; cut -c1-400 $OUT/config_sweep.jsonl; tail -3 $OUT/config_sweep.err
+echo "== config sweep"; timeout 1200 python scripts/config_sweep.py c2 c3 c5 > $OUT/config_sweep.jsonl 2> $OUT/config_sweep.err; echo "rc=$?"; cut -c1-400 $OUT/config_sweep.jsonl; tail -3 $OUT/config_sweep.err
 ls -la $OUT
