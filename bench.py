@@ -316,6 +316,10 @@ def run_reference(args):
     from oracle import oracle as O
     mesh, free, U_half, _, _ = build_problem(cells, 1)
     m = O.FlatModel(xyz=mesh.xyz, tets=mesh.tets, mat_kind=[O.MAT_NEOHOOKEAN], mat_params=[[KBULK, MU]], free_dofs=free)
+    try:   # torchrun sets OMP_NUM_THREADS=1 for its workers: the reference arm uses all host cores
+        O.lib().orc_set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     asm = O.AssemblyMT(m)
     for _ in range(max(1, min(W, 2))):
         asm.assemble(U_half)

@@ -50,6 +50,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm of bench.py asks for all host cores */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static double det3(const double *A) {
     return M3(A, 0, 0) * (M3(A, 1, 1) * M3(A, 2, 2) - M3(A, 1, 2) * M3(A, 2, 1)) -
            M3(A, 0, 1) * (M3(A, 1, 0) * M3(A, 2, 2) - M3(A, 1, 2) * M3(A, 2, 0)) +
