@@ -920,9 +920,10 @@ int32_t onsas_get_Fint(onsas_ctx* c, double* F) {
     if (!c || !F) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
-        std::fill(F, F + c->n_local_dofs(), 0.0);
+        if (c->n_local_dofs() > c->n_own_dofs()) std::fill(F + c->n_own_dofs(), F + c->n_local_dofs(), 0.0);  // halo part
+        // one stream synchronisation for the vector and the deferred-error flag
+        CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         download(c, F, c->Fint.p, (size_t)c->n_own_dofs());
-        CUDA_CHECK(cudaMemcpy(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
         check_deferred(c);
     });
 }

@@ -277,3 +277,51 @@ def test_high_valence_hub_falls_back_to_the_register_fed_solver(ob, oracle):
         ctx.set_option(ob._lib.OPT_CG_MODE, mode)
         xs, its, res = ctx.pcg(b, ob.PRECOND_JACOBI, 1e-13)
         assert its <= 4 and cases.rel_err(xs, xd) < 1e-10
+
+
+@pytest.mark.parametrize("mat", ["svk", "neo"])
+def test_random_node_and_element_numbering(ob, oracle, mat):
+    """An 'unstructured' numbering of the same mesh: nodes and elements randomly permuted, so rows have scattered
+    columns, slices have ragged widths and a node's elements are far apart in memory.  Assembly (reference order =
+    ascending element id of the PERMUTED mesh), SpMV and the three solver modes still match the oracle, and one
+    Newton step equals the direct solve."""
+    m0, _ = cases.box_model(11, 6, 5, mat=mat, jitter=0.15)
+    rng = np.random.default_rng(11)
+    n = m0.xyz.shape[0]
+    perm = rng.permutation(n)                      # new id of old node i
+    inv = np.empty(n, np.int64)
+    inv[perm] = np.arange(n)
+    xyz = m0.xyz[inv]
+    tets = perm[m0.tets][rng.permutation(len(m0.tets))].astype(np.int32)
+    free = np.sort(perm[m0.free_dofs // 3] * 3 + m0.free_dofs % 3)
+    m = oracle.FlatModel(xyz=xyz, tets=tets, mat_kind=m0.mat_kind, mat_params=m0.mat_params, free_dofs=free)
+    U = cases.random_U(m, 0.03)
+    ref = oracle.Assembly(m).assemble(U)
+    ctx = _ctx(ob, m)
+    ctx.set_U(U)
+    ctx.assemble()
+    rp, ci, v = ctx.get_csr()
+    np.testing.assert_array_equal(ci, ref.col)
+    assert cases.rel_err(v, ref.val) < 1e-12 and cases.rel_err(ctx.get_Fint(), ref.F_int) < 1e-12
+    mask = m.free_mask()
+    x = rng.standard_normal(m.n_dofs) * mask
+    assert cases.rel_err(ctx.spmv(x), (ref.csr() @ x) * mask) < 1e-13
+    b = rng.standard_normal(m.n_dofs)
+    import scipy.sparse.linalg as spla
+    A = ref.csr()
+    xd = np.zeros(m.n_dofs)
+    xd[free] = spla.spsolve(A[free][:, free].tocsc(), b[free])
+    its = []
+    for mode in (0, 1, 2):
+        ctx.set_option(ob._lib.OPT_CG_MODE, mode)
+        xs, it, res = ctx.pcg(b, ob.PRECOND_JACOBI, 1e-12)
+        assert cases.rel_err(xs, xd) < 1e-8
+        its.append(it)
+    assert max(its) - min(its) <= max(2, min(its) // 50)
+    ctx.set_option(ob._lib.OPT_CG_MODE, 0)
+    Fext = rng.standard_normal(m.n_dofs) * 1e-3
+    ctx.set_Fext(Fext)
+    info = ctx.newton_step(ob.PRECOND_JACOBI, 1e-13)
+    Uref = U.copy()
+    Uref[free] += spla.spsolve(A[free][:, free].tocsc(), (Fext - ref.F_int)[free])
+    assert cases.rel_err(ctx.get_U(), Uref) < 1e-8
