@@ -59,6 +59,8 @@ typedef struct onsas_ctx onsas_ctx;
 /* preconditioners for the CG solve */
 #define ONSAS_PRECOND_NONE 0   /* IterativeSolversJL_CG default of the reference, StructuralSolvers.jl:29 */
 #define ONSAS_PRECOND_JACOBI 1 /* the north-star solver */
+#define ONSAS_PRECOND_TWO_LEVEL 2 /* Jacobi + aggregated coarse space (piecewise-constant translations on ~7^3-node aggregates,
+                                     E = Z^T K Z inverted explicitly once per assembly); streamed persistent solver only. SURVEY 8f-4 */
 
 /* tuning keys for onsas_set_option */
 #define ONSAS_OPT_CG_MODE 1      /* 0 = persistent cooperative kernel with K streamed through shared memory by TMA bulk copies (default;

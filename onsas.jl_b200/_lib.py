@@ -19,7 +19,7 @@ OK, ERR_INVALID_ARG, ERR_NEGATIVE_VOLUME, ERR_CUDA, ERR_NOT_READY, ERR_UNSUPPORT
 MAT_SVK, MAT_NEOHOOKEAN, MAT_ISOLINEAR = 0, 1, 2
 STRAIN_ROTATED_ENGINEERING, STRAIN_GREEN = 0, 1
 FAMILY_TET, FAMILY_TRUSS = 0, 1
-PRECOND_NONE, PRECOND_JACOBI = 0, 1
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_TWO_LEVEL = 0, 1, 2
 OPT_CG_MODE, OPT_ASM_MINBLOCKS, OPT_CG_CHECK_EVERY, OPT_CG_BLOCKS_PER_SM, OPT_CG_PROFILE, OPT_FORCE_MG = 1, 2, 3, 4, 5, 6
 
 

@@ -379,6 +379,18 @@ struct CgState {
 
 enum : int { P_RR = 0, P_RZ = 1, P_FF = 2, P_UU = 3, P_PAP = 4, P_DD = 5, P_COUNT = 8 };  // 8 rows: cg_stream alternates two sets of 4
 
+// Two-level preconditioner (precond = 2): M^-1 = D^-1 + Z E^-1 Z^T with Z = piecewise-constant translations on node
+// aggregates (masked at fixed dofs) and E = Z^T K Z, inverted explicitly once per assembly (nc = BS * n_agg <= 1536).
+struct CoarseArgs {
+    int n_agg, nc;
+    const int32_t* agg;        // [n_rows] aggregate of every owned node
+    const int32_t* agg_ptr;    // [n_agg+1]
+    const int32_t* agg_nodes;  // [n_rows] node ids grouped by aggregate, ascending inside each
+    const double* Einv;        // [nc][nc]
+    double* w;                 // [nc]  Z^T r
+    double* y;                 // [nc]  E^-1 w
+};
+
 struct CgArgs {
     int64_t n_rows;   // owned block rows
     int64_t n;        // owned dofs = n_rows * BS
@@ -406,6 +418,7 @@ struct CgArgs {
     long long* prof;    // optional [8]: SM-clock cycles block 0 spent per phase of the persistent kernel (diagnostics)
     int* err;           // device error flag (3 = a shared-memory stage never arrived)
     double* p_pad;      // cg_stream: search direction with one 32-byte sector per node (BS = 3: stride 4), owned + halo nodes
+    CoarseArgs co;      // precond = 2
 };
 
 // fixed-order block reduction; result valid in every thread
@@ -764,6 +777,110 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A, P2PA
 }
 
 // ------------------------------------------------------------------------------------------------
+// two-level preconditioner: coarse operator E = Z^T (M K M) Z and its explicit inverse
+// ------------------------------------------------------------------------------------------------
+// One CTA per aggregate a builds the BS rows 3a..3a+2 of E in shared memory.  Its nodes are visited in ascending order
+// and a node's blocks in storage order by the same BS*BS threads, so every entry of E is summed in a fixed order
+// (deterministic); the loads of a row (column ids -> aggregate ids, values) are issued by the whole CTA in parallel.
+constexpr int CO_THREADS = 256;
+constexpr int CO_SPLIT = 3;  // warps per aggregate in the w = Z^T r reduction (13 warps: 4 aggregates per CTA and pass)
+template <int BS>
+__global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double* E) {
+    extern __shared__ double erow[];  // [BS][nc]
+    constexpr int BB = BS * BS;
+    const CoarseArgs& G = A.co;
+    const int a = blockIdx.x, tid = threadIdx.x, nc = G.nc;
+    __shared__ int s_b[CO_THREADS];         // aggregate of the block's column (-1: halo column)
+    __shared__ unsigned char s_m[CO_THREADS];  // mask bits of the column node's dofs
+    double* sval = erow + (size_t)BS * nc;  // [CO_THREADS / BB][BB] values of the current batch of blocks
+    for (int k = tid; k < BS * nc; k += CO_THREADS) erow[k] = 0.0;
+    __syncthreads();
+    constexpr int NBLK = CO_THREADS / BB;   // blocks staged per batch
+    for (int q = G.agg_ptr[a]; q < G.agg_ptr[a + 1]; ++q) {
+        const int64_t i = G.agg_nodes[q];
+        const int64_t base = A.slice_ptr[i / C];
+        const int width = (int)(A.slice_ptr[i / C + 1] - base);
+        const int lane = (int)(i % C);
+        unsigned mi = 0;
+        for (int r = 0; r < BS; ++r) mi |= (unsigned)(A.mask[i * BS + r] & 1) << r;
+        for (int s0 = 0; s0 < width; s0 += NBLK) {
+            const int nb = width - s0 < NBLK ? width - s0 : NBLK;
+            if (tid < nb) {
+                const int64_t j = A.col[(base + s0 + tid) * C + lane];
+                int b = -1;
+                unsigned mj = 0;
+                if (j < A.n_rows) {
+                    b = G.agg[j];
+                    for (int c = 0; c < BS; ++c) mj |= (unsigned)(A.mask[j * BS + c] & 1) << c;
+                }
+                s_b[tid] = b;
+                s_m[tid] = (unsigned char)mj;
+            }
+            if (tid < nb * BB) sval[tid] = A.val[((base + s0 + tid / BB) * BB + tid % BB) * C + lane];
+            __syncthreads();
+            if (tid < BB) {  // thread (r, c) applies the staged blocks in order
+                const int r = tid / BS, c = tid % BS;
+                if ((mi >> r) & 1u)
+                    for (int s = 0; s < nb; ++s) {
+                        const int b = s_b[s];
+                        if (b >= 0 && ((s_m[s] >> c) & 1u)) erow[(size_t)r * nc + b * BS + c] += sval[s * BB + tid];
+                    }
+            }
+            __syncthreads();
+        }
+    }
+    // coarse dofs without any free fine dof: unit diagonal keeps E invertible (their w is always 0)
+    if (tid < BS && erow[(size_t)tid * nc + a * BS + tid] == 0.0) erow[(size_t)tid * nc + a * BS + tid] = 1.0;
+    __syncthreads();
+    for (int k = tid; k < BS * nc; k += CO_THREADS) E[(size_t)(a * BS) * nc + k] = erow[k];
+}
+
+// In-place Gauss-Jordan inversion of the SPD coarse matrix (no pivoting) in ONE cooperative launch.  The matrix is
+// distributed by rows over the CTAs' shared memory (<= 11 rows of 1536 doubles = 135 KB per CTA); per elimination
+// step only the pivot row travels (its owner publishes the already updated row k+1 before the step's single grid
+// barrier: look-ahead), so a step costs one barrier + 12 KB of L2 reads per CTA instead of a pass over the matrix.
+constexpr int GJ_THREADS = 512;
+constexpr int GJ_MAX_ROWS = 12;  // rows of the matrix per CTA (shared memory: 12 x 1536 doubles = 144 KB)
+__global__ void __launch_bounds__(GJ_THREADS, 1) k_gj_invert(double* M, int nc, int rows_per_cta, double* rowbuf /*[2][nc]*/) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double sm[];  // [rows_per_cta][nc]
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int nr = r0 >= nc ? 0 : (nc - r0 < rows_per_cta ? nc - r0 : rows_per_cta);
+    for (int k = tid; k < nr * nc; k += GJ_THREADS) sm[k] = M[(size_t)r0 * nc + k];
+    __syncthreads();
+    if (r0 == 0)
+        for (int j = tid; j < nc; j += GJ_THREADS) rowbuf[j] = sm[j];
+    grid.sync();
+    for (int k = 0; k < nc; ++k) {
+        const double* prow = rowbuf + (size_t)(k & 1) * nc;   // row k as it was before this step
+        double* nrow = rowbuf + (size_t)((k + 1) & 1) * nc;   // row k+1 after this step
+        // column k of the CTA's rows before anybody overwrites it (a thread owns whole columns below)
+        double mik[GJ_MAX_ROWS];
+#pragma unroll
+        for (int li = 0; li < GJ_MAX_ROWS; ++li) mik[li] = li < nr ? sm[li * nc + k] : 0.0;
+        const double ip = 1.0 / __ldcg(prow + k);
+        __syncthreads();
+        for (int j = tid; j < nc; j += GJ_THREADS) {
+            const double pj = __ldcg(prow + j);
+#pragma unroll
+            for (int li = 0; li < GJ_MAX_ROWS; ++li) {
+                if (li < nr) {
+                    const int i = r0 + li;
+                    double v;
+                    if (i == k) v = j == k ? ip : pj * ip;
+                    else v = j == k ? -mik[li] * ip : sm[li * nc + j] - mik[li] * pj * ip;
+                    sm[li * nc + j] = v;
+                    if (i == k + 1) nrow[j] = v;
+                }
+            }
+        }
+        grid.sync();
+    }
+    for (int k = tid; k < nr * nc; k += GJ_THREADS) M[(size_t)r0 * nc + k] = sm[k];
+}
+
+// ------------------------------------------------------------------------------------------------
 // cg_stream: the persistent PCG with K streamed through shared memory by the TMA engine (cp.async.bulk)
 // ------------------------------------------------------------------------------------------------
 // Why: the register-fed SpMV above keeps only a handful of 8-byte loads in flight per thread, so its HBM
@@ -864,6 +981,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     __shared__ double sh4[4];
     __shared__ __align__(8) uint64_t full[ST_MAX_CW][ST_MAX_DEPTH], empty[ST_MAX_CW][ST_MAX_DEPTH];
     __shared__ int s_width[ST_MAX_CW][ST_MAX_DEPTH];  // blocks per row of the slice sitting in a slot
+    __shared__ double s_wp[ST_MAX_CW + 1][BS];        // two-level preconditioner: chunk sums of w = Z^T r
     constexpr int BB = BS * BS;
     constexpr int PS = BS == 3 ? 4 : BS;  // stride of a node in the padded search direction
     const int tid = threadIdx.x;
@@ -954,11 +1072,104 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         for (; f_next < D; ++f_next) fill(f_next);
     }
 
-    // ---- prologue: residual, Jacobi diagonal, norms; multi-GPU: first halo push of z = r / d
+    // ---- two-level preconditioner (precond = 2): z = D^-1 r + Z y, y = E^-1 w, w = Z^T r, for the r every CTA has
+    //      just finished writing.  z is never stored: r.z = sum r^2 d + w.y, so this routine only leaves y in memory
+    //      and returns the thread's share of w.y; the p update forms z_i = d_i r_i + y[agg(i)] on the fly.
+    //      Two more grid barriers per application (r complete -> w; w complete -> y), the third is the reduction
+    //      that follows anyway.
+    const bool two_level = A.precond == 2;
+    auto coarse_apply = [&]() -> double {
+        const CoarseArgs& G = A.co;
+        const int gw = (int)(gtid >> 5), nw = (int)(gsz >> 5);
+        grid.sync();
+        // w = Z^T r: CO_SPLIT warps of one CTA share an aggregate (enough warps in flight to hide the two dependent load
+        // levels: node ids -> residuals); their chunk sums meet in shared memory and are added in chunk order
+        constexpr int AG_PER_CTA = (CW + 1) / CO_SPLIT;
+        for (int base_a = (int)blockIdx.x * AG_PER_CTA; base_a < G.n_agg; base_a += (int)gridDim.x * AG_PER_CTA) {
+            const int m = w / CO_SPLIT, ch = w % CO_SPLIT, a = base_a + m;
+            if (m < AG_PER_CTA && a < G.n_agg) {
+                const int q0 = G.agg_ptr[a], q1 = G.agg_ptr[a + 1];
+                const int len = (q1 - q0 + CO_SPLIT - 1) / CO_SPLIT;
+                const int b0 = q0 + ch * len, b1 = b0 + len < q1 ? b0 + len : q1;
+                double acc[BS];
+#pragma unroll
+                for (int c = 0; c < BS; ++c) acc[c] = 0.0;
+                for (int q = b0 + lane; q < b1; q += 128) {  // four nodes per lane and trip: ids first, then their residuals
+                    int64_t nd[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) nd[u] = q + 32 * u < b1 ? G.agg_nodes[q + 32 * u] : -1;
+                    double rv[4][BS];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) rv[u][c] = nd[u] >= 0 ? A.r[nd[u] * BS + c] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) acc[c] += rv[u][c];
+                }
+#pragma unroll
+                for (int c = 0; c < BS; ++c) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                    if (lane == 0) s_wp[w][c] = acc[c];
+                }
+            }
+            __syncthreads();
+            if (tid < AG_PER_CTA * BS && base_a + tid / BS < G.n_agg) {
+                const int m2 = tid / BS, c = tid % BS;
+                double v = 0.0;
+#pragma unroll
+                for (int k2 = 0; k2 < CO_SPLIT; ++k2) v += s_wp[m2 * CO_SPLIT + k2][c];
+                G.w[(base_a + m2) * BS + c] = v;
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        // y = E^-1 w: one warp per row of the dense inverse (L2-resident); 16-byte loads, 12 + 12 of them in flight per lane
+        double wy = 0.0;
+        for (int k = gw; k < G.nc; k += nw) {
+            double acc = 0.0;
+            if ((G.nc & 1) == 0) {  // rows are 16-byte aligned
+                const double2* row = reinterpret_cast<const double2*>(G.Einv + (size_t)k * G.nc);
+                const double2* wv = reinterpret_cast<const double2*>(G.w);
+                const int n2 = G.nc >> 1;
+                int j = lane;
+                for (; j + 11 * 32 < n2; j += 12 * 32) {
+                    double2 e[12], ww[12];
+#pragma unroll
+                    for (int u = 0; u < 12; ++u) {
+                        e[u] = __ldg(row + j + 32 * u);
+                        ww[u] = __ldcg(wv + j + 32 * u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 12; ++u) acc += e[u].x * ww[u].x + e[u].y * ww[u].y;
+                }
+                for (; j < n2; j += 32) {
+                    const double2 e = __ldg(row + j), ww = __ldcg(wv + j);
+                    acc += e.x * ww.x + e.y * ww.y;
+                }
+            } else {
+                const double* row = G.Einv + (size_t)k * G.nc;
+                for (int j = lane; j < G.nc; j += 32) acc += __ldg(row + j) * __ldcg(G.w + j);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) {
+                G.y[k] = acc;
+                wy += __ldcg(G.w + k) * acc;
+            }
+        }
+        return wy;
+    };
+
+    // ---- prologue: residual, Jacobi diagonal, norms; multi-GPU: first halo push of the preconditioned residual
     double g4[4];
     cg_prologue_body<BS>(A, gtid, gsz, g4);
-    if (mg) {
-        ++hepoch;
+    if (mg) ++hepoch;
+    if (two_level) {
+        g4[P_RZ] += coarse_apply();  // r.z = sum r^2 d (already there) + w.y; z itself is pushed / formed in the p update
+    } else if (mg) {
         for (int64_t i = gtid; i < A.n; i += gsz)
             if (A.mask[i] & 2) p2p_push(P, i, A.r[i] * A.dinv[i], hepoch);
     }
@@ -985,18 +1196,24 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
             double* __restrict__ pv = A.p_pad;
             // one CTA per SM: batches of VB independent dofs per thread keep enough loads in flight
             for (int64_t i0 = gtid; i0 < A.n; i0 += VB * gsz) {
-                double a[VB], b[VB], c[VB];
+                double a[VB], b[VB], c[VB], yc[VB];
 #pragma unroll
                 for (int u = 0; u < VB; ++u) {  // loads of a batch first (tail lanes re-read the last dof: no branches)
                     const int64_t i = i0 + u * gsz < A.n ? i0 + u * gsz : A.n - 1;
                     a[u] = rv[i];
                     b[u] = dv[i];
                     c[u] = pv[pad_of(i)];
+                    yc[u] = 0.0;
+                    if (two_level) yc[u] = __ldcg(A.co.y + (size_t)A.co.agg[i / BS] * BS + (i % BS));
                 }
 #pragma unroll
                 for (int u = 0; u < VB; ++u) {
                     const int64_t i = i0 + u * gsz;
-                    if (i < A.n) pv[pad_of(i)] = a[u] * b[u] + beta * c[u];
+                    if (i < A.n) {
+                        const double zi = b[u] != 0.0 ? a[u] * b[u] + yc[u] : 0.0;  // z = D^-1 r (+ Z y), zero at fixed dofs
+                        pv[pad_of(i)] = zi + beta * c[u];
+                        if (two_level && mg && (A.mask[i] & 2)) p2p_push(P, i, zi, hepoch);  // Jacobi pushed z with the r update
+                    }
                 }
             }
             if (mg) {
@@ -1100,11 +1317,12 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                         const double zi = ri * di[u];
                         s2[0] += ri * ri;
                         s2[1] += ri * zi;
-                        if (mg && (A.mask[i] & 2)) p2p_push(P, i, zi, hepoch);
+                        if (mg && !two_level && (A.mask[i] & 2)) p2p_push(P, i, zi, hepoch);
                     }
                 }
             }
         }
+        if (two_level) s2[1] += coarse_apply();  // r.z = sum r^2 d + w.y
         s2[0] = block_sum<ST_THREADS>(s2[0], sh);
         s2[1] = block_sum<ST_THREADS>(s2[1], sh);
         prof(4);

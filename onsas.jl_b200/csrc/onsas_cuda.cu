@@ -163,6 +163,14 @@ struct onsas_ctx {
     // options
     int cg_mode = 0, asm_minb = 3, check_every = 16, cg_bps = 6;
     int cg_grid = 0, part_stride = 4096;
+    // two-level preconditioner (precond = 2): node aggregates, dense coarse inverse, work vectors
+    struct Coarse {
+        bool built = false;   // aggregates exist for the current mesh
+        bool fresh = false;   // Einv matches the K currently assembled
+        int n_agg = 0, nc = 0;
+    } co;
+    DevBuf<int32_t> co_agg, co_agg_ptr, co_agg_nodes;
+    DevBuf<double> co_E, co_w, co_y, co_rowbuf;
     struct StreamPlan {
         bool built = false, ok = false;
         int n_cw = 0, depth = 0, grid = 0, threads = 0;
@@ -299,6 +307,7 @@ void halo_exchange(onsas_ctx* c, double* v, int gate);
 
 void launch_assemble(onsas_ctx* c) {
     require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
+    c->co.fresh = false;  // K is about to change: the coarse inverse of the two-level preconditioner is stale
     if (c->n_ranks > 1) halo_exchange(c, c->U.p, 0);
     bool wrote = false;
     if (c->n_tets > 0) {
@@ -501,11 +510,123 @@ void launch_stream(onsas_ctx* c, CgArgs A) {
     CUDA_CHECK(cudaLaunchCooperativeKernel(c->st_plan.kern, dim3(c->st_plan.grid), dim3(c->st_plan.threads), args, c->st_plan.smem, c->stream));
 }
 
+// ---------------------------------------------------------------- two-level preconditioner: aggregates + coarse inverse
+constexpr int CO_NC_MAX = 1536;     // coarse dofs: the dense inverse (18.9 MB) stays in L2 and fits the Gauss-Jordan kernel's shared memory
+constexpr int CO_TARGET_NODES = 343;  // nodes per aggregate (7^3) when the mesh is large enough
+
+// k-way recursive coordinate bisection of the owned nodes (deterministic: ties broken by node id)
+void rcb_aggregate(const double* xyz, int dim, std::vector<int32_t>& ids, size_t lo, size_t hi, int parts, int first, std::vector<int32_t>& agg) {
+    if (parts <= 1 || hi - lo <= 1) {
+        for (size_t k = lo; k < hi; ++k) agg[ids[k]] = first;
+        return;
+    }
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (size_t k = lo; k < hi; ++k)
+        for (int d = 0; d < dim; ++d) {
+            const double v = xyz[(size_t)ids[k] * dim + d];
+            mn[d] = std::min(mn[d], v);
+            mx[d] = std::max(mx[d], v);
+        }
+    int ax = 0;
+    for (int d = 1; d < dim; ++d)
+        if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
+    const int p1 = parts / 2;
+    const size_t mid = lo + (hi - lo) * (size_t)p1 / (size_t)parts;
+    std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int32_t a, int32_t b) {
+        const double va = xyz[(size_t)a * dim + ax], vb = xyz[(size_t)b * dim + ax];
+        return va < vb || (va == vb && a < b);
+    });
+    rcb_aggregate(xyz, dim, ids, lo, mid, p1, first, agg);
+    rcb_aggregate(xyz, dim, ids, mid, hi, parts - p1, first + p1, agg);
+}
+
+void build_coarse(onsas_ctx* c) {
+    if (c->co.built) return;
+    const int64_t n = c->n_owned;
+    require(n > 0, ONSAS_ERR_NOT_READY, "two-level preconditioner: no owned nodes");
+    int n_agg = (int)std::max<int64_t>(1, std::min<int64_t>(n / CO_TARGET_NODES, CO_NC_MAX / c->dim));
+    std::vector<int32_t> ids((size_t)n), agg((size_t)n, 0);
+    for (int64_t i = 0; i < n; ++i) ids[i] = (int32_t)i;
+    rcb_aggregate(c->h_xyz.data(), c->dim, ids, 0, (size_t)n, n_agg, 0, agg);
+    std::vector<int32_t> ptr((size_t)n_agg + 1, 0), nodes((size_t)n);
+    for (int64_t i = 0; i < n; ++i) ptr[agg[i] + 1]++;
+    for (int a = 0; a < n_agg; ++a) ptr[a + 1] += ptr[a];
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t i = 0; i < n; ++i) nodes[fill[agg[i]]++] = (int32_t)i;  // ascending node id inside every aggregate
+    const int nc = n_agg * c->dim;
+    cudaStream_t s = c->stream;
+    c->co_agg.upload(agg, s);
+    c->co_agg_ptr.upload(ptr, s);
+    c->co_agg_nodes.upload(nodes, s);
+    c->co_E.alloc((size_t)nc * nc);
+    c->co_w.alloc((size_t)nc);
+    c->co_y.alloc((size_t)nc);
+    c->co_rowbuf.alloc((size_t)2 * nc);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    c->co.n_agg = n_agg;
+    c->co.nc = nc;
+    c->co.built = true;
+    c->co.fresh = false;
+    if (getenv("ONSAS_VERBOSE")) fprintf(stderr, "[onsas] two-level preconditioner: %d aggregates of ~%lld nodes, %d coarse dofs\n", n_agg, (long long)(n / n_agg), nc);
+}
+
+void fill_coarse_args(onsas_ctx* c, CgArgs& A) {
+    A.co.n_agg = c->co.n_agg;
+    A.co.nc = c->co.nc;
+    A.co.agg = c->co_agg.p;
+    A.co.agg_ptr = c->co_agg_ptr.p;
+    A.co.agg_nodes = c->co_agg_nodes.p;
+    A.co.Einv = c->co_E.p;
+    A.co.w = c->co_w.p;
+    A.co.y = c->co_y.p;
+}
+
+// E = Z^T (M K M) Z for the K currently in memory, then its explicit inverse (both deterministic)
+template <int BS>
+void refresh_coarse(onsas_ctx* c, CgArgs& A) {
+    build_coarse(c);
+    fill_coarse_args(c, A);
+    if (c->co.fresh) return;
+    const int nc = c->co.nc;
+    {
+        const size_t smem = ((size_t)BS * nc + (CO_THREADS / (BS * BS)) * BS * BS) * sizeof(double);
+        static size_t configured = 0;
+        if (smem > configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(k_coarse_assemble<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        k_coarse_assemble<BS><<<c->co.n_agg, CO_THREADS, smem, c->stream>>>(A, c->co_E.p);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    {
+        const int rows = (nc + c->n_sm - 1) / c->n_sm;
+        require(rows <= GJ_MAX_ROWS, ONSAS_ERR_UNSUPPORTED, "coarse space too large for the Gauss-Jordan kernel");
+        const int grid = (nc + rows - 1) / rows;
+        const size_t smem = (size_t)rows * nc * sizeof(double);
+        static size_t configured = 0;
+        if (smem > configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(k_gj_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        double* M = c->co_E.p;
+        int ncv = nc, rowsv = rows;
+        double* rb = c->co_rowbuf.p;
+        void* args[] = {&M, &ncv, &rowsv, &rb};
+        CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gj_invert, dim3(grid), dim3(GJ_THREADS), args, smem, c->stream));
+    }
+    c->co.fresh = true;
+}
+
 template <int BS>
 void run_cg_bs(onsas_ctx* c, CgArgs A) {
     const int64_t n = A.n;
     // persistent solver: single GPU, or N GPUs once the peer-memory window is imported; without the window a
     // multi-rank solve runs the multi-launch driver below (NCCL between the phases)
+    if (A.precond == 2) {
+        require(c->cg_mode == 0 && (c->n_ranks == 1 || c->p2p_ready) && plan_stream<BS>(c), ONSAS_ERR_UNSUPPORTED,
+                "the two-level preconditioner runs in the streamed persistent solver only (ONSAS_OPT_CG_MODE = 0)");
+        refresh_coarse<BS>(c, A);
+    }
     if (c->cg_mode != 1 && (c->n_ranks == 1 || c->p2p_ready)) {
         if (c->cg_mode == 0 && plan_stream<BS>(c)) {
             launch_stream<BS>(c, A);
@@ -886,6 +1007,8 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         CUDA_CHECK(cudaStreamSynchronize(s));
         c->cg_grid = 0;
         c->st_plan.built = false;
+        c->co.built = false;
+        c->co.fresh = false;
         c->n_patterns = 0;
         c->patterns.release();
         c->finalized = true;
@@ -1094,7 +1217,7 @@ static void step_impl(onsas_ctx* c, bool assemble, int32_t precond, double relto
                       int update_U, onsas_step_info* info) {
     require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
     require(info != nullptr, ONSAS_ERR_INVALID_ARG, "info is NULL");
-    require(precond == 0 || precond == 1, ONSAS_ERR_INVALID_ARG, "unknown preconditioner");
+    require(precond >= 0 && precond <= 2, ONSAS_ERR_INVALID_ARG, "unknown preconditioner");
     CUDA_CHECK(cudaEventRecord(c->ev[0], c->stream));
     if (assemble) launch_assemble(c);
     CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
@@ -1126,7 +1249,7 @@ int32_t onsas_pcg(onsas_ctx* c, const double* b, double* x, int32_t precond, dou
     if (!c || !b || !x) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
-        require(precond == 0 || precond == 1, ONSAS_ERR_INVALID_ARG, "unknown preconditioner");
+        require(precond >= 0 && precond <= 2, ONSAS_ERR_INVALID_ARG, "unknown preconditioner");
         CUDA_CHECK(cudaMemcpyAsync(c->rhs.p, b, c->n_local_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CgArgs A = make_cg_args(c, precond, reltol, abstol, maxiter, true, 0);
         run_cg(c, A);
@@ -1252,7 +1375,7 @@ int32_t onsas_get_cg_profile(onsas_ctx* c, int64_t out[8]) {
         for (size_t k = 16; k < 16 + 2048; ++k) mx = std::max(mx, h[k]);
         out[7] = mx;
         if (getenv("ONSAS_PROF_VERBOSE"))
-            fprintf(stderr, "[onsas prof] aux counters: %lld %lld %lld\n", h[8], h[9], h[10]);
+            fprintf(stderr, "[onsas prof] two-level, cycles of block 0: sync %lld, w %lld, sync %lld, y %lld, sync %lld, z %lld\n", h[8], h[9], h[10], h[11], h[12], h[13]);
         if (const char* f = getenv("ONSAS_PROF_DUMP")) {  // diagnostics: per-CTA SpMV cycles of the last profiled solve
             if (FILE* fp = fopen(f, "w")) {
                 for (size_t k = 16; k < h.size(); ++k) fprintf(fp, "%lld\n", h[k]);

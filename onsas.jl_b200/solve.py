@@ -104,14 +104,14 @@ class NewtonRaphson:
     def __init__(self, tol: ConvergenceSettings | None = None, *, preconditioner="jacobi", cg_reltol=None,
                  cg_abstol=0.0, cg_maxiter=0, device=0, cg_mode=None):
         self.tol = tol or ConvergenceSettings()
-        assert preconditioner in ("jacobi", "none")
+        assert preconditioner in ("jacobi", "none", "two_level")
         self.preconditioner = preconditioner
         self.cg_reltol = math.sqrt(np.finfo(np.float64).eps) if cg_reltol is None else float(cg_reltol)
         self.cg_abstol, self.cg_maxiter, self.device, self.cg_mode = float(cg_abstol), int(cg_maxiter), device, cg_mode
 
     @property
     def precond_code(self):
-        return L.PRECOND_JACOBI if self.preconditioner == "jacobi" else L.PRECOND_NONE
+        return {"jacobi": L.PRECOND_JACOBI, "two_level": L.PRECOND_TWO_LEVEL}.get(self.preconditioner, L.PRECOND_NONE)
 
 
 NewtonRaphsonCUDA = NewtonRaphson

@@ -15,20 +15,32 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     mesh, free, U_half, U_prev, Fext = bench.build_problem(55, 1)
     ctx = ob.context_from_flat(mesh.xyz, tets=mesh.tets, mat_kind=[ob.MAT_NEOHOOKEAN], mat_params=[[bench.KBULK, bench.MU]], free_dofs=free)
     ctx.set_Fext(Fext)
-    for llbar in (0,):
+    for precond in (ob.PRECOND_JACOBI, ob.PRECOND_TWO_LEVEL):
         for prof in (0, 0, 1):
             ctx.set_option(L.OPT_CG_PROFILE, prof)
             ctx.set_U(U_prev)
-            info = ctx.newton_step(ob.PRECOND_JACOBI)
-            line = (f"cw={os.environ.get('ONSAS_STREAM_CW', '12')} depth={os.environ.get('ONSAS_STREAM_DEPTH', '2')} prof={prof} "
-                    f"cg_iters={info.cg_iters} ms_solve={info.ms_solve:.2f} us/iter={1e3 * info.ms_solve / info.cg_iters:.2f}")
+            info = ctx.newton_step(precond)
+            line = (f"cw={os.environ.get('ONSAS_STREAM_CW', '12')} depth={os.environ.get('ONSAS_STREAM_DEPTH', '2')} precond={precond} prof={prof} "
+                    f"cg_iters={info.cg_iters} ms_solve={info.ms_solve:.2f} us/iter={1e3 * info.ms_solve / info.cg_iters:.2f} |dU|={info.norm_dU:.10e}")
             if prof:
                 pv = ctx.cg_profile()
                 slow = pv.pop("slowest_cta_spmv", 0)
                 tot = sum(pv.values())
                 line += " | " + " ".join(f"{k}={v / info.cg_iters:.0f}" for k, v in pv.items()) + f" cyc/iter={tot / info.cg_iters:.0f} slowest_warp_spmv/iter={slow / info.cg_iters:.0f}"
             print(line, flush=True)
+    # set-up cost of the two-level preconditioner: the first solve after an assembly builds and inverts E
+    import time
+    import numpy as np
+    b = np.random.default_rng(0).standard_normal(mesh.n_nodes * 3)
+    ctx.set_option(L.OPT_CG_PROFILE, 0)
+    ctx.set_U(U_prev)
+    ctx.assemble()
+    ctx.synchronize()
+    for k in range(3):
+        t0 = time.perf_counter()
+        x, its, res = ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-6)
+        print(f"two-level pcg call {k} (first one includes the coarse set-up): {1e3 * (time.perf_counter() - t0):.2f} ms, {its} iterations", flush=True)
 else:
-    for cw, depth in ((12, 2), (8, 3)):
+    for cw, depth in ((12, 2),):
         env = dict(os.environ, ONSAS_STREAM_CW=str(cw), ONSAS_STREAM_DEPTH=str(depth))
         subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, timeout=300)

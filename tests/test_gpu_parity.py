@@ -325,3 +325,56 @@ def test_random_node_and_element_numbering(ob, oracle, mat):
     Uref = U.copy()
     Uref[free] += spla.spsolve(A[free][:, free].tocsc(), (Fext - ref.F_int)[free])
     assert cases.rel_err(ctx.get_U(), Uref) < 1e-8
+
+
+def test_two_level_preconditioner(ob, oracle):
+    """Jacobi + aggregated coarse space (precond = 2).  Same solution as the direct solve, far fewer
+    iterations than Jacobi on a mesh with several aggregates, bitwise reproducible, coarse inverse refreshed after a
+    re-assembly, and rejected outside the streamed solver."""
+    m, _ = cases.box_model(24, 12, 12, mat="neo", jitter=0.1)      # 4225 nodes -> 12 aggregates
+    U = cases.random_U(m, 0.002)
+    ref = oracle.Assembly(m).assemble(U)
+    ctx = _ctx(ob, m)
+    ctx.set_U(U)
+    ctx.assemble()
+    rng = np.random.default_rng(8)
+    b = rng.standard_normal(m.n_dofs)
+    import scipy.sparse.linalg as spla
+    A = ref.csr()
+    free = m.free_dofs
+    xd = np.zeros(m.n_dofs)
+    xd[free] = spla.spsolve(A[free][:, free].tocsc(), b[free])
+    xj, itj, _ = ctx.pcg(b, ob.PRECOND_JACOBI, 1e-12)
+    x2, it2, res2 = ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-12)
+    assert cases.rel_err(x2, xd) < 1e-8 and cases.rel_err(xj, xd) < 1e-8
+    assert np.all(x2[m.free_mask() == 0] == 0)
+    assert it2 < 0.8 * itj, (it2, itj)
+    x3, it3, _ = ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-12)
+    assert it3 == it2
+    np.testing.assert_array_equal(x3, x2)
+    # a new K (other state): the coarse operator follows it
+    U2 = cases.random_U(m, 0.004, seed=9)
+    ref2 = oracle.Assembly(m).assemble(U2)
+    ctx.set_U(U2)
+    ctx.assemble()
+    A2 = ref2.csr()
+    xd2 = np.zeros(m.n_dofs)
+    xd2[free] = spla.spsolve(A2[free][:, free].tocsc(), b[free])
+    x4, it4, _ = ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-12)
+    x5, it5, _ = ctx.pcg(b, ob.PRECOND_JACOBI, 1e-12)
+    assert cases.rel_err(x5, xd2) < 1e-8 and cases.rel_err(x4, xd2) < 1e-8 and it4 < 0.8 * it5
+    # one aggregate only (tiny mesh): still a valid preconditioner
+    ms, _ = cases.box_model(3, 2, 2, mat="svk")
+    cs = _ctx(ob, ms)
+    cs.set_U(cases.random_U(ms, 0.01))
+    cs.assemble()
+    bs = rng.standard_normal(ms.n_dofs)
+    refs = oracle.Assembly(ms).assemble(cases.random_U(ms, 0.01))
+    xs, its, _ = cs.pcg(bs, ob.PRECOND_TWO_LEVEL, 1e-12)
+    xds = np.zeros(ms.n_dofs)
+    xds[ms.free_dofs] = spla.spsolve(refs.csr()[ms.free_dofs][:, ms.free_dofs].tocsc(), bs[ms.free_dofs])
+    assert cases.rel_err(xs, xds) < 1e-8
+    # only the streamed solver implements it
+    ctx.set_option(ob._lib.OPT_CG_MODE, 1)
+    with pytest.raises(ob.OnsasError):
+        ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-12)
