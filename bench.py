@@ -217,6 +217,25 @@ def run_ours(args):
                        info.norm_r / info.norm_Fext, info.norm_dU / max(info.norm_U, 1e-300)))
     newton.sort()
     nw = newton[len(newton) // 2]
+    # ---- (3b) the same Newton step with the two-level preconditioner (Jacobi + aggregated coarse space);
+    #      its time includes the coarse set-up (E = Z^T K Z and its inverse are rebuilt after every assembly)
+    nw2 = None
+    try:
+        if N > 1 and not os.environ.get("ONSAS_BENCH_TWO_LEVEL_MULTI"):
+            raise ob.OnsasError(0, "not enabled at N > 1 (set ONSAS_BENCH_TWO_LEVEL_MULTI=1)")
+        newton2 = []
+        for _ in range(max(1, min(K, 3))):
+            ctx.set_U(loc(U_prev))
+            barrier()
+            info = ctx.newton_step(ob.PRECOND_TWO_LEVEL)
+            newton2.append((max_over_ranks(info.ms_assemble + info.ms_solve), info.ms_assemble, info.ms_solve, int(info.cg_iters),
+                            info.norm_dU / max(info.norm_U, 1e-300)))
+        newton2.sort()
+        nw2 = newton2[len(newton2) // 2]
+    except ob.OnsasError as exc:   # e.g. --no-p2p: only the streamed persistent solver implements it
+        nw2 = None
+        if rank == 0:
+            print(f"[bench] two-level Newton step skipped: {exc}", file=sys.stderr)
 
     # ---- (4) SpMV alone (secondary roofline)
     for _ in range(3):
@@ -259,6 +278,9 @@ def run_ours(args):
         "newton_step_ms": nw[0], "newton_step": {"ms_assemble": nw[1], "ms_solve": nw[2], "cg_iters": nw[3], "precond": "jacobi",
                                                   "cg_reltol": float(np.sqrt(np.finfo(np.float64).eps)), "rel_residual_in": nw[4],
                                                   "rel_dU": nw[5]},
+        "newton_step_two_level": None if nw2 is None else {
+            "ms": nw2[0], "ms_assemble": nw2[1], "ms_solve": nw2[2], "cg_iters": nw2[3], "rel_dU": nw2[4],
+            "precond": "jacobi + aggregated coarse space (precond = 2), coarse set-up inside ms_solve"},
         "e2e": {"value": e2e_value, "unit": "tets/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(ctx.n_dofs * 8),
                 "d2h_bytes_per_step": int(ctx.n_dofs * 8), "what": "onsas_set_U(pinned host) + onsas_assemble + onsas_get_Fint(pinned host)"},
         "gpu_launches": K * (1 if N == 1 else 2),

@@ -1,5 +1,5 @@
 """Small driver for ncu / compute-sanitizer: a few launches of each hot kernel, no CPU baseline.
-usage: python scripts/profile_target.py [cells] [mat] [n_asm] [n_spmv] [newton 0/1]"""
+usage: python scripts/profile_target.py [cells] [mat] [n_asm] [n_spmv] [newton 0/1] [precond 0/1/2]"""
 import os
 import sys
 
@@ -14,6 +14,7 @@ mat = sys.argv[2] if len(sys.argv) > 2 else "neo"
 n_asm = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 n_spmv = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 newton = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+precond = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 minb = int(os.environ.get("ONSAS_ASM_MINB", "2"))
 
 mesh, free, U_half, U_prev, Fext = bench.build_problem(cells, 1)
@@ -32,8 +33,9 @@ for _ in range(n_spmv):
 ctx.synchronize()
 if newton:
     ctx.set_U(U_prev)
-    info = ctx.newton_step(ob.PRECOND_JACOBI)
-    print("newton step: cg_iters", info.cg_iters, "ms_assemble", info.ms_assemble, "ms_solve", info.ms_solve)
+    info = ctx.newton_step(precond)
+    print("newton step: precond", precond, "cg_iters", info.cg_iters, "ms_assemble", info.ms_assemble, "ms_solve", info.ms_solve)
+if newton and os.environ.get("ONSAS_PROFILE_MULTILAUNCH"):
     ctx.set_option(ob._lib.OPT_CG_MODE, 1)
     ctx.set_U(U_prev)
     info = ctx.newton_step(ob.PRECOND_JACOBI)
