@@ -16,6 +16,7 @@ from .model import (SVK, Circle, FixedField, GenericCrossSection, GlobalLoad, Gr
 from .solve import (ConvergenceSettings, DeltaUCriterion, LinearStaticAnalysis, MaxIterCriterion,  # noqa: F401
                     NewtonRaphson, NewtonRaphsonCUDA, NonLinearStaticAnalysis, NotConvergedYet,
                     ResidualForceCriterion, ResidualsIterationStep, Solution, isconverged, solve, solve_)
+from .vtk import write_vtk, write_vtu  # noqa: F401
 
 
 def build(verbose: bool = False) -> str:

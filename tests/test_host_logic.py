@@ -338,3 +338,60 @@ def test_two_rank_halo_exchange_gloo(oracle, hostsim, tmp_path):
     assert cases.rel_err(y, yref) < 1e-13
     d0, d1 = np.load(tmp_path / "d0.npy"), np.load(tmp_path / "d1.npy")
     assert d0 == d1 and d0[0] == pytest.approx(xg @ yref, rel=1e-12)
+
+
+# ----------------------------------------------------------------------------- result hand-back
+
+def test_write_vtk_from_flat_solution(ob, tmp_path):
+    """write_vtk (Interfaces/VTK.jl:209-262) from the flat per-step arrays: cell types, point vector field with the
+    reference's component names, one scalar cell array per tensor label taken at the (i, j) the label names."""
+    from onsas_jl_b200 import vtk
+    s, n, t = _uniaxial_structure(ob)
+    sa = ob.NonLinearStaticAnalysis(s, np.linspace(0.5, 1.0, 2))
+    sol = ob.Solution(sa, ob.NewtonRaphson())
+    rng = np.random.default_rng(3)
+    fl = s.flat
+    for _ in range(2):
+        sol.U.append(rng.standard_normal(fl.n_dofs))
+        sol.tet_stress.append(rng.standard_normal((len(fl.tets), 9)))
+        sol.tet_strain.append(rng.standard_normal((len(fl.tets), 9)))
+    path = ob.write_vtk(sol, str(tmp_path / "uniaxial"), 2)
+    assert path.endswith("uniaxial.vtu") and os.path.exists(path)
+    arrays, meta = vtk.read_vtu(path)
+    assert meta["n_points"] == 8 and meta["n_cells"] == 6
+    np.testing.assert_array_equal(arrays["Points"], fl.xyz)
+    np.testing.assert_array_equal(arrays["connectivity"].reshape(-1, 4), fl.tets)
+    np.testing.assert_array_equal(arrays["offsets"], 4 * np.arange(1, 7))
+    assert set(arrays["types"].tolist()) == {10}                                   # VTK_TETRA
+    np.testing.assert_array_equal(arrays["Displacement"], sol.U[1].reshape(-1, 3))
+    assert meta["component_names"]["Displacement"] == ["ux", "uy", "uz"]
+    sig = sol.tet_stress[1].reshape(-1, 3, 3).transpose(0, 2, 1)                   # column-major 3x3 -> [e, i, j]
+    eps = sol.tet_strain[1].reshape(-1, 3, 3).transpose(0, 2, 1)
+    np.testing.assert_array_equal(arrays["σxx"], sig[:, 0, 0])
+    np.testing.assert_array_equal(arrays["τyz"], sig[:, 1, 2])
+    np.testing.assert_array_equal(arrays["τzy"], sig[:, 2, 1])
+    np.testing.assert_array_equal(arrays["τzx"], sig[:, 2, 0])
+    np.testing.assert_array_equal(arrays["γxy"], eps[:, 0, 1])
+    np.testing.assert_array_equal(arrays["γyx"], eps[:, 1, 0])
+    assert len([k for k in arrays if k[0] in "στϵγ"]) == 18
+    # only displacements
+    arrays_u, _ = vtk.read_vtu(ob.write_vtk(sol, str(tmp_path / "u_only.vtu"), 1, fields=("u",)))
+    assert "σxx" not in arrays_u and "Displacement" in arrays_u
+    # the time series: one file per stored step + the ParaView collection with the load factors as times
+    pvd = ob.write_vtk(sol, str(tmp_path / "series"))
+    text = open(pvd, encoding="utf-8").read()
+    assert pvd.endswith("series.pvd") and 'timestep="0.5"' in text and 'timestep="1.0"' in text
+    assert os.path.exists(tmp_path / "series_timestep_1.vtu") and os.path.exists(tmp_path / "series_timestep_2.vtu")
+    assert 'file="series_timestep_2.vtu"' in text
+    # NaN in a cell field is refused like the reference's @assert (VTK.jl:139-140); a bad step index too
+    sol.tet_stress[0][0, 0] = np.nan
+    with pytest.raises(AssertionError):
+        ob.write_vtk(sol, str(tmp_path / "bad"), 1)
+    with pytest.raises(IndexError):
+        ob.write_vtk(sol, str(tmp_path / "bad"), 3)
+    # trusses become VTK_LINE cells after the tets
+    p2 = vtk.write_vtu(str(tmp_path / "mixed"), np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]), trusses=[[0, 1], [1, 2]],
+                       cell_data={"σxx": np.array([1.0, 2.0])})
+    a2, m2 = vtk.read_vtu(p2)
+    assert m2["n_cells"] == 2 and a2["types"].tolist() == [3, 3] and a2["offsets"].tolist() == [2, 4]
+    assert a2["Points"].shape == (3, 3) and np.all(a2["Points"][:, 2] == 0)
