@@ -71,6 +71,8 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_CG_CHECK_EVERY 3 /* multi-launch CG: iterations enqueued between host convergence checks (default 16) */
 #define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: resident CTAs per SM the kernel is compiled for: 4, 5 or 6 (default 6); 1-3 shrink the grid */
 #define ONSAS_OPT_FORCE_MG 6         /* diagnostics: set before onsas_finalize_mesh to run the multi-GPU CG kernel with a single rank */
+#define ONSAS_OPT_GJ_BLOCKED 8        /* two-level preconditioner: 1 = coarse inverse by 12-row panels (default), 0 = one pivot row per grid barrier */
+#define ONSAS_OPT_HOST_CHUNKS 7       /* onsas_assemble_host: slice ranges the assembly is cut into so that the copies of U and F_int overlap it (default 4; 1 = no overlap) */
 #define ONSAS_OPT_CG_PROFILE 5       /* 1 = the persistent CG kernel records per-phase SM-clock cycles (onsas_get_cg_profile) */
 
 /* ---------------------------------------------------------------- life cycle */
@@ -139,6 +141,14 @@ int32_t onsas_clear_loads(onsas_ctx* ctx);
 /* assemble!(s, sa): reset, evaluate every element at the current U, assemble F_int, K, stress, strain.
  * StructuralAnalyses/StaticAnalyses.jl:99-132.  Multi-GPU: refreshes the halo part of U first. */
 int32_t onsas_assemble(onsas_ctx* ctx);
+
+/* assemble!(s, sa) with the state on the HOST on both sides, the way the reference's caller holds it
+ * (`displacements(state)` in, `internal_forces(state)` out; StaticAnalyses.jl:99-122, StaticStates.jl:33-102):
+ * U (dim * n_local_nodes doubles) is copied in, K / F_int / stress / strain are assembled on the device and F_int
+ * (same length; zero on halo nodes) is copied out.  Equivalent to onsas_set_U + onsas_assemble + onsas_get_Fint and bitwise
+ * identical in every result, but the two copies are pipelined with the kernel over ONSAS_OPT_HOST_CHUNKS slice ranges
+ * (pinned host buffers are needed for the overlap, not for correctness).  Synchronous: both buffers are free on return. */
+int32_t onsas_assemble_host(onsas_ctx* ctx, const double* U, double* F_int);
 
 /* internal_forces(mat, e, u_e[, cache]) for elements [first, first+count) of one family, un-assembled:
  * f (ndof_e per element), K (ndof_e^2, column-major), sig, eps (9 each, column-major).

@@ -21,6 +21,7 @@ STRAIN_ROTATED_ENGINEERING, STRAIN_GREEN = 0, 1
 FAMILY_TET, FAMILY_TRUSS = 0, 1
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_TWO_LEVEL = 0, 1, 2
 OPT_CG_MODE, OPT_ASM_MINBLOCKS, OPT_CG_CHECK_EVERY, OPT_CG_BLOCKS_PER_SM, OPT_CG_PROFILE, OPT_FORCE_MG = 1, 2, 3, 4, 5, 6
+OPT_HOST_CHUNKS, OPT_GJ_BLOCKED = 7, 8
 
 
 class StepInfo(C.Structure):
@@ -59,6 +60,7 @@ SIGNATURES = {
     "onsas_clear_loads": (C.c_int32, [_vp]),
     "onsas_get_dU": (C.c_int32, [_vp, _dp]),
     "onsas_assemble": (C.c_int32, [_vp]),
+    "onsas_assemble_host": (C.c_int32, [_vp, _dp, _dp]),
     "onsas_eval_elements": (C.c_int32, [_vp, C.c_int32, C.c_int64, C.c_int64, _dp, _dp, _dp, _dp]),
     "onsas_newton_step": (C.c_int32, [_vp, C.c_int32, C.c_double, C.c_double, C.c_int64, C.POINTER(StepInfo)]),
     "onsas_step": (C.c_int32, [_vp, C.c_int32, C.c_double, C.c_double, C.c_int64, C.c_int32, C.POINTER(StepInfo)]),

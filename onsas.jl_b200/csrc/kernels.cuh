@@ -54,6 +54,7 @@ struct AsmArgs {
     int max_pairs;     // sizes of the shared-memory regions
     int max_width;
     int64_t n_rows_guard;  // number of owned rows (the last slice may be partial)
+    int slice0;            // first slice of this launch (CTA b works on slice slice0 + b): onsas_assemble_host launches ranges
 };
 
 template <int KIND>
@@ -155,7 +156,8 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     const int tid = threadIdx.x, nth = blockDim.x;
 
     // ---- level 1: the slice header (same address for every thread: one sector, broadcast)
-    const int4* hp = reinterpret_cast<const int4*>(A.hdr + blockIdx.x);
+    const int slice = A.slice0 + (int)blockIdx.x;
+    const int4* hp = reinterpret_cast<const int4*>(A.hdr + slice);
     const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2);
     const int64_t p0 = (int64_t)(uint32_t)h0.x | ((int64_t)h0.y << 32);
     const int64_t base = (int64_t)(uint32_t)h0.z | ((int64_t)h0.w << 32);
@@ -234,7 +236,7 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
             const int j = w - nK;
             const int lane = j / DIM, r = j % DIM;
             const int t0 = row_off(lane), t1 = row_off(lane + 1);
-            const int64_t row = (int64_t)blockIdx.x * C + lane;
+            const int64_t row = (int64_t)slice * C + lane;
             if (t1 > t0 || !ACCUM) {
                 double acc = 0.0;
                 for (int tt = t0; tt < t1; ++tt) acc += stage[tt * REC + lane + FOFF + r];
@@ -874,6 +876,105 @@ __global__ void __launch_bounds__(GJ_THREADS, 1) k_gj_invert(double* M, int nc, 
                     if (i == k + 1) nrow[j] = v;
                 }
             }
+        }
+        grid.sync();
+    }
+    for (int k = tid; k < nr * nc; k += GJ_THREADS) M[(size_t)r0 * nc + k] = sm[k];
+}
+
+// Blocked form of the same inversion (default): the rows of one CTA (GJ_MAX_ROWS = 12) are one pivot PANEL, so the
+// matrix is eliminated in nc / 12 steps instead of nc -- 128 grid barriers instead of 1536 for the largest coarse space.
+// Step k, with P the panel's rows / columns, D = A[P,P] and R the panel's rows after its own factorisation
+// (R = D^-1 A[P,:], R[:,P] = D^-1; published to `rowbuf` by its owner):
+//     every other CTA:  L = A[rows,P];  A[rows,j] = (j in P ? 0 : A[rows,j]) - L R[:,j]
+// and the owner of panel k+1, as soon as its rows are updated, factorises and publishes them before the step's
+// single grid barrier (look-ahead), so the critical path of a step is update + 12x12 inverse + one barrier.
+// Same fixed operation order on every run: the explicit inverse stays bitwise reproducible.
+constexpr int GJ_B = GJ_MAX_ROWS;
+__global__ void __launch_bounds__(GJ_THREADS, 1) k_gj_invert_blocked(double* M, int nc, double* rowbuf /*[2][GJ_B][nc]*/) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double sm[];      // [GJ_B][nc] rows of this CTA, then L [GJ_B][GJ_B], D [GJ_B][GJ_B]
+    double* Lm = sm + (size_t)GJ_B * nc;
+    double* Dm = Lm + GJ_B * GJ_B;
+    const int tid = threadIdx.x, c = blockIdx.x;
+    const int r0 = c * GJ_B;
+    const int nr = nc - r0 < GJ_B ? nc - r0 : GJ_B;  // >= 1: the grid is ceil(nc / GJ_B)
+    const int np = (nc + GJ_B - 1) / GJ_B;
+    for (int k = tid; k < nr * nc; k += GJ_THREADS) sm[k] = M[(size_t)r0 * nc + k];
+    __syncthreads();
+
+    // this CTA's rows are the pivot panel: D^-1 by unblocked Gauss-Jordan in shared memory (no pivoting: SPD), then
+    // rows <- D^-1 rows with D^-1 itself in the panel's columns; the result is stored locally and published
+    auto factor_and_publish = [&](double* out) {
+        const int i = tid / GJ_B, j = tid % GJ_B;
+        const bool mine = tid < GJ_B * GJ_B && i < nr && j < nr;
+        if (mine) Dm[i * GJ_B + j] = sm[i * nc + r0 + j];
+        __syncthreads();
+        for (int s = 0; s < nr; ++s) {
+            double v = 0.0;
+            if (mine) {
+                const double ip = 1.0 / Dm[s * GJ_B + s];
+                const double dis = Dm[i * GJ_B + s], dsj = Dm[s * GJ_B + j];
+                if (i == s) v = j == s ? ip : dsj * ip;
+                else v = j == s ? -dis * ip : Dm[i * GJ_B + j] - dis * dsj * ip;
+            }
+            __syncthreads();
+            if (mine) Dm[i * GJ_B + j] = v;
+            __syncthreads();
+        }
+        for (int col = tid; col < nc; col += GJ_THREADS) {
+            double a[GJ_B];
+#pragma unroll
+            for (int q = 0; q < GJ_B; ++q) a[q] = q < nr ? sm[q * nc + col] : 0.0;
+            const bool inP = col >= r0 && col < r0 + nr;
+#pragma unroll
+            for (int li = 0; li < GJ_B; ++li) {
+                if (li < nr) {
+                    double v;
+                    if (inP) {
+                        v = Dm[li * GJ_B + (col - r0)];
+                    } else {
+                        v = 0.0;
+#pragma unroll
+                        for (int q = 0; q < GJ_B; ++q)
+                            if (q < nr) v += Dm[li * GJ_B + q] * a[q];
+                    }
+                    sm[li * nc + col] = v;
+                    out[(size_t)li * nc + col] = v;
+                }
+            }
+        }
+    };
+
+    if (c == 0) factor_and_publish(rowbuf);
+    grid.sync();
+    for (int k = 0; k < np; ++k) {
+        const int pk0 = k * GJ_B;
+        const int pn = nc - pk0 < GJ_B ? nc - pk0 : GJ_B;
+        const double* R = rowbuf + (size_t)(k & 1) * GJ_B * nc;
+        if (c != k) {
+            for (int t = tid; t < GJ_B * GJ_B; t += GJ_THREADS) {
+                const int li = t / GJ_B, q = t % GJ_B;
+                Lm[t] = (li < nr && q < pn) ? sm[li * nc + pk0 + q] : 0.0;  // zero padding: the loops below run to GJ_B
+            }
+            __syncthreads();
+            for (int col = tid; col < nc; col += GJ_THREADS) {
+                double rj[GJ_B];
+#pragma unroll
+                for (int q = 0; q < GJ_B; ++q) rj[q] = q < pn ? __ldcg(R + (size_t)q * nc + col) : 0.0;
+                const bool inP = col >= pk0 && col < pk0 + pn;
+#pragma unroll
+                for (int li = 0; li < GJ_B; ++li) {
+                    if (li < nr) {
+                        double acc = inP ? 0.0 : sm[li * nc + col];
+#pragma unroll
+                        for (int q = 0; q < GJ_B; ++q) acc -= Lm[li * GJ_B + q] * rj[q];
+                        sm[li * nc + col] = acc;
+                    }
+                }
+            }
+            __syncthreads();
+            if (c == k + 1) factor_and_publish(rowbuf + (size_t)((k + 1) & 1) * GJ_B * nc);
         }
         grid.sync();
     }

@@ -171,6 +171,18 @@ struct onsas_ctx {
     } co;
     DevBuf<int32_t> co_agg, co_agg_ptr, co_agg_nodes;
     DevBuf<double> co_E, co_w, co_y, co_rowbuf;
+    // onsas_assemble_host: slice ranges launched one after the other while the copies of U (in) and F_int (out) overlap them
+    int64_t asm_first = 0, asm_count = -1;  // slice range of the next assembly launches (-1: all slices)
+    int host_chunks = 4;
+    bool gj_blocked = true;  // coarse inverse by the panel (blocked) Gauss-Jordan kernel; false: one pivot row per grid barrier
+    struct HostPlan {
+        bool built = false;
+        std::vector<int64_t> slice0;   // [n_chunks + 1]
+        std::vector<int64_t> node_hi;  // [n_chunks] the chunk's elements touch nodes [0, node_hi) only
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        cudaEvent_t ev_start = nullptr;
+        std::vector<cudaEvent_t> ev_in, ev_k;
+    } hp;
     struct StreamPlan {
         bool built = false, ok = false;
         int n_cw = 0, depth = 0, grid = 0, threads = 0;
@@ -250,7 +262,7 @@ void launch_asm_inst(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kern<<<(unsigned)c->tab.n_slices, threads, smem, c->stream>>>(A);
+    kern<<<(unsigned)(c->asm_count < 0 ? c->tab.n_slices : c->asm_count), threads, smem, c->stream>>>(A);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -262,7 +274,7 @@ void launch_asm_reg(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kern<<<(unsigned)c->tab.n_slices, threads, smem, c->stream>>>(A);
+    kern<<<(unsigned)(c->asm_count < 0 ? c->tab.n_slices : c->asm_count), threads, smem, c->stream>>>(A);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -295,6 +307,7 @@ AsmArgs make_asm_args(onsas_ctx* c, int family) {
     A.F_int = c->Fint.p;
     A.elem_out = family == 0 ? c->tet_out.p : c->truss_out.p;
     A.err_flag = c->err_flag.p;
+    A.slice0 = (int)c->asm_first;
     return A;
 }
 
@@ -304,11 +317,11 @@ int round_threads(int pairs) {
 }
 
 void halo_exchange(onsas_ctx* c, double* v, int gate);
+void download(onsas_ctx* c, double* h, const double* d, size_t n);
+void check_deferred(onsas_ctx* c);
 
-void launch_assemble(onsas_ctx* c) {
-    require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
-    c->co.fresh = false;  // K is about to change: the coarse inverse of the two-level preconditioner is stale
-    if (c->n_ranks > 1) halo_exchange(c, c->U.p, 0);
+// the assembly kernels of every element family over the slice range [c->asm_first, c->asm_first + c->asm_count)
+void launch_assemble_range(onsas_ctx* c) {
     bool wrote = false;
     if (c->n_tets > 0) {
         AsmArgs A = make_asm_args(c, 0);
@@ -343,6 +356,105 @@ void launch_assemble(onsas_ctx* c) {
         c->val.zero(c->stream);
         c->Fint.zero(c->stream);
     }
+}
+
+void launch_assemble(onsas_ctx* c) {
+    require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
+    c->co.fresh = false;  // K is about to change: the coarse inverse of the two-level preconditioner is stale
+    if (c->n_ranks > 1) halo_exchange(c, c->U.p, 0);
+    c->asm_first = 0;
+    c->asm_count = -1;
+    launch_assemble_range(c);
+}
+
+// ---------------------------------------------------------------- assemble! with host buffers on both sides
+// U travels in and F_int travels out in pieces that overlap the kernel: the slices are cut into `host_chunks` ranges;
+// range k starts as soon as the nodes its elements touch, [0, node_hi[k]), have arrived (copy stream, ascending
+// prefixes of U), and its rows of F_int leave on a third stream while range k + 1 computes.  With a banded node
+// numbering (any mesh numbered for locality) node_hi grows with k and the copies hide behind the kernels; with an
+// arbitrary numbering node_hi[0] = n_nodes and the call degenerates to copy-in, compute, overlapped copy-out.
+// K, F_int and the element records are bitwise what onsas_set_U + onsas_assemble produce (same kernel, same slices).
+void build_host_plan(onsas_ctx* c) {
+    auto& H = c->hp;
+    if (H.built && (int)H.node_hi.size() == std::max(1, c->host_chunks)) return;
+    const int64_t ns = c->tab.n_slices;
+    const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, c->host_chunks), ns));
+    H.slice0.assign((size_t)nch + 1, 0);
+    for (int k = 0; k <= nch; ++k) H.slice0[k] = ns * k / nch;
+    H.node_hi.assign((size_t)nch, 0);
+    for (int k = 0; k < nch; ++k) {
+        int64_t hi = std::min<int64_t>(H.slice0[k + 1] * SLICE_ROWS, c->n_nodes);  // the rows themselves
+        for (int f = 0; f < 2; ++f) {
+            const FamilyTables& T = c->tab.fam[f];
+            if (T.n_elem == 0 || T.hdr.empty() || H.slice0[k + 1] == H.slice0[k]) continue;
+            const SliceHdr& h0 = T.hdr[(size_t)H.slice0[k]];
+            const SliceHdr& h1 = T.hdr[(size_t)H.slice0[k + 1] - 1];
+            const int64_t q0 = h0.pair_base * T.npe, q1 = (h1.pair_base + h1.n_pairs) * T.npe;
+            int32_t mx = -1;
+#pragma omp parallel for reduction(max : mx)
+            for (int64_t q = q0; q < q1; ++q) mx = std::max(mx, T.pair_nodes[(size_t)q]);
+            hi = std::max<int64_t>(hi, (int64_t)mx + 1);
+        }
+        H.node_hi[k] = std::max(hi, k > 0 ? H.node_hi[k - 1] : 0);
+    }
+    if (!H.s_in) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&H.s_in, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&H.s_out, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&H.ev_start, cudaEventDisableTiming));
+    }
+    while ((int)H.ev_in.size() < nch) {
+        cudaEvent_t a, b;
+        CUDA_CHECK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        H.ev_in.push_back(a);
+        H.ev_k.push_back(b);
+    }
+    H.built = true;
+}
+
+void assemble_host(onsas_ctx* c, const double* U, double* F) {
+    require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
+    const size_t nl = (size_t)c->n_local_dofs(), no = (size_t)c->n_own_dofs();
+    if (c->n_ranks > 1 || c->host_chunks <= 1 || c->tab.n_slices == 0 || (c->n_tets == 0 && c->n_trusses == 0)) {
+        // multi-GPU (the halo of U is exchanged first) or pipelining switched off: copy in, assemble, copy out
+        CUDA_CHECK(cudaMemcpyAsync(c->U.p, U, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        launch_assemble(c);
+        if (nl > no) std::fill(F + no, F + nl, 0.0);
+        CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        download(c, F, c->Fint.p, no);
+        check_deferred(c);
+        return;
+    }
+    build_host_plan(c);
+    auto& H = c->hp;
+    const int nch = (int)H.node_hi.size();
+    const int bs = c->dim;
+    c->co.fresh = false;
+    CUDA_CHECK(cudaEventRecord(H.ev_start, c->stream));  // earlier work on the compute stream may still read U / F_int
+    CUDA_CHECK(cudaStreamWaitEvent(H.s_in, H.ev_start, 0));
+    int64_t up = 0;  // nodes of U already sent
+    for (int k = 0; k < nch; ++k) {
+        const int64_t hi = k + 1 == nch ? c->n_nodes : H.node_hi[k];  // the last piece takes what no element touches
+        if (hi > up) {
+            CUDA_CHECK(cudaMemcpyAsync(c->U.p + up * bs, U + up * bs, (size_t)(hi - up) * bs * sizeof(double), cudaMemcpyHostToDevice, H.s_in));
+            up = hi;
+        }
+        CUDA_CHECK(cudaEventRecord(H.ev_in[k], H.s_in));
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, H.ev_in[k], 0));
+        c->asm_first = H.slice0[k];
+        c->asm_count = H.slice0[k + 1] - H.slice0[k];
+        if (c->asm_count > 0) launch_assemble_range(c);
+        CUDA_CHECK(cudaEventRecord(H.ev_k[k], c->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(H.s_out, H.ev_k[k], 0));
+        const int64_t r0 = std::min<int64_t>(H.slice0[k] * SLICE_ROWS, c->n_owned), r1 = std::min<int64_t>(H.slice0[k + 1] * SLICE_ROWS, c->n_owned);
+        if (r1 > r0)
+            CUDA_CHECK(cudaMemcpyAsync(F + r0 * bs, c->Fint.p + r0 * bs, (size_t)(r1 - r0) * bs * sizeof(double), cudaMemcpyDeviceToHost, H.s_out));
+    }
+    c->asm_first = 0;
+    c->asm_count = -1;
+    CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, H.s_out));
+    CUDA_CHECK(cudaStreamSynchronize(H.s_out));  // the last kernel has finished too: the compute stream is idle
+    check_deferred(c);
 }
 
 // ---------------------------------------------------------------- halo exchange (NCCL send/recv)
@@ -561,7 +673,7 @@ void build_coarse(onsas_ctx* c) {
     c->co_E.alloc((size_t)nc * nc);
     c->co_w.alloc((size_t)nc);
     c->co_y.alloc((size_t)nc);
-    c->co_rowbuf.alloc((size_t)2 * nc);
+    c->co_rowbuf.alloc((size_t)2 * GJ_B * nc);
     CUDA_CHECK(cudaStreamSynchronize(s));
     c->co.n_agg = n_agg;
     c->co.nc = nc;
@@ -598,7 +710,20 @@ void refresh_coarse(onsas_ctx* c, CgArgs& A) {
         k_coarse_assemble<BS><<<c->co.n_agg, CO_THREADS, smem, c->stream>>>(A, c->co_E.p);
         CUDA_CHECK(cudaGetLastError());
     }
-    {
+    if (c->gj_blocked && (nc + GJ_B - 1) / GJ_B <= c->n_sm) {  // panels of 12 rows: nc / 12 grid barriers
+        const int grid = (nc + GJ_B - 1) / GJ_B;
+        const size_t smem = ((size_t)GJ_B * nc + 2 * GJ_B * GJ_B) * sizeof(double);
+        static size_t configured = 0;
+        if (smem > configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(k_gj_invert_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        double* M = c->co_E.p;
+        int ncv = nc;
+        double* rb = c->co_rowbuf.p;
+        void* args[] = {&M, &ncv, &rb};
+        CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gj_invert_blocked, dim3(grid), dim3(GJ_THREADS), args, smem, c->stream));
+    } else {
         const int rows = (nc + c->n_sm - 1) / c->n_sm;
         require(rows <= GJ_MAX_ROWS, ONSAS_ERR_UNSUPPORTED, "coarse space too large for the Gauss-Jordan kernel");
         const int grid = (nc + rows - 1) / rows;
@@ -781,6 +906,11 @@ int32_t onsas_destroy(onsas_ctx* c) {
         if (ev) cudaEventDestroy(ev);
     if (c->h_st) cudaFreeHost(c->h_st);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->hp.s_in) cudaStreamDestroy(c->hp.s_in);
+    if (c->hp.s_out) cudaStreamDestroy(c->hp.s_out);
+    if (c->hp.ev_start) cudaEventDestroy(c->hp.ev_start);
+    for (auto e : c->hp.ev_in) cudaEventDestroy(e);
+    for (auto e : c->hp.ev_k) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return ONSAS_OK;
@@ -802,6 +932,8 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_ASM_MINBLOCKS: require(value >= 1 && value <= 3, ONSAS_ERR_INVALID_ARG, "min blocks must be 1..3"); c->asm_minb = (int)value; break;
             case ONSAS_OPT_CG_CHECK_EVERY: require(value >= 1 && value <= 4096, ONSAS_ERR_INVALID_ARG, "check_every out of range"); c->check_every = (int)value; break;
             case ONSAS_OPT_FORCE_MG: c->force_mg = value != 0; break;
+            case ONSAS_OPT_GJ_BLOCKED: c->gj_blocked = value != 0; c->co.fresh = false; break;
+            case ONSAS_OPT_HOST_CHUNKS: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "host chunks must be 1..64"); c->host_chunks = (int)value; c->hp.built = false; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
@@ -1009,6 +1141,7 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->st_plan.built = false;
         c->co.built = false;
         c->co.fresh = false;
+        c->hp.built = false;
         c->n_patterns = 0;
         c->patterns.release();
         c->finalized = true;
@@ -1172,6 +1305,11 @@ int32_t onsas_get_Fext(onsas_ctx* c, double* F) {
 int32_t onsas_assemble(onsas_ctx* c) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] { launch_assemble(c); });  // asynchronous; errors surface at the next synchronizing call
+}
+
+int32_t onsas_assemble_host(onsas_ctx* c, const double* U, double* F_int) {
+    if (!c || !U || !F_int) return ONSAS_ERR_INVALID_ARG;
+    return guard(c, [&] { assemble_host(c, U, F_int); });
 }
 
 int32_t onsas_eval_elements(onsas_ctx* c, int32_t family, int64_t first, int64_t count, double* f, double* K, double* sig,

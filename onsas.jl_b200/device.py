@@ -170,6 +170,15 @@ class DeviceContext:
         """assemble!(s, sa) -- asynchronous; errors surface at the next synchronizing call."""
         self._check(self._lib.onsas_assemble(self._h))
 
+    def assemble_host(self, U, out=None):
+        """assemble!(s, sa) with host state on both sides: U in, F_int out, the copies pipelined with the kernel
+        (onsas_assemble_host).  `out` may be a preallocated (pinned) float64 array of n_dofs."""
+        U = _as(U, np.float64).ravel()
+        assert U.size == self.n_dofs
+        out = np.empty(self.n_dofs) if out is None else out
+        self._check(self._lib.onsas_assemble_host(self._h, U, out))
+        return out
+
     def synchronize(self):
         self._check(self._lib.onsas_synchronize(self._h))
 

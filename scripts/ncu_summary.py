@@ -31,10 +31,10 @@ for r in rows[2:]:
             if v >= 0.05:
                 lines.append(f"| {h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]} | {v:.2f} |")
     lines.append("")
-    break
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 if len(rows) > 2:
+    lines += ["Source page (first kernel of the report):", ""]
     hdr = rows[1]
     iS, iSrc, iEx = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Source"), hdr.index("Instructions Executed")
     data = []

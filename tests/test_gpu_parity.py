@@ -378,3 +378,76 @@ def test_two_level_preconditioner(ob, oracle):
     ctx.set_option(ob._lib.OPT_CG_MODE, 1)
     with pytest.raises(ob.OnsasError):
         ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-12)
+
+
+def test_two_level_blocked_and_unblocked_coarse_inverse_agree(ob, oracle):
+    """The coarse inverse by 12-row panels (default) and by single pivot rows are the same matrix up to rounding: same
+    iteration count within one, same solution to 1e-10; sizes with full and partial last panels."""
+    for grid in ((24, 12, 12), (30, 15, 15), (3, 2, 2)):
+        m, _ = cases.box_model(*grid, mat="svk", jitter=0.1)
+        U = cases.random_U(m, 0.002)
+        b = np.random.default_rng(5).standard_normal(m.n_dofs)
+        out = []
+        for blocked in (1, 0):
+            ctx = _ctx(ob, m)
+            ctx.set_option(ob._lib.OPT_GJ_BLOCKED, blocked)
+            ctx.set_U(U)
+            ctx.assemble()
+            out.append(ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-12))
+            ctx.close()
+        (x1, it1, _), (x0, it0, _) = out
+        assert abs(it1 - it0) <= 1, (grid, it1, it0)
+        assert cases.rel_err(x1, x0) < 1e-9, grid
+
+
+@pytest.mark.parametrize("case", ["box", "random_numbering", "mixed"])
+def test_assemble_host_is_bitwise_the_three_call_path(ob, oracle, case):
+    """onsas_assemble_host (U in, F_int out, copies pipelined over slice ranges) against onsas_set_U + onsas_assemble +
+    onsas_get_Fint: F_int, K, stress and strain bitwise equal for every chunk count, on a banded numbering, a random
+    numbering (every chunk needs all of U) and a structure with two element families (accumulating second pass)."""
+    if case == "box":
+        m, _ = cases.box_model(20, 10, 10, mat="neo", jitter=0.1)
+    elif case == "random_numbering":
+        m0, _ = cases.box_model(11, 6, 5, mat="svk", jitter=0.15)
+        rng = np.random.default_rng(11)
+        n = m0.xyz.shape[0]
+        perm = rng.permutation(n)
+        inv = np.empty(n, np.int64)
+        inv[perm] = np.arange(n)
+        tets = perm[m0.tets][rng.permutation(len(m0.tets))].astype(np.int32)
+        free = np.sort(perm[m0.free_dofs // 3] * 3 + m0.free_dofs % 3)
+        m = oracle.FlatModel(xyz=m0.xyz[inv], tets=tets, mat_kind=m0.mat_kind, mat_params=m0.mat_params, free_dofs=free)
+    else:
+        m0, mesh = cases.box_model(7, 4, 4, jitter=0.1)
+        rng = np.random.default_rng(2)
+        bars = np.stack([np.arange(0, mesh.n_nodes - 1), np.arange(1, mesh.n_nodes)], axis=1).astype(np.int32)
+        m = oracle.FlatModel(xyz=m0.xyz, tets=m0.tets, tet_mat=rng.integers(0, 3, len(m0.tets)), trusses=bars,
+                             truss_mat=rng.integers(0, 2, len(bars)), truss_area=rng.uniform(0.1, 0.3, len(bars)),
+                             truss_strain=1, mat_kind=[0, 1, 2], mat_params=[[0.58, 0.38], [0.83, 0.38], [1.0, 0.3]],
+                             free_dofs=m0.free_dofs)
+    U = cases.random_U(m, 0.03)
+    ctx = _ctx(ob, m)
+    ctx.set_U(U)
+    ctx.assemble()
+    F0, K0 = ctx.get_Fint(), ctx.get_csr()[2]
+    S0 = ctx.get_stress_strain(ob.FAMILY_TET)
+    ref = oracle.Assembly(m).assemble(U)
+    assert cases.rel_err(F0, ref.F_int) < 1e-12
+    for chunks in (4, 1, 3, 64):
+        ctx.set_option(ob._lib.OPT_HOST_CHUNKS, chunks)
+        ctx.set_U(np.zeros_like(U))           # stale state that the call must replace
+        ctx.assemble()
+        F1 = ctx.assemble_host(U)
+        np.testing.assert_array_equal(F1, F0)
+        np.testing.assert_array_equal(ctx.get_csr()[2], K0)
+        np.testing.assert_array_equal(ctx.get_U(), U)
+        S1 = ctx.get_stress_strain(ob.FAMILY_TET)
+        np.testing.assert_array_equal(S1[0], S0[0])
+        np.testing.assert_array_equal(S1[1], S0[1])
+    # the state it leaves behind feeds the solver like onsas_assemble's does
+    b = np.random.default_rng(4).standard_normal(m.n_dofs)
+    x1 = ctx.pcg(b, ob.PRECOND_JACOBI, 1e-12)[0]
+    ctx.set_U(U)
+    ctx.assemble()
+    np.testing.assert_array_equal(ctx.pcg(b, ob.PRECOND_JACOBI, 1e-12)[0], x1)
+    ctx.close()
