@@ -1182,7 +1182,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     auto coarse_apply = [&]() -> double {
         const CoarseArgs& G = A.co;
         const int gw = (int)(gtid >> 5), nw = (int)(gsz >> 5);
+        long long tca = profiling ? clock64() : 0;
+        auto cprof = [&](int k) {  // aux counters 8..11: barrier, w = Z^T r, barrier, y = E^-1 w (cycles of block 0)
+            if (profiling) {
+                const long long tn = clock64();
+                A.prof[k] += tn - tca;
+                tca = tn;
+            }
+        };
         grid.sync();
+        cprof(8);
         // w = Z^T r: CO_SPLIT warps of one CTA share an aggregate (enough warps in flight to hide the two dependent load
         // levels: node ids -> residuals); their chunk sums meet in shared memory and are added in chunk order
         constexpr int AG_PER_CTA = (CW + 1) / CO_SPLIT;
@@ -1226,7 +1235,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
             }
             __syncthreads();
         }
+        cprof(9);
         grid.sync();
+        cprof(10);
         // y = E^-1 w: one warp per row of the dense inverse (L2-resident); 16-byte loads, 12 + 12 of them in flight per lane
         double wy = 0.0;
         for (int k = gw; k < G.nc; k += nw) {
@@ -1261,6 +1272,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                 wy += __ldcg(G.w + k) * acc;
             }
         }
+        cprof(11);
         return wy;
     };
 

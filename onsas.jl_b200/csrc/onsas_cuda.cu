@@ -1513,7 +1513,7 @@ int32_t onsas_get_cg_profile(onsas_ctx* c, int64_t out[8]) {
         for (size_t k = 16; k < 16 + 2048; ++k) mx = std::max(mx, h[k]);
         out[7] = mx;
         if (getenv("ONSAS_PROF_VERBOSE"))
-            fprintf(stderr, "[onsas prof] two-level, cycles of block 0: sync %lld, w %lld, sync %lld, y %lld, sync %lld, z %lld\n", h[8], h[9], h[10], h[11], h[12], h[13]);
+            fprintf(stderr, "[onsas prof] two-level coarse apply, cycles of block 0 (whole solve): barrier %lld, w = Z^T r %lld, barrier %lld, y = E^-1 w %lld\n", h[8], h[9], h[10], h[11]);
         if (const char* f = getenv("ONSAS_PROF_DUMP")) {  // diagnostics: per-CTA SpMV cycles of the last profiled solve
             if (FILE* fp = fopen(f, "w")) {
                 for (size_t k = 16; k < h.size(); ++k) fprintf(fp, "%lld\n", h[k]);
