@@ -60,13 +60,28 @@ device linear solve that replaces `IterativeSolversJL_CG` (StructuralSolvers.jl:
 """
 Base.@kwdef struct NewtonRaphsonCUDA <: AbstractSolver
     tol::ConvergenceSettings = ConvergenceSettings()
-    jacobi::Bool = true                 # false = un-preconditioned CG, the reference default
+    preconditioner::Symbol = :jacobi    # :none = un-preconditioned CG (the reference default), :jacobi, :two_level
+                                        # (Jacobi + aggregated coarse space, ONSAS_PRECOND_TWO_LEVEL)
     cg_reltol::Float64 = sqrt(eps())    # StructuralSolvers.jl:229-234
     cg_abstol::Float64 = 0.0
     cg_maxiter::Int = 0                 # 0 -> number of free dofs
     device::Int = 0
 end
 NewtonRaphsonCUDA(tol::ConvergenceSettings; kw...) = NewtonRaphsonCUDA(; tol, kw...)
+precond_code(alg::NewtonRaphsonCUDA) = Int32(alg.preconditioner === :none ? 0 : alg.preconditioner === :two_level ? 2 : 1)
+
+"""
+`assemble!(s, sa)` (StaticAnalyses.jl:99-122) on the device with the reference's host state on both sides:
+`displacements(state)` goes in, `internal_forces(state)` comes back, K / stress / strain stay on the device
+(fetch them with `onsas_get_csr` / `onsas_get_stress_strain` when needed).  One ccall; the two copies are pipelined
+with the assembly kernel inside the library (onsas_assemble_host).
+"""
+function assemble_device!(ctx::CudaContext, state::FullStaticState)
+    U, F = displacements(state), internal_forces(state)
+    GC.@preserve U F check(ctx, ccall((:onsas_assemble_host, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        ctx.handle, U, F))
+    state
+end
 
 material_code(m::SVK) = (Int32(0), collect(Float64, lame_parameters(m)))
 material_code(m::NeoHookean) = (Int32(1), [bulk_modulus(m), shear_modulus(m)])
@@ -193,7 +208,7 @@ function _solve!(sa::NonLinearStaticAnalysis, alg::NewtonRaphsonCUDA, linear_sol
         while isconverged!(current_iteration(sa), tolerances(alg)) isa NotConvergedYet   # :90
             # assemble!(s, sa) + step!(sa, alg, linear_solver) in one call (:92-95, :107-148)
             check(ctx, ccall((:onsas_newton_step, LIB[]), Int32, (Ptr{Cvoid}, Int32, Float64, Float64, Int64, Ref{StepInfo}),
-                ctx.handle, Int32(alg.jacobi), alg.cg_reltol, alg.cg_abstol, alg.cg_maxiter, info))
+                ctx.handle, precond_code(alg), alg.cg_reltol, alg.cg_abstol, alg.cg_maxiter, info))
             i = info[]
             update!(current_iteration(sa), i.norm_dU, i.norm_dU / i.norm_U, i.norm_r, i.norm_r / i.norm_Fext)  # :138-147
         end

@@ -15,12 +15,13 @@ for G in 2 4 8; do
   if [ $G -le $N ] && { [ $ONLY -eq 0 ] || [ $G -eq $N ]; }; then
     for P2P in "" "--no-p2p"; do
       echo "== bench N=$G $P2P"
-      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $G --steps 20 --warmup 3 $P2P > $OUT/bench_$G$P2P.json 2> $OUT/bench_$G$P2P.err
+      ONSAS_BENCH_TWO_LEVEL_MULTI=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $G --steps 20 --warmup 3 $P2P > $OUT/bench_$G$P2P.json 2> $OUT/bench_$G$P2P.err
       echo "rc=$?"; python - <<PY
 import json
 try:
     d = json.loads(open("$OUT/bench_$G$P2P.json").read().strip().splitlines()[-1]); ns = d["newton_step"]
     print("N=%d value %.3f Gtets/s  newton %.1f ms  cg_iters %d  us/iter %.2f  e2e %.3f Gtets/s" % (d["n_gpus"], d["value"] / 1e9, d["newton_step_ms"], ns["cg_iters"], 1e3 * ns["ms_solve"] / ns["cg_iters"], d["e2e"]["value"] / 1e9))
+    print("   two-level:", d.get("newton_step_two_level"))
 except Exception as ex:
     print("no JSON:", ex)
 PY

@@ -66,6 +66,13 @@ def main():
         its_modes.append(its)
     ctx.set_option(ob._lib.OPT_CG_MODE, 0)
     its = its_modes
+    # two-level preconditioner on N ranks: every rank's coarse space covers its owned nodes (block-diagonal E)
+    e_x2, its2 = float("inf"), -1
+    try:
+        xs2, its2, _ = ctx.pcg(part.scatter_global(b, 3), ob.PRECOND_TWO_LEVEL, 1e-12)
+        e_x2 = np.abs(xs2[:len(own)] - xo[own]).max() / np.abs(xo).max()
+    except ob.OnsasError as exc:
+        print(f"rank {rank}: two-level PCG failed: {exc}", flush=True)
 
     # ---- distributed Newton solve of the compression example (9 load steps, tol 1e-10, as the reference ships it)
     #      vs the oracle's direct-solve Newton, on the undistorted mesh of the same grid
@@ -94,14 +101,15 @@ def main():
         iters.append(it)
     Ul = ctx.get_U()[:len(own)]
     e_u = np.abs(Ul - refn.U[-1][own]).max() / np.abs(refn.U[-1]).max()
-    errs = torch.tensor([e_f, e_k, e_y, e_x, e_u], dtype=torch.float64, device="cuda")
+    errs = torch.tensor([e_f, e_k, e_y, e_x, e_u, e_x2], dtype=torch.float64, device="cuda")
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     ok = True
     if rank == 0:
-        e_f, e_k, e_y, e_x, e_u = errs.tolist()
+        e_f, e_k, e_y, e_x, e_u, e_x2 = errs.tolist()
+        print(f"multi-gpu check world={world}: two-level pcg x {e_x2:.2e} (its {its2} vs jacobi {its[0]})", flush=True)
         print(f"multi-gpu check world={world}: F_int {e_f:.2e}  K {e_k:.2e}  spmv {e_y:.2e}  pcg x {e_x:.2e} (its {its} vs {ito})  "
               f"newton U {e_u:.2e} iters {iters} vs {refn.iterations}", flush=True)
-        ok = e_f < 1e-12 and e_k < 1e-12 and e_y < 1e-12 and e_x < 1e-8 and e_u < 1e-8 and iters == refn.iterations
+        ok = e_f < 1e-12 and e_k < 1e-12 and e_y < 1e-12 and e_x < 1e-8 and e_u < 1e-8 and iters == refn.iterations and e_x2 < 1e-8
         print("MULTI_GPU_CHECK_OK" if ok else "MULTI_GPU_CHECK_FAILED", flush=True)
     dist.barrier()          # never leave the other ranks waiting on a failed assertion
     dist.destroy_process_group()

@@ -39,7 +39,7 @@ def test_uniaxial_extension_as_shipped(ob, oracle):
     assert all(isinstance(c, (ob.ResidualForceCriterion, ob.DeltaUCriterion)) for c in sol.criterion())
 
 
-@pytest.mark.parametrize("precond", ["jacobi", "none"])
+@pytest.mark.parametrize("precond", ["jacobi", "none", "two_level"])
 def test_uniaxial_compression_neohookean(ob, oracle, precond):
     """configs[1] at oracle-sized refinement: NeoHookean cube compression, 9 steps, tol 1e-10."""
     m, mesh = cases.box_model(6, 3, 3, mat="neo")
