@@ -786,49 +786,68 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A, P2PA
 // (deterministic); the loads of a row (column ids -> aggregate ids, values) are issued by the whole CTA in parallel.
 constexpr int CO_THREADS = 256;
 constexpr int CO_SPLIT = 3;  // warps per aggregate in the w = Z^T r reduction (13 warps: 4 aggregates per CTA and pass)
+constexpr int CO_NW = CO_THREADS / 32;  // nodes of the aggregate in flight (one per warp)
+constexpr int CO_WB = 32;               // blocks of a node staged per round
 template <int BS>
 __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double* E) {
-    extern __shared__ double erow[];  // [BS][nc]
+    extern __shared__ double erow[];  // [BS][nc], then the staged block values [CO_NW][CO_WB][BS*BS]
     constexpr int BB = BS * BS;
     const CoarseArgs& G = A.co;
-    const int a = blockIdx.x, tid = threadIdx.x, nc = G.nc;
-    __shared__ int s_b[CO_THREADS];         // aggregate of the block's column (-1: halo column)
-    __shared__ unsigned char s_m[CO_THREADS];  // mask bits of the column node's dofs
-    double* sval = erow + (size_t)BS * nc;  // [CO_THREADS / BB][BB] values of the current batch of blocks
+    const int a = blockIdx.x, tid = threadIdx.x, nc = G.nc, warp = tid >> 5, lane = tid & 31;
+    double* sval = erow + (size_t)BS * nc;
+    __shared__ int s_b[CO_NW][CO_WB];            // aggregate of the block's column (-1: halo column)
+    __shared__ unsigned char s_m[CO_NW][CO_WB];  // mask bits of the column node's dofs
+    __shared__ int s_nb[CO_NW];                  // blocks the warp staged this round
+    __shared__ unsigned s_mi[CO_NW];             // mask bits of the row node's dofs
     for (int k = tid; k < BS * nc; k += CO_THREADS) erow[k] = 0.0;
     __syncthreads();
-    constexpr int NBLK = CO_THREADS / BB;   // blocks staged per batch
-    for (int q = G.agg_ptr[a]; q < G.agg_ptr[a + 1]; ++q) {
-        const int64_t i = G.agg_nodes[q];
-        const int64_t base = A.slice_ptr[i / C];
-        const int width = (int)(A.slice_ptr[i / C + 1] - base);
-        const int lane = (int)(i % C);
+    // Eight nodes are fetched at a time, one per warp (the four dependent load levels node id -> slice -> column ids
+    // -> aggregate ids overlap across the warps); BS*BS threads then apply the staged blocks in (node, block) order.
+    const int q0 = G.agg_ptr[a], q1 = G.agg_ptr[a + 1];
+    for (int qb = q0; qb < q1; qb += CO_NW) {
+        const int q = qb + warp;
+        int64_t base = 0;
+        int width = 0, lrow = 0;
         unsigned mi = 0;
-        for (int r = 0; r < BS; ++r) mi |= (unsigned)(A.mask[i * BS + r] & 1) << r;
-        for (int s0 = 0; s0 < width; s0 += NBLK) {
-            const int nb = width - s0 < NBLK ? width - s0 : NBLK;
-            if (tid < nb) {
-                const int64_t j = A.col[(base + s0 + tid) * C + lane];
+        if (q < q1) {
+            const int64_t i = G.agg_nodes[q];
+            base = A.slice_ptr[i / C];
+            width = (int)(A.slice_ptr[i / C + 1] - base);
+            lrow = (int)(i % C);
+            for (int r = 0; r < BS; ++r) mi |= (unsigned)(A.mask[i * BS + r] & 1) << r;
+        }
+        for (int s0 = 0;; s0 += CO_WB) {
+            const int left = width - s0;
+            const int nb = left <= 0 ? 0 : (left < CO_WB ? left : CO_WB);
+            if (lane < nb) {
+                const int64_t j = A.col[(base + s0 + lane) * C + lrow];
                 int b = -1;
                 unsigned mj = 0;
                 if (j < A.n_rows) {
                     b = G.agg[j];
                     for (int c = 0; c < BS; ++c) mj |= (unsigned)(A.mask[j * BS + c] & 1) << c;
                 }
-                s_b[tid] = b;
-                s_m[tid] = (unsigned char)mj;
+                s_b[warp][lane] = b;
+                s_m[warp][lane] = (unsigned char)mj;
             }
-            if (tid < nb * BB) sval[tid] = A.val[((base + s0 + tid / BB) * BB + tid % BB) * C + lane];
+            for (int t = lane; t < nb * BB; t += 32) sval[(size_t)warp * CO_WB * BB + t] = A.val[((base + s0 + t / BB) * BB + t % BB) * C + lrow];
+            if (lane == 0) {
+                s_nb[warp] = nb;
+                s_mi[warp] = mi;
+            }
             __syncthreads();
-            if (tid < BB) {  // thread (r, c) applies the staged blocks in order
+            if (tid < BB) {  // thread (r, c): nodes in ascending order, blocks in storage order -> a fixed summation order
                 const int r = tid / BS, c = tid % BS;
-                if ((mi >> r) & 1u)
-                    for (int s = 0; s < nb; ++s) {
-                        const int b = s_b[s];
-                        if (b >= 0 && ((s_m[s] >> c) & 1u)) erow[(size_t)r * nc + b * BS + c] += sval[s * BB + tid];
+                for (int w = 0; w < CO_NW; ++w) {
+                    if (!((s_mi[w] >> r) & 1u)) continue;
+                    const int nbw = s_nb[w];
+                    for (int s = 0; s < nbw; ++s) {
+                        const int b = s_b[w][s];
+                        if (b >= 0 && ((s_m[w][s] >> c) & 1u)) erow[(size_t)r * nc + b * BS + c] += sval[((size_t)w * CO_WB + s) * BB + tid];
                     }
+                }
             }
-            __syncthreads();
+            if (!__syncthreads_or(left > CO_WB)) break;  // barrier (staging buffers are free again) + "another round?"
         }
     }
     // coarse dofs without any free fine dof: unit diagonal keeps E invertible (their w is always 0)

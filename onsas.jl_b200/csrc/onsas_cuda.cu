@@ -173,7 +173,7 @@ struct onsas_ctx {
     DevBuf<double> co_E, co_w, co_y, co_rowbuf;
     // onsas_assemble_host: slice ranges launched one after the other while the copies of U (in) and F_int (out) overlap them
     int64_t asm_first = 0, asm_count = -1;  // slice range of the next assembly launches (-1: all slices)
-    int host_chunks = 4;
+    int host_chunks = 4, host_mid_weight = 3;
     bool gj_blocked = true;  // coarse inverse by the panel (blocked) Gauss-Jordan kernel; false: one pivot row per grid barrier
     struct HostPlan {
         bool built = false;
@@ -379,8 +379,18 @@ void build_host_plan(onsas_ctx* c) {
     if (H.built && (int)H.node_hi.size() == std::max(1, c->host_chunks)) return;
     const int64_t ns = c->tab.n_slices;
     const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, c->host_chunks), ns));
+    // the first and the last range are short (weight 1 against `host_mid_weight` for the others): the first kernel
+    // waits for its piece of U and the last piece of F_int leaves after the last kernel -- the two exposed copies
     H.slice0.assign((size_t)nch + 1, 0);
-    for (int k = 0; k <= nch; ++k) H.slice0[k] = ns * k / nch;
+    {
+        const int wm = std::max(1, c->host_mid_weight);
+        const int64_t wt = nch <= 2 ? nch : 2 + (int64_t)(nch - 2) * wm;
+        int64_t acc = 0;
+        for (int k = 0; k < nch; ++k) {
+            acc += (nch <= 2 || k == 0 || k == nch - 1) ? 1 : wm;
+            H.slice0[k + 1] = ns * acc / wt;
+        }
+    }
     H.node_hi.assign((size_t)nch, 0);
     for (int k = 0; k < nch; ++k) {
         int64_t hi = std::min<int64_t>(H.slice0[k + 1] * SLICE_ROWS, c->n_nodes);  // the rows themselves
@@ -701,7 +711,7 @@ void refresh_coarse(onsas_ctx* c, CgArgs& A) {
     if (c->co.fresh) return;
     const int nc = c->co.nc;
     {
-        const size_t smem = ((size_t)BS * nc + (CO_THREADS / (BS * BS)) * BS * BS) * sizeof(double);
+        const size_t smem = ((size_t)BS * nc + (size_t)CO_NW * CO_WB * BS * BS) * sizeof(double);
         static size_t configured = 0;
         if (smem > configured) {
             CUDA_CHECK(cudaFuncSetAttribute(k_coarse_assemble<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -934,6 +944,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_FORCE_MG: c->force_mg = value != 0; break;
             case ONSAS_OPT_GJ_BLOCKED: c->gj_blocked = value != 0; c->co.fresh = false; break;
             case ONSAS_OPT_HOST_CHUNKS: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "host chunks must be 1..64"); c->host_chunks = (int)value; c->hp.built = false; break;
+            case ONSAS_OPT_HOST_MID_WEIGHT: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "weight must be 1..64"); c->host_mid_weight = (int)value; c->hp.built = false; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");

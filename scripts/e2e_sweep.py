@@ -17,15 +17,17 @@ hU, hF = bench.pinned(ctx.n_dofs), bench.pinned(ctx.n_dofs)
 hU[:] = U_half
 lib, h = ctx._lib, ctx._h
 K = 50
-for chunks in (1, 2, 3, 4, 6, 8, 12, 16, 32):
+for chunks, weight in ((1, 1), (2, 1), (3, 1), (4, 1), (6, 1), (8, 1), (3, 2), (3, 4), (3, 8), (4, 2), (4, 3), (4, 4), (4, 6), (5, 3), (5, 5),
+                       (6, 3), (6, 5), (8, 4)):
     ctx.set_option(ob._lib.OPT_HOST_CHUNKS, chunks)
+    ctx.set_option(ob._lib.OPT_HOST_MID_WEIGHT, weight)
     for _ in range(5):
         assert lib.onsas_assemble_host(h, hU, hF) == 0
     t0 = time.perf_counter()
     for _ in range(K):
         assert lib.onsas_assemble_host(h, hU, hF) == 0
     ms = (time.perf_counter() - t0) * 1e3 / K
-    print(f"chunks={chunks:3d}  {ms:.4f} ms per call  {mesh.n_tets / ms / 1e6:.3f} G tets/s", flush=True)
+    print(f"chunks={chunks:3d} mid_weight={weight:2d}  {ms:.4f} ms per call  {mesh.n_tets / ms / 1e6:.3f} G tets/s", flush=True)
 t0 = time.perf_counter()
 for _ in range(K):
     assert lib.onsas_set_U(h, hU) == 0
