@@ -173,7 +173,7 @@ struct onsas_ctx {
     DevBuf<double> co_E, co_w, co_y, co_rowbuf;
     // onsas_assemble_host: slice ranges launched one after the other while the copies of U (in) and F_int (out) overlap them
     int64_t asm_first = 0, asm_count = -1;  // slice range of the next assembly launches (-1: all slices)
-    int host_chunks = 4, host_mid_weight = 3;
+    int host_chunks = 4, host_mid_weight = 4;
     bool gj_blocked = true;  // coarse inverse by the panel (blocked) Gauss-Jordan kernel; false: one pivot row per grid barrier
     struct HostPlan {
         bool built = false;
