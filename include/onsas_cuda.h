@@ -59,8 +59,9 @@ typedef struct onsas_ctx onsas_ctx;
 /* preconditioners for the CG solve */
 #define ONSAS_PRECOND_NONE 0   /* IterativeSolversJL_CG default of the reference, StructuralSolvers.jl:29 */
 #define ONSAS_PRECOND_JACOBI 1 /* the north-star solver */
-#define ONSAS_PRECOND_TWO_LEVEL 2 /* Jacobi + aggregated coarse space (piecewise-constant translations on ~7^3-node aggregates,
-                                     E = Z^T K Z inverted explicitly once per assembly); streamed persistent solver only. SURVEY 8f-4 */
+#define ONSAS_PRECOND_TWO_LEVEL 2 /* Jacobi + aggregated coarse space (rigid-body modes of node aggregates: translations, in 3D also
+                                     rotations; E = Z^T K Z inverted explicitly once per assembly); streamed persistent solver only.
+                                     SURVEY 8f-4 */
 
 /* tuning keys for onsas_set_option */
 #define ONSAS_OPT_CG_MODE 1      /* 0 = persistent cooperative kernel with K streamed through shared memory by TMA bulk copies (default;
@@ -72,6 +73,7 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: resident CTAs per SM the kernel is compiled for: 4, 5 or 6 (default 6); 1-3 shrink the grid */
 #define ONSAS_OPT_FORCE_MG 6         /* diagnostics: set before onsas_finalize_mesh to run the multi-GPU CG kernel with a single rank */
 #define ONSAS_OPT_HOST_MID_WEIGHT 9   /* onsas_assemble_host: size of an inner slice range relative to the first / last one (default 4) */
+#define ONSAS_OPT_COARSE_RBM 10       /* two-level preconditioner in 3D: 1 = rigid-body rotations of every aggregate join the coarse space (default), 0 = translations only */
 #define ONSAS_OPT_GJ_BLOCKED 8        /* two-level preconditioner: 1 = coarse inverse by 12-row panels (default), 0 = one pivot row per grid barrier */
 #define ONSAS_OPT_HOST_CHUNKS 7       /* onsas_assemble_host: slice ranges the assembly is cut into so that the copies of U and F_int overlap it (default 4; 1 = no overlap) */
 #define ONSAS_OPT_CG_PROFILE 5       /* 1 = the persistent CG kernel records per-phase SM-clock cycles (onsas_get_cg_profile) */

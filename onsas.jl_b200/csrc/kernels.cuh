@@ -385,6 +385,8 @@ enum : int { P_RR = 0, P_RZ = 1, P_FF = 2, P_UU = 3, P_PAP = 4, P_DD = 5, P_COUN
 // aggregates (masked at fixed dofs) and E = Z^T K Z, inverted explicitly once per assembly (nc = BS * n_agg <= 1536).
 struct CoarseArgs {
     int n_agg, nc;
+    int cd;                    // coarse dofs per aggregate: BS (translations) or 6 (+ rigid-body rotations, BS = 3 only)
+    const double* rho;         // [n_rows][3] node position relative to its aggregate's centroid (cd = 6), else null
     const int32_t* agg;        // [n_rows] aggregate of every owned node
     const int32_t* agg_ptr;    // [n_agg+1]
     const int32_t* agg_nodes;  // [n_rows] node ids grouped by aggregate, ascending inside each
@@ -785,36 +787,55 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A, P2PA
 // and a node's blocks in storage order by the same BS*BS threads, so every entry of E is summed in a fixed order
 // (deterministic); the loads of a row (column ids -> aggregate ids, values) are issued by the whole CTA in parallel.
 constexpr int CO_THREADS = 256;
-constexpr int CO_SPLIT = 3;  // warps per aggregate in the w = Z^T r reduction (13 warps: 4 aggregates per CTA and pass)
+// (the warps-per-aggregate split of the w = Z^T r reduction is chosen at run time inside cg_stream)
 constexpr int CO_NW = CO_THREADS / 32;  // nodes of the aggregate in flight (one per warp)
 constexpr int CO_WB = 32;               // blocks of a node staged per round
+// entry (p, k) of R = -skew(rho): the displacement of a node at rho under a unit rotation about axis k (u = omega x rho)
+__device__ __forceinline__ double rot_entry(const double* rho, int p, int k) {
+    if (p == k) return 0.0;
+    const double v = rho[3 - p - k];
+    return (k - p + 3) % 3 == 1 ? v : -v;
+}
+// column `cdof` of Z_i = [I | R_i] (or [I] without rotations), rows of fixed dofs zeroed
+template <int BS>
+__device__ __forceinline__ void z_column(int cdof, const double* rho, unsigned mask, double (&z)[BS]) {
+#pragma unroll
+    for (int p = 0; p < BS; ++p) {
+        double v = cdof < BS ? (p == cdof ? 1.0 : 0.0) : rot_entry(rho, p, cdof - BS);
+        z[p] = ((mask >> p) & 1u) ? v : 0.0;
+    }
+}
 template <int BS>
 __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double* E) {
-    extern __shared__ double erow[];  // [BS][nc], then the staged block values [CO_NW][CO_WB][BS*BS]
+    extern __shared__ double erow[];  // [CD][nc], then the staged block values [CO_NW][CO_WB][BS*BS]
     constexpr int BB = BS * BS;
     const CoarseArgs& G = A.co;
-    const int a = blockIdx.x, tid = threadIdx.x, nc = G.nc, warp = tid >> 5, lane = tid & 31;
-    double* sval = erow + (size_t)BS * nc;
+    const int a = blockIdx.x, tid = threadIdx.x, nc = G.nc, CD = G.cd, warp = tid >> 5, lane = tid & 31;
+    const bool rbm = CD > BS;
+    double* sval = erow + (size_t)CD * nc;
     __shared__ int s_b[CO_NW][CO_WB];            // aggregate of the block's column (-1: halo column)
     __shared__ unsigned char s_m[CO_NW][CO_WB];  // mask bits of the column node's dofs
+    __shared__ double s_rj[CO_NW][CO_WB][3];     // rho of the column node
+    __shared__ double s_ri[CO_NW][3];            // rho of the row node
     __shared__ int s_nb[CO_NW];                  // blocks the warp staged this round
     __shared__ unsigned s_mi[CO_NW];             // mask bits of the row node's dofs
-    for (int k = tid; k < BS * nc; k += CO_THREADS) erow[k] = 0.0;
+    for (int k = tid; k < CD * nc; k += CO_THREADS) erow[k] = 0.0;
     __syncthreads();
     // Eight nodes are fetched at a time, one per warp (the four dependent load levels node id -> slice -> column ids
-    // -> aggregate ids overlap across the warps); BS*BS threads then apply the staged blocks in (node, block) order.
+    // -> aggregate ids overlap across the warps); CD*CD threads then apply the staged blocks in (node, block) order:
+    // E[a-rows, b-cols] += Z_i^T (M K_ij M) Z_j.
     const int q0 = G.agg_ptr[a], q1 = G.agg_ptr[a + 1];
     for (int qb = q0; qb < q1; qb += CO_NW) {
         const int q = qb + warp;
-        int64_t base = 0;
+        int64_t base = 0, inode = 0;
         int width = 0, lrow = 0;
         unsigned mi = 0;
         if (q < q1) {
-            const int64_t i = G.agg_nodes[q];
-            base = A.slice_ptr[i / C];
-            width = (int)(A.slice_ptr[i / C + 1] - base);
-            lrow = (int)(i % C);
-            for (int r = 0; r < BS; ++r) mi |= (unsigned)(A.mask[i * BS + r] & 1) << r;
+            inode = G.agg_nodes[q];
+            base = A.slice_ptr[inode / C];
+            width = (int)(A.slice_ptr[inode / C + 1] - base);
+            lrow = (int)(inode % C);
+            for (int r = 0; r < BS; ++r) mi |= (unsigned)(A.mask[inode * BS + r] & 1) << r;
         }
         for (int s0 = 0;; s0 += CO_WB) {
             const int left = width - s0;
@@ -826,6 +847,8 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double
                 if (j < A.n_rows) {
                     b = G.agg[j];
                     for (int c = 0; c < BS; ++c) mj |= (unsigned)(A.mask[j * BS + c] & 1) << c;
+                    if (rbm)
+                        for (int c = 0; c < 3; ++c) s_rj[warp][lane][c] = G.rho[j * 3 + c];
                 }
                 s_b[warp][lane] = b;
                 s_m[warp][lane] = (unsigned char)mj;
@@ -835,25 +858,45 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double
                 s_nb[warp] = nb;
                 s_mi[warp] = mi;
             }
+            if (rbm && lane < 3 && nb > 0) s_ri[warp][lane] = G.rho[inode * 3 + lane];
             __syncthreads();
-            if (tid < BB) {  // thread (r, c): nodes in ascending order, blocks in storage order -> a fixed summation order
-                const int r = tid / BS, c = tid % BS;
+            if (tid < CD * CD) {  // thread (r, c): nodes in ascending order, blocks in storage order -> a fixed summation order
+                const int r = tid / CD, c = tid % CD;
                 for (int w = 0; w < CO_NW; ++w) {
-                    if (!((s_mi[w] >> r) & 1u)) continue;
                     const int nbw = s_nb[w];
+                    if (nbw == 0) continue;
+                    double zi[BS];
+                    z_column<BS>(r, s_ri[w], s_mi[w], zi);
                     for (int s = 0; s < nbw; ++s) {
                         const int b = s_b[w][s];
-                        if (b >= 0 && ((s_m[w][s] >> c) & 1u)) erow[(size_t)r * nc + b * BS + c] += sval[((size_t)w * CO_WB + s) * BB + tid];
+                        if (b < 0) continue;
+                        double zj[BS];
+                        z_column<BS>(c, s_rj[w][s], s_m[w][s], zj);
+                        const double* Kb = sval + ((size_t)w * CO_WB + s) * BB;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int p = 0; p < BS; ++p) {
+                            double t = 0.0;
+#pragma unroll
+                            for (int qq = 0; qq < BS; ++qq) t += Kb[p * BS + qq] * zj[qq];
+                            acc += zi[p] * t;
+                        }
+                        erow[(size_t)r * nc + b * CD + c] += acc;
                     }
                 }
             }
             if (!__syncthreads_or(left > CO_WB)) break;  // barrier (staging buffers are free again) + "another round?"
         }
     }
-    // coarse dofs without any free fine dof: unit diagonal keeps E invertible (their w is always 0)
-    if (tid < BS && erow[(size_t)tid * nc + a * BS + tid] == 0.0) erow[(size_t)tid * nc + a * BS + tid] = 1.0;
+    // coarse dofs without any free fine dof: unit diagonal keeps E invertible (their w is always 0).  With rotations a
+    // degenerate aggregate (collinear nodes) has a rotation that moves nothing: E + 1e-9 diag(E) stays positive definite.
+    if (tid < CD) {
+        double& d = erow[(size_t)tid * nc + a * CD + tid];
+        if (d == 0.0) d = 1.0;
+        else if (rbm) d *= 1.0 + 1e-9;
+    }
     __syncthreads();
-    for (int k = tid; k < BS * nc; k += CO_THREADS) E[(size_t)(a * BS) * nc + k] = erow[k];
+    for (int k = tid; k < CD * nc; k += CO_THREADS) E[(size_t)(a * CD) * nc + k] = erow[k];
 }
 
 // In-place Gauss-Jordan inversion of the SPD coarse matrix (no pivoting) in ONE cooperative launch.  The matrix is
@@ -1101,7 +1144,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     __shared__ double sh4[4];
     __shared__ __align__(8) uint64_t full[ST_MAX_CW][ST_MAX_DEPTH], empty[ST_MAX_CW][ST_MAX_DEPTH];
     __shared__ int s_width[ST_MAX_CW][ST_MAX_DEPTH];  // blocks per row of the slice sitting in a slot
-    __shared__ double s_wp[ST_MAX_CW + 1][BS];        // two-level preconditioner: chunk sums of w = Z^T r
+    constexpr int CDM = BS == 3 ? 6 : BS;             // most coarse dofs per aggregate (translations + rotations in 3D)
+    __shared__ double s_wp[ST_MAX_CW + 1][CDM];       // two-level preconditioner: chunk sums of w = Z^T r
     constexpr int BB = BS * BS;
     constexpr int PS = BS == 3 ? 4 : BS;  // stride of a node in the padded search direction
     const int tid = threadIdx.x;
@@ -1198,31 +1242,71 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     //      Two more grid barriers per application (r complete -> w; w complete -> y), the third is the reduction
     //      that follows anyway.
     const bool two_level = A.precond == 2;
-    auto coarse_apply = [&]() -> double {
-        const CoarseArgs& G = A.co;
-        const int gw = (int)(gtid >> 5), nw = (int)(gsz >> 5);
-        long long tca = profiling ? clock64() : 0;
-        auto cprof = [&](int k) {  // aux counters 8..11: barrier, w = Z^T r, barrier, y = E^-1 w (cycles of block 0)
-            if (profiling) {
-                const long long tn = clock64();
-                A.prof[k] += tn - tca;
-                tca = tn;
+    const int CD = A.co.cd;
+    const bool rbm = BS == 3 && CD == 6;
+    long long tca = 0;
+    auto cprof = [&](int k) {  // aux counters 8..11 (cycles of block 0): barrier, w = Z^T r (stand-alone pass), barrier, y = E^-1 w
+        if (profiling) {
+            const long long tn = clock64();
+            A.prof[k] += tn - tca;
+            tca = tn;
+        }
+    };
+    // aggregates are dealt over ALL CTAs: AG_PER_CTA per CTA and pass, SPLIT warps share one aggregate (512 aggregates on
+    // 148 CTAs: 4 x 3 warps; 256 aggregates: 2 x 6 warps).  Fixed by (n_agg, grid) alone, so the summation order is too.
+    const int AG_PER_CTA = two_level ? max(1, min(CW + 1, (A.co.n_agg + (int)gridDim.x - 1) / (int)gridDim.x)) : 1;
+    const int SPLIT = (CW + 1) / AG_PER_CTA;
+    // adds node nd's share of w = Z^T r to the lane's accumulators: [sum r | sum rho x r]
+    auto w_accumulate = [&](double (&acc)[CDM], int64_t nd, const double (&rv)[BS]) {
+#pragma unroll
+        for (int c = 0; c < BS; ++c) acc[c] += rv[c];
+        if constexpr (BS == 3) {
+            if (rbm) {
+                const double* rp = A.co.rho + nd * 3;
+                const double r0 = rp[0], r1 = rp[1], r2 = rp[2];
+                acc[3] += r1 * rv[2] - r2 * rv[1];
+                acc[4] += r2 * rv[0] - r0 * rv[2];
+                acc[5] += r0 * rv[1] - r1 * rv[0];
             }
-        };
+        }
+    };
+    // the SPLIT chunk sums of an aggregate meet in shared memory and are added in chunk order (both barriers inside)
+    auto w_combine = [&](const double (&acc)[CDM], bool active, int base_a) {
+        if (active) {
+#pragma unroll
+            for (int c = 0; c < CDM; ++c) {
+                double v = acc[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) s_wp[w][c] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < AG_PER_CTA * CD && base_a + tid / CD < A.co.n_agg) {
+            const int m2 = tid / CD, c = tid % CD;
+            double v = 0.0;
+            for (int k2 = 0; k2 < SPLIT; ++k2) v += s_wp[m2 * SPLIT + k2][c];
+            A.co.w[(base_a + m2) * CD + c] = v;
+        }
+        __syncthreads();
+    };
+    // stand-alone w = Z^T r for the r every CTA has just finished writing (prologue): barrier, then the gather pass.
+    // SPLIT warps of one CTA share an aggregate (enough warps in flight to hide the dependent load levels).
+    auto coarse_w_pass = [&]() {
+        const CoarseArgs& G = A.co;
+        if (profiling) tca = clock64();
         grid.sync();
         cprof(8);
-        // w = Z^T r: CO_SPLIT warps of one CTA share an aggregate (enough warps in flight to hide the two dependent load
-        // levels: node ids -> residuals); their chunk sums meet in shared memory and are added in chunk order
-        constexpr int AG_PER_CTA = (CW + 1) / CO_SPLIT;
         for (int base_a = (int)blockIdx.x * AG_PER_CTA; base_a < G.n_agg; base_a += (int)gridDim.x * AG_PER_CTA) {
-            const int m = w / CO_SPLIT, ch = w % CO_SPLIT, a = base_a + m;
-            if (m < AG_PER_CTA && a < G.n_agg) {
-                const int q0 = G.agg_ptr[a], q1 = G.agg_ptr[a + 1];
-                const int len = (q1 - q0 + CO_SPLIT - 1) / CO_SPLIT;
-                const int b0 = q0 + ch * len, b1 = b0 + len < q1 ? b0 + len : q1;
-                double acc[BS];
+            const int m = w / SPLIT, ch = w % SPLIT, a = base_a + m;
+            const bool active = m < AG_PER_CTA && a < G.n_agg;
+            double acc[CDM];
 #pragma unroll
-                for (int c = 0; c < BS; ++c) acc[c] = 0.0;
+            for (int c = 0; c < CDM; ++c) acc[c] = 0.0;
+            if (active) {
+                const int q0 = G.agg_ptr[a], q1 = G.agg_ptr[a + 1];
+                const int len = (q1 - q0 + SPLIT - 1) / SPLIT;
+                const int b0 = q0 + ch * len, b1 = b0 + len < q1 ? b0 + len : q1;
                 for (int q = b0 + lane; q < b1; q += 128) {  // four nodes per lane and trip: ids first, then their residuals
                     int64_t nd[4];
 #pragma unroll
@@ -1234,30 +1318,22 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                         for (int c = 0; c < BS; ++c) rv[u][c] = nd[u] >= 0 ? A.r[nd[u] * BS + c] : 0.0;
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-#pragma unroll
-                        for (int c = 0; c < BS; ++c) acc[c] += rv[u][c];
-                }
-#pragma unroll
-                for (int c = 0; c < BS; ++c) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-                    if (lane == 0) s_wp[w][c] = acc[c];
+                        if (nd[u] >= 0) w_accumulate(acc, nd[u], rv[u]);
                 }
             }
-            __syncthreads();
-            if (tid < AG_PER_CTA * BS && base_a + tid / BS < G.n_agg) {
-                const int m2 = tid / BS, c = tid % BS;
-                double v = 0.0;
-#pragma unroll
-                for (int k2 = 0; k2 < CO_SPLIT; ++k2) v += s_wp[m2 * CO_SPLIT + k2][c];
-                G.w[(base_a + m2) * BS + c] = v;
-            }
-            __syncthreads();
+            w_combine(acc, active, base_a);
         }
         cprof(9);
+    };
+    // y = E^-1 w once w is complete: barrier, then one warp per row of the dense inverse (L2-resident; 16-byte loads,
+    // 12 + 12 of them in flight per lane).  z is never stored: r.z = sum r^2 d + w.y, so this leaves y in memory and
+    // returns the thread's share of w.y; the p update forms z_i = d_i r_i + (Z y)_i on the fly.
+    auto coarse_solve = [&]() -> double {
+        const CoarseArgs& G = A.co;
+        const int gw = (int)(gtid >> 5), nw = (int)(gsz >> 5);
+        if (profiling) tca = clock64();
         grid.sync();
         cprof(10);
-        // y = E^-1 w: one warp per row of the dense inverse (L2-resident); 16-byte loads, 12 + 12 of them in flight per lane
         double wy = 0.0;
         for (int k = gw; k < G.nc; k += nw) {
             double acc = 0.0;
@@ -1300,7 +1376,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     cg_prologue_body<BS>(A, gtid, gsz, g4);
     if (mg) ++hepoch;
     if (two_level) {
-        g4[P_RZ] += coarse_apply();  // r.z = sum r^2 d (already there) + w.y; z itself is pushed / formed in the p update
+        coarse_w_pass();
+        g4[P_RZ] += coarse_solve();  // r.z = sum r^2 d (already there) + w.y; z itself is pushed / formed in the p update
     } else if (mg) {
         for (int64_t i = gtid; i < A.n; i += gsz)
             if (A.mask[i] & 2) p2p_push(P, i, A.r[i] * A.dinv[i], hepoch);
@@ -1336,7 +1413,19 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                     b[u] = dv[i];
                     c[u] = pv[pad_of(i)];
                     yc[u] = 0.0;
-                    if (two_level) yc[u] = __ldcg(A.co.y + (size_t)A.co.agg[i / BS] * BS + (i % BS));
+                    if (two_level) {
+                        const int64_t nd = i / BS;
+                        const int cc = (int)(i % BS);
+                        const double* ya = A.co.y + (size_t)A.co.agg[nd] * CD;
+                        yc[u] = __ldcg(ya + cc);
+                        if constexpr (BS == 3) {
+                            if (rbm) {  // (omega x rho)_c = omega_{c+1} rho_{c+2} - omega_{c+2} rho_{c+1}
+                                const int c1 = cc == 2 ? 0 : cc + 1, c2 = cc == 0 ? 2 : cc - 1;
+                                const double* rp = A.co.rho + nd * 3;
+                                yc[u] += __ldcg(ya + 3 + c1) * rp[c2] - __ldcg(ya + 3 + c2) * rp[c1];
+                            }
+                        }
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < VB; ++u) {
@@ -1422,6 +1511,60 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         // ---- x += alpha p ; r -= alpha Ap ; multi-GPU: push z of the interface dofs right away
         ++hepoch;
         double s2[2] = {0.0, 0.0};
+        if (two_level) {
+            // the same update in AGGREGATE order, so that w = Z^T r of the new residual is accumulated on the way
+            // (no second pass over r, no barrier between the update and the gather): SPLIT warps per aggregate,
+            // two nodes per lane and trip (ids first, then the 5 vectors of both nodes)
+            const CoarseArgs& G = A.co;
+            for (int base_a = (int)blockIdx.x * AG_PER_CTA; base_a < G.n_agg; base_a += (int)gridDim.x * AG_PER_CTA) {
+                const int m = w / SPLIT, ch = w % SPLIT, a = base_a + m;
+                const bool active = m < AG_PER_CTA && a < G.n_agg;
+                double acc[CDM];
+#pragma unroll
+                for (int c = 0; c < CDM; ++c) acc[c] = 0.0;
+                if (active) {
+                    const int q0 = G.agg_ptr[a], q1 = G.agg_ptr[a + 1];
+                    const int len = (q1 - q0 + SPLIT - 1) / SPLIT;
+                    const int b0 = q0 + ch * len, b1 = b0 + len < q1 ? b0 + len : q1;
+                    for (int q = b0 + lane; q < b1; q += 64) {
+                        int64_t nd[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) nd[u] = q + 32 * u < b1 ? G.agg_nodes[q + 32 * u] : -1;
+                        double x[2][BS], pp[2][BS], rr[2][BS], ap[2][BS], di[2][BS];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int64_t n0 = nd[u] >= 0 ? nd[u] : 0;
+#pragma unroll
+                            for (int c = 0; c < BS; ++c) {
+                                const int64_t i = n0 * BS + c;
+                                x[u][c] = A.x[i];
+                                pp[u][c] = A.p_pad[pad_of(i)];
+                                rr[u][c] = A.r[i];
+                                ap[u][c] = A.Ap[i];
+                                di[u][c] = A.dinv[i];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (nd[u] < 0) continue;
+                            double rn[BS];
+#pragma unroll
+                            for (int c = 0; c < BS; ++c) {
+                                const int64_t i = nd[u] * BS + c;
+                                A.x[i] = x[u][c] + alpha * pp[u][c];
+                                const double ri = di[u][c] != 0.0 ? rr[u][c] - alpha * ap[u][c] : 0.0;
+                                A.r[i] = ri;
+                                rn[c] = ri;
+                                s2[0] += ri * ri;
+                                s2[1] += ri * (ri * di[u][c]);
+                            }
+                            w_accumulate(acc, nd[u], rn);
+                        }
+                    }
+                }
+                w_combine(acc, active, base_a);
+            }
+        } else
         {
             double* __restrict__ xv = A.x;
             double* __restrict__ rv = A.r;
@@ -1454,7 +1597,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                 }
             }
         }
-        if (two_level) s2[1] += coarse_apply();  // r.z = sum r^2 d + w.y
+        if (two_level) s2[1] += coarse_solve();  // r.z = sum r^2 d + w.y
         s2[0] = block_sum<ST_THREADS>(s2[0], sh);
         s2[1] = block_sum<ST_THREADS>(s2[1], sh);
         prof(4);

@@ -167,10 +167,11 @@ struct onsas_ctx {
     struct Coarse {
         bool built = false;   // aggregates exist for the current mesh
         bool fresh = false;   // Einv matches the K currently assembled
-        int n_agg = 0, nc = 0;
+        int n_agg = 0, nc = 0, cd = 0;
     } co;
+    bool coarse_rbm = true;  // 3D: rigid-body rotations of every aggregate join the coarse space (6 coarse dofs per aggregate)
     DevBuf<int32_t> co_agg, co_agg_ptr, co_agg_nodes;
-    DevBuf<double> co_E, co_w, co_y, co_rowbuf;
+    DevBuf<double> co_E, co_w, co_y, co_rowbuf, co_rho;
     // onsas_assemble_host: slice ranges launched one after the other while the copies of U (in) and F_int (out) overlap them
     int64_t asm_first = 0, asm_count = -1;  // slice range of the next assembly launches (-1: all slices)
     int host_chunks = 4, host_mid_weight = 4;
@@ -666,7 +667,8 @@ void build_coarse(onsas_ctx* c) {
     if (c->co.built) return;
     const int64_t n = c->n_owned;
     require(n > 0, ONSAS_ERR_NOT_READY, "two-level preconditioner: no owned nodes");
-    int n_agg = (int)std::max<int64_t>(1, std::min<int64_t>(n / CO_TARGET_NODES, CO_NC_MAX / c->dim));
+    const int cd = (c->dim == 3 && c->coarse_rbm) ? 6 : c->dim;
+    int n_agg = (int)std::max<int64_t>(1, std::min<int64_t>(n / CO_TARGET_NODES, CO_NC_MAX / cd));
     std::vector<int32_t> ids((size_t)n), agg((size_t)n, 0);
     for (int64_t i = 0; i < n; ++i) ids[i] = (int32_t)i;
     rcb_aggregate(c->h_xyz.data(), c->dim, ids, 0, (size_t)n, n_agg, 0, agg);
@@ -675,7 +677,19 @@ void build_coarse(onsas_ctx* c) {
     for (int a = 0; a < n_agg; ++a) ptr[a + 1] += ptr[a];
     std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
     for (int64_t i = 0; i < n; ++i) nodes[fill[agg[i]]++] = (int32_t)i;  // ascending node id inside every aggregate
-    const int nc = n_agg * c->dim;
+    if (cd == 6) {  // node positions relative to the aggregate's centroid (reference configuration): the rotation modes
+        std::vector<double> cen((size_t)n_agg * 3, 0.0), rho((size_t)n * 3);
+        for (int a = 0; a < n_agg; ++a) {
+            for (int32_t q = ptr[a]; q < ptr[a + 1]; ++q)
+                for (int d = 0; d < 3; ++d) cen[(size_t)a * 3 + d] += c->h_xyz[(size_t)nodes[q] * 3 + d];
+            const double inv = 1.0 / std::max<int32_t>(1, ptr[a + 1] - ptr[a]);
+            for (int d = 0; d < 3; ++d) cen[(size_t)a * 3 + d] *= inv;
+        }
+        for (int64_t i = 0; i < n; ++i)
+            for (int d = 0; d < 3; ++d) rho[(size_t)i * 3 + d] = c->h_xyz[(size_t)i * 3 + d] - cen[(size_t)agg[i] * 3 + d];
+        c->co_rho.upload(rho, c->stream);
+    }
+    const int nc = n_agg * cd;
     cudaStream_t s = c->stream;
     c->co_agg.upload(agg, s);
     c->co_agg_ptr.upload(ptr, s);
@@ -687,14 +701,17 @@ void build_coarse(onsas_ctx* c) {
     CUDA_CHECK(cudaStreamSynchronize(s));
     c->co.n_agg = n_agg;
     c->co.nc = nc;
+    c->co.cd = cd;
     c->co.built = true;
     c->co.fresh = false;
-    if (getenv("ONSAS_VERBOSE")) fprintf(stderr, "[onsas] two-level preconditioner: %d aggregates of ~%lld nodes, %d coarse dofs\n", n_agg, (long long)(n / n_agg), nc);
+    if (getenv("ONSAS_VERBOSE")) fprintf(stderr, "[onsas] two-level preconditioner: %d aggregates of ~%lld nodes, %d coarse dofs each (%s), %d in total\n", n_agg, (long long)(n / n_agg), cd, cd == 6 ? "translations + rotations" : "translations", nc);
 }
 
 void fill_coarse_args(onsas_ctx* c, CgArgs& A) {
     A.co.n_agg = c->co.n_agg;
     A.co.nc = c->co.nc;
+    A.co.cd = c->co.cd;
+    A.co.rho = c->co.cd == 6 ? c->co_rho.p : nullptr;
     A.co.agg = c->co_agg.p;
     A.co.agg_ptr = c->co_agg_ptr.p;
     A.co.agg_nodes = c->co_agg_nodes.p;
@@ -711,7 +728,7 @@ void refresh_coarse(onsas_ctx* c, CgArgs& A) {
     if (c->co.fresh) return;
     const int nc = c->co.nc;
     {
-        const size_t smem = ((size_t)BS * nc + (size_t)CO_NW * CO_WB * BS * BS) * sizeof(double);
+        const size_t smem = ((size_t)c->co.cd * nc + (size_t)CO_NW * CO_WB * BS * BS) * sizeof(double);
         static size_t configured = 0;
         if (smem > configured) {
             CUDA_CHECK(cudaFuncSetAttribute(k_coarse_assemble<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -942,6 +959,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_ASM_MINBLOCKS: require(value >= 1 && value <= 3, ONSAS_ERR_INVALID_ARG, "min blocks must be 1..3"); c->asm_minb = (int)value; break;
             case ONSAS_OPT_CG_CHECK_EVERY: require(value >= 1 && value <= 4096, ONSAS_ERR_INVALID_ARG, "check_every out of range"); c->check_every = (int)value; break;
             case ONSAS_OPT_FORCE_MG: c->force_mg = value != 0; break;
+            case ONSAS_OPT_COARSE_RBM: c->coarse_rbm = value != 0; c->co.built = false; c->co.fresh = false; break;
             case ONSAS_OPT_GJ_BLOCKED: c->gj_blocked = value != 0; c->co.fresh = false; break;
             case ONSAS_OPT_HOST_CHUNKS: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "host chunks must be 1..64"); c->host_chunks = (int)value; c->hp.built = false; break;
             case ONSAS_OPT_HOST_MID_WEIGHT: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "weight must be 1..64"); c->host_mid_weight = (int)value; c->hp.built = false; break;

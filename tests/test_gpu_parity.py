@@ -345,10 +345,15 @@ def test_two_level_preconditioner(ob, oracle):
     xd = np.zeros(m.n_dofs)
     xd[free] = spla.spsolve(A[free][:, free].tocsc(), b[free])
     xj, itj, _ = ctx.pcg(b, ob.PRECOND_JACOBI, 1e-12)
+    # translations only, then (default) translations + rotations of every aggregate
+    ctx.set_option(ob._lib.OPT_COARSE_RBM, 0)
+    xt, itt, _ = ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-12)
+    assert cases.rel_err(xt, xd) < 1e-8 and itt < 0.8 * itj, (itt, itj)
+    ctx.set_option(ob._lib.OPT_COARSE_RBM, 1)
     x2, it2, res2 = ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-12)
     assert cases.rel_err(x2, xd) < 1e-8 and cases.rel_err(xj, xd) < 1e-8
     assert np.all(x2[m.free_mask() == 0] == 0)
-    assert it2 < 0.8 * itj, (it2, itj)
+    assert it2 < itt < 0.8 * itj, (it2, itt, itj)
     x3, it3, _ = ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-12)
     assert it3 == it2
     np.testing.assert_array_equal(x3, x2)
