@@ -386,6 +386,7 @@ enum : int { P_RR = 0, P_RZ = 1, P_FF = 2, P_UU = 3, P_PAP = 4, P_DD = 5, P_COUN
 struct CoarseArgs {
     int n_agg, nc;
     int cd;                    // coarse dofs per aggregate: BS (translations) or 6 (+ rigid-body rotations, BS = 3 only)
+    int fused;                 // 1: the residual update runs in aggregate order and accumulates w = Z^T r on the way
     const double* rho;         // [n_rows][3] node position relative to its aggregate's centroid (cd = 6), else null
     const int32_t* agg;        // [n_rows] aggregate of every owned node
     const int32_t* agg_ptr;    // [n_agg+1]
@@ -1403,8 +1404,58 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
             const double* __restrict__ rv = A.r;
             const double* __restrict__ dv = A.dinv;
             double* __restrict__ pv = A.p_pad;
+            bool nodewise = false;
+            if constexpr (BS == 3) {
+                if (two_level) {
+                    // one thread per NODE: its aggregate id, the aggregate's 3 (or 6) coarse values and the node's rho are
+                    // fetched once for the three dofs; p travels as one 32-byte sector in and out
+                    nodewise = true;
+                    const int32_t* __restrict__ agv = A.co.agg;
+                    for (int64_t n0 = gtid; n0 < A.n_rows; n0 += 2 * gsz) {
+                        double ra[2][3], da[2][3], pa[2][3], rh[2][3];
+                        int ag[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int64_t nd = n0 + u * gsz < A.n_rows ? n0 + u * gsz : A.n_rows - 1;
+                            ag[u] = agv[nd];
+                            ld_node<BS>(pv + nd * PS, pa[u]);
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) {
+                                ra[u][cc] = rv[nd * 3 + cc];
+                                da[u][cc] = dv[nd * 3 + cc];
+                                rh[u][cc] = rbm ? A.co.rho[nd * 3 + cc] : 0.0;
+                            }
+                        }
+                        double ty[2][3], om[2][3];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const double* ya = A.co.y + (size_t)ag[u] * CD;
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) {
+                                ty[u][cc] = __ldcg(ya + cc);
+                                om[u][cc] = rbm ? __ldcg(ya + 3 + cc) : 0.0;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int64_t nd = n0 + u * gsz;
+                            if (nd < A.n_rows) {
+                                const double zc[3] = {ty[u][0] + om[u][1] * rh[u][2] - om[u][2] * rh[u][1],   // t + omega x rho
+                                                      ty[u][1] + om[u][2] * rh[u][0] - om[u][0] * rh[u][2],
+                                                      ty[u][2] + om[u][0] * rh[u][1] - om[u][1] * rh[u][0]};
+#pragma unroll
+                                for (int cc = 0; cc < 3; ++cc) {
+                                    const double zi = da[u][cc] != 0.0 ? ra[u][cc] * da[u][cc] + zc[cc] : 0.0;
+                                    pv[nd * PS + cc] = zi + beta * pa[u][cc];
+                                    if (mg && (A.mask[nd * 3 + cc] & 2)) p2p_push(P, nd * 3 + cc, zi, hepoch);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
             // one CTA per SM: batches of VB independent dofs per thread keep enough loads in flight
-            for (int64_t i0 = gtid; i0 < A.n; i0 += VB * gsz) {
+            for (int64_t i0 = gtid; !nodewise && i0 < A.n; i0 += VB * gsz) {
                 double a[VB], b[VB], c[VB], yc[VB];
 #pragma unroll
                 for (int u = 0; u < VB; ++u) {  // loads of a batch first (tail lanes re-read the last dof: no branches)
@@ -1511,7 +1562,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         // ---- x += alpha p ; r -= alpha Ap ; multi-GPU: push z of the interface dofs right away
         ++hepoch;
         double s2[2] = {0.0, 0.0};
-        if (two_level) {
+        const bool fused_w = two_level && A.co.fused != 0;
+        if (fused_w) {
             // the same update in AGGREGATE order, so that w = Z^T r of the new residual is accumulated on the way
             // (no second pass over r, no barrier between the update and the gather): SPLIT warps per aggregate,
             // two nodes per lane and trip (ids first, then the 5 vectors of both nodes)
@@ -1597,7 +1649,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                 }
             }
         }
-        if (two_level) s2[1] += coarse_solve();  // r.z = sum r^2 d + w.y
+        if (two_level) {  // r.z = sum r^2 d + w.y
+            if (!fused_w) coarse_w_pass();
+            s2[1] += coarse_solve();
+        }
         s2[0] = block_sum<ST_THREADS>(s2[0], sh);
         s2[1] = block_sum<ST_THREADS>(s2[1], sh);
         prof(4);

@@ -15,12 +15,15 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     mesh, free, U_half, U_prev, Fext = bench.build_problem(55, 1)
     ctx = ob.context_from_flat(mesh.xyz, tets=mesh.tets, mat_kind=[ob.MAT_NEOHOOKEAN], mat_params=[[bench.KBULK, bench.MU]], free_dofs=free)
     ctx.set_Fext(Fext)
-    for precond in (ob.PRECOND_JACOBI, ob.PRECOND_TWO_LEVEL):
+    for precond, rbm, fused in ((ob.PRECOND_JACOBI, 0, 0), (ob.PRECOND_TWO_LEVEL, 0, 0), (ob.PRECOND_TWO_LEVEL, 0, 1),
+                                (ob.PRECOND_TWO_LEVEL, 1, 1), (ob.PRECOND_TWO_LEVEL, 1, 0)):
+        ctx.set_option(L.OPT_COARSE_RBM, rbm)
+        ctx.set_option(L.OPT_COARSE_FUSED, fused)
         for prof in (0, 0, 1):
             ctx.set_option(L.OPT_CG_PROFILE, prof)
             ctx.set_U(U_prev)
             info = ctx.newton_step(precond)
-            line = (f"cw={os.environ.get('ONSAS_STREAM_CW', '12')} depth={os.environ.get('ONSAS_STREAM_DEPTH', '2')} precond={precond} prof={prof} "
+            line = (f"precond={precond} rbm={rbm} fused={fused} prof={prof} "
                     f"cg_iters={info.cg_iters} ms_solve={info.ms_solve:.2f} us/iter={1e3 * info.ms_solve / info.cg_iters:.2f} |dU|={info.norm_dU:.10e}")
             if prof:
                 pv = ctx.cg_profile()
