@@ -1396,6 +1396,27 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     long long it = 0;
     if (profiling) tprev = clock64();
 
+    // fused residual update (two-level): this warp's chunk of its aggregate, fixed for the whole solve
+    const int fw_base_a = (int)blockIdx.x * AG_PER_CTA;
+    const bool fw_cta = two_level && fw_base_a < A.co.n_agg;  // AG_PER_CTA = ceil(n_agg / grid): a single pass covers all aggregates
+    bool fw_active = false;
+    int fw_b0 = 0, fw_b1 = 0;
+    int fw_nid[4] = {-1, -1, -1, -1};
+    if (fw_cta && A.co.fused != 0) {
+        const int m = w / SPLIT, ch = w % SPLIT, a = fw_base_a + m;
+        fw_active = m < AG_PER_CTA && a < A.co.n_agg;
+        if (fw_active) {
+            const int q0 = A.co.agg_ptr[a], q1 = A.co.agg_ptr[a + 1];
+            const int len = (q1 - q0 + SPLIT - 1) / SPLIT;
+            fw_b0 = q0 + ch * len;
+            fw_b1 = fw_b0 + len < q1 ? fw_b0 + len : q1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = fw_b0 + lane + 32 * u;
+                fw_nid[u] = q < fw_b1 ? A.co.agg_nodes[q] : -1;
+            }
+        }
+    }
     const int lrow = lane & 7, qpart = lane >> 3;
     while (!(it >= A.maxiter || res <= tol)) {
         // ---- p = z + beta p (owned dofs; halo dofs from the neighbours' pushes of epoch hepoch)
@@ -1411,11 +1432,12 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                     // fetched once for the three dofs; p travels as one 32-byte sector in and out
                     nodewise = true;
                     const int32_t* __restrict__ agv = A.co.agg;
-                    for (int64_t n0 = gtid; n0 < A.n_rows; n0 += 2 * gsz) {
-                        double ra[2][3], da[2][3], pa[2][3], rh[2][3];
-                        int ag[2];
+                    constexpr int NB = 2;  // nodes per thread and trip (3 would cover the 1 M-tet cube in one trip but spills: 54 live doubles)
+                    for (int64_t n0 = gtid; n0 < A.n_rows; n0 += NB * gsz) {
+                        double ra[NB][3], da[NB][3], pa[NB][3], rh[NB][3];
+                        int ag[NB];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < NB; ++u) {
                             const int64_t nd = n0 + u * gsz < A.n_rows ? n0 + u * gsz : A.n_rows - 1;
                             ag[u] = agv[nd];
                             ld_node<BS>(pv + nd * PS, pa[u]);
@@ -1426,9 +1448,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                                 rh[u][cc] = rbm ? A.co.rho[nd * 3 + cc] : 0.0;
                             }
                         }
-                        double ty[2][3], om[2][3];
+                        double ty[NB][3], om[NB][3];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < NB; ++u) {
                             const double* ya = A.co.y + (size_t)ag[u] * CD;
 #pragma unroll
                             for (int cc = 0; cc < 3; ++cc) {
@@ -1437,7 +1459,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < NB; ++u) {
                             const int64_t nd = n0 + u * gsz;
                             if (nd < A.n_rows) {
                                 const double zc[3] = {ty[u][0] + om[u][1] * rh[u][2] - om[u][2] * rh[u][1],   // t + omega x rho
@@ -1565,56 +1587,61 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         const bool fused_w = two_level && A.co.fused != 0;
         if (fused_w) {
             // the same update in AGGREGATE order, so that w = Z^T r of the new residual is accumulated on the way
-            // (no second pass over r, no barrier between the update and the gather): SPLIT warps per aggregate,
-            // two nodes per lane and trip (ids first, then the 5 vectors of both nodes)
+            // (no second pass over r, no barrier between the update and the gather).  A warp keeps the same chunk of
+            // the same aggregate for the whole solve: the ids of its first 128 nodes live in registers (fw_nid), so
+            // an update is one round trip to the five vectors per two nodes instead of three dependent ones.
             const CoarseArgs& G = A.co;
-            for (int base_a = (int)blockIdx.x * AG_PER_CTA; base_a < G.n_agg; base_a += (int)gridDim.x * AG_PER_CTA) {
-                const int m = w / SPLIT, ch = w % SPLIT, a = base_a + m;
-                const bool active = m < AG_PER_CTA && a < G.n_agg;
+            if (fw_cta) {
                 double acc[CDM];
 #pragma unroll
                 for (int c = 0; c < CDM; ++c) acc[c] = 0.0;
-                if (active) {
-                    const int q0 = G.agg_ptr[a], q1 = G.agg_ptr[a + 1];
-                    const int len = (q1 - q0 + SPLIT - 1) / SPLIT;
-                    const int b0 = q0 + ch * len, b1 = b0 + len < q1 ? b0 + len : q1;
-                    for (int q = b0 + lane; q < b1; q += 64) {
-                        int64_t nd[2];
+                auto update_pair = [&](const int64_t (&nd)[2]) {
+                    double x[2][BS], pp[2][BS], rr[2][BS], ap[2][BS], di[2][BS];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) nd[u] = q + 32 * u < b1 ? G.agg_nodes[q + 32 * u] : -1;
-                        double x[2][BS], pp[2][BS], rr[2][BS], ap[2][BS], di[2][BS];
+                    for (int u = 0; u < 2; ++u) {
+                        const int64_t n0 = nd[u] >= 0 ? nd[u] : 0;
+                        ld_node<BS>(A.p_pad + n0 * PS, pp[u]);
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int64_t n0 = nd[u] >= 0 ? nd[u] : 0;
-#pragma unroll
-                            for (int c = 0; c < BS; ++c) {
-                                const int64_t i = n0 * BS + c;
-                                x[u][c] = A.x[i];
-                                pp[u][c] = A.p_pad[pad_of(i)];
-                                rr[u][c] = A.r[i];
-                                ap[u][c] = A.Ap[i];
-                                di[u][c] = A.dinv[i];
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            if (nd[u] < 0) continue;
-                            double rn[BS];
-#pragma unroll
-                            for (int c = 0; c < BS; ++c) {
-                                const int64_t i = nd[u] * BS + c;
-                                A.x[i] = x[u][c] + alpha * pp[u][c];
-                                const double ri = di[u][c] != 0.0 ? rr[u][c] - alpha * ap[u][c] : 0.0;
-                                A.r[i] = ri;
-                                rn[c] = ri;
-                                s2[0] += ri * ri;
-                                s2[1] += ri * (ri * di[u][c]);
-                            }
-                            w_accumulate(acc, nd[u], rn);
+                        for (int c = 0; c < BS; ++c) {
+                            const int64_t i = n0 * BS + c;
+                            x[u][c] = A.x[i];
+                            rr[u][c] = A.r[i];
+                            ap[u][c] = A.Ap[i];
+                            di[u][c] = A.dinv[i];
                         }
                     }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (nd[u] < 0) continue;
+                        double rn[BS];
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) {
+                            const int64_t i = nd[u] * BS + c;
+                            A.x[i] = x[u][c] + alpha * pp[u][c];
+                            const double ri = di[u][c] != 0.0 ? rr[u][c] - alpha * ap[u][c] : 0.0;
+                            A.r[i] = ri;
+                            rn[c] = ri;
+                            s2[0] += ri * ri;
+                            s2[1] += ri * (ri * di[u][c]);
+                        }
+                        w_accumulate(acc, nd[u], rn);
+                    }
+                };
+                if (fw_active) {
+                    {
+                        const int64_t nd[2] = {fw_nid[0], fw_nid[1]};
+                        update_pair(nd);
+                    }
+                    if (fw_nid[2] >= 0) {
+                        const int64_t nd[2] = {fw_nid[2], fw_nid[3]};
+                        update_pair(nd);
+                    }
+                    for (int q = fw_b0 + 128 + lane; q < fw_b1; q += 64) {  // chunks longer than 128 nodes: ids from memory
+                        const int64_t nd[2] = {G.agg_nodes[q], q + 32 < fw_b1 ? G.agg_nodes[q + 32] : -1};
+                        update_pair(nd);
+                    }
                 }
-                w_combine(acc, active, base_a);
+                w_combine(acc, fw_active, fw_base_a);
             }
         } else
         {

@@ -169,7 +169,7 @@ struct onsas_ctx {
         bool fresh = false;   // Einv matches the K currently assembled
         int n_agg = 0, nc = 0, cd = 0;
     } co;
-    bool coarse_fused = false;  // residual update in aggregate order, fused with w = Z^T r (measured slower: gathers, r15 vs r17)
+    bool coarse_fused = true;  // residual update in aggregate order, fused with w = Z^T r (same-box sweep: profiles/r18)
     bool coarse_rbm = true;  // 3D: rigid-body rotations of every aggregate join the coarse space (6 coarse dofs per aggregate)
     DevBuf<int32_t> co_agg, co_agg_ptr, co_agg_nodes;
     DevBuf<double> co_E, co_w, co_y, co_rowbuf, co_rho;
