@@ -73,7 +73,6 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: resident CTAs per SM the kernel is compiled for: 4, 5 or 6 (default 6); 1-3 shrink the grid */
 #define ONSAS_OPT_FORCE_MG 6         /* diagnostics: set before onsas_finalize_mesh to run the multi-GPU CG kernel with a single rank */
 #define ONSAS_OPT_HOST_MID_WEIGHT 9   /* onsas_assemble_host: size of an inner slice range relative to the first / last one (default 4) */
-#define ONSAS_OPT_ASM_PREFETCH 12     /* assembly kernel: the CTA of slice s prefetches the tables of slice s + value into L2 (0 = off) */
 #define ONSAS_OPT_COARSE_FUSED 11     /* two-level preconditioner: 1 = residual update in aggregate order, fused with w = Z^T r (default), 0 = separate pass */
 #define ONSAS_OPT_COARSE_RBM 10       /* two-level preconditioner in 3D: 1 = rigid-body rotations of every aggregate join the coarse space (default), 0 = translations only */
 #define ONSAS_OPT_GJ_BLOCKED 8        /* two-level preconditioner: 1 = coarse inverse by 12-row panels (default), 0 = one pivot row per grid barrier */

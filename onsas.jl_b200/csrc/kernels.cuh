@@ -55,8 +55,6 @@ struct AsmArgs {
     int max_width;
     int64_t n_rows_guard;  // number of owned rows (the last slice may be partial)
     int slice0;            // first slice of this launch (CTA b works on slice slice0 + b): onsas_assemble_host launches ranges
-    int pf_dist;           // > 0: the CTA of slice s pulls the tables of slice s + pf_dist into L2 (0 = off)
-    int n_slices;
 };
 
 template <int KIND>
@@ -209,23 +207,6 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     }
     __syncthreads();
 
-    // ---- L2 prefetch for the CTA that will run ~one wave later: the pair records, contribution codes and slot ranges of
-    //      a slice are a compulsory DRAM stream that its CTA needs at once, two dependent round trips deep (header ->
-    //      records).  The last warp reads the header of slice + pf_dist now (it was prefetched by slice - pf_dist) and,
-    //      after its phase B work, touches that slice's table lines with prefetch.global.L2 (no registers held on data).
-    const bool pf_warp = A.pf_dist > 0 && (tid >> 5) == (nth >> 5) - 1;
-    int4 g0 = make_int4(0, 0, 0, 0), g1 = g0;
-    bool pf_ok = false;
-    if (pf_warp) {
-        const int s2 = slice + A.pf_dist;
-        pf_ok = s2 < A.n_slices;
-        if (pf_ok) {
-            const int4* gp = reinterpret_cast<const int4*>(A.hdr + s2);
-            g0 = __ldg(gp);
-            g1 = __ldg(gp + 1);
-        }
-    }
-
     // ---- phase B
     const int nK = width * DIM * C;
     const int nF = C * DIM;
@@ -265,21 +246,6 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
                 }
             }
         }
-    }
-    if (pf_warp && pf_ok) {
-        const int lane = tid & 31;
-        const int64_t q0 = (int64_t)(uint32_t)g0.x | ((int64_t)g0.y << 32);
-        const int64_t qb = (int64_t)(uint32_t)g0.z | ((int64_t)g0.w << 32);
-        const int qn = g1.x, qw = g1.y;
-        auto touch = [&](const void* base, int64_t bytes) {
-            const char* b = reinterpret_cast<const char*>(base);
-            for (int64_t off = (int64_t)lane * 128; off < bytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + off));
-        };
-        touch(A.pair_nodes + q0 * NPE, (int64_t)qn * NPE * 4);
-        touch(A.pair_code + q0, (int64_t)qn * 4);
-        touch(A.ccode + q0 * NPE, (int64_t)qn * NPE * 2);
-        touch(A.cptr + qb * C, ((int64_t)qw * C + 1) * 4);
-        if (lane == 0 && slice + 2 * A.pf_dist < A.n_slices) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.hdr + slice + 2 * A.pf_dist));
     }
 }
 

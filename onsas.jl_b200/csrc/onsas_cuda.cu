@@ -176,7 +176,6 @@ struct onsas_ctx {
     // onsas_assemble_host: slice ranges launched one after the other while the copies of U (in) and F_int (out) overlap them
     int64_t asm_first = 0, asm_count = -1;  // slice range of the next assembly launches (-1: all slices)
     int host_chunks = 4, host_mid_weight = 4;
-    int asm_prefetch = 0;  // assembly: L2 prefetch distance in slices (0 = off)
     bool gj_blocked = true;  // coarse inverse by the panel (blocked) Gauss-Jordan kernel; false: one pivot row per grid barrier
     struct HostPlan {
         bool built = false;
@@ -311,8 +310,6 @@ AsmArgs make_asm_args(onsas_ctx* c, int family) {
     A.elem_out = family == 0 ? c->tet_out.p : c->truss_out.p;
     A.err_flag = c->err_flag.p;
     A.slice0 = (int)c->asm_first;
-    A.pf_dist = c->asm_prefetch;
-    A.n_slices = (int)c->tab.n_slices;
     return A;
 }
 
@@ -964,7 +961,6 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_ASM_MINBLOCKS: require(value >= 1 && value <= 3, ONSAS_ERR_INVALID_ARG, "min blocks must be 1..3"); c->asm_minb = (int)value; break;
             case ONSAS_OPT_CG_CHECK_EVERY: require(value >= 1 && value <= 4096, ONSAS_ERR_INVALID_ARG, "check_every out of range"); c->check_every = (int)value; break;
             case ONSAS_OPT_FORCE_MG: c->force_mg = value != 0; break;
-            case ONSAS_OPT_ASM_PREFETCH: require(value >= 0 && value <= 1000000, ONSAS_ERR_INVALID_ARG, "prefetch distance out of range"); c->asm_prefetch = (int)value; break;
             case ONSAS_OPT_COARSE_FUSED: c->coarse_fused = value != 0; break;
             case ONSAS_OPT_COARSE_RBM: c->coarse_rbm = value != 0; c->co.built = false; c->co.fresh = false; break;
             case ONSAS_OPT_GJ_BLOCKED: c->gj_blocked = value != 0; c->co.fresh = false; break;
