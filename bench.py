@@ -231,23 +231,27 @@ def run_ours(args):
     nw = newton[len(newton) // 2]
     # ---- (3b) the same Newton step with the two-level preconditioner (Jacobi + aggregated coarse space);
     #      its time includes the coarse set-up (E = Z^T K Z and its inverse are rebuilt after every assembly)
-    nw2 = None
-    try:
-        if N > 1 and not os.environ.get("ONSAS_BENCH_TWO_LEVEL_MULTI"):
-            raise ob.OnsasError(0, "not enabled at N > 1 (set ONSAS_BENCH_TWO_LEVEL_MULTI=1)")
-        newton2 = []
-        for _ in range(max(1, min(K, 3))):
-            ctx.set_U(loc(U_prev))
-            barrier()
-            info = ctx.newton_step(ob.PRECOND_TWO_LEVEL)
-            newton2.append((max_over_ranks(info.ms_assemble + info.ms_solve), info.ms_assemble, info.ms_solve, int(info.cg_iters),
-                            info.norm_dU / max(info.norm_U, 1e-300)))
+    #      Every rank always takes part in the collectives below, whatever happened in its own solve.
+    nw2, two_level_ok = None, 1.0
+    newton2 = []
+    for _ in range(max(1, min(K, 3))):
+        ctx.set_U(loc(U_prev))
+        barrier()
+        ms_local, rec = float("nan"), None
+        if two_level_ok > 0:
+            try:
+                info = ctx.newton_step(ob.PRECOND_TWO_LEVEL)
+                ms_local = info.ms_assemble + info.ms_solve
+                rec = (info.ms_assemble, info.ms_solve, int(info.cg_iters), info.norm_dU / max(info.norm_U, 1e-300))
+            except ob.OnsasError as exc:   # e.g. --no-p2p: only the streamed persistent solver implements it
+                print(f"[bench] rank {rank}: two-level Newton step skipped: {exc}", file=sys.stderr)
+        two_level_ok = -max_over_ranks(-(1.0 if rec is not None else 0.0))   # min over ranks: did every rank succeed?
+        ms_all = max_over_ranks(ms_local if rec is not None else 0.0)
+        if two_level_ok > 0:
+            newton2.append((ms_all,) + rec)
+    if two_level_ok > 0 and newton2:
         newton2.sort()
         nw2 = newton2[len(newton2) // 2]
-    except ob.OnsasError as exc:   # e.g. --no-p2p: only the streamed persistent solver implements it
-        nw2 = None
-        if rank == 0:
-            print(f"[bench] two-level Newton step skipped: {exc}", file=sys.stderr)
 
     # ---- (4) SpMV alone (secondary roofline)
     for _ in range(3):

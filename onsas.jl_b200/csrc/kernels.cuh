@@ -164,9 +164,23 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     const int np = h1.x, width = h1.y;
     const uint32_t cbase = (uint32_t)(p0 * NPE);
     const int nscp = width * C + 1;
-    auto row_off = [&](int l) -> int {
-        const uint32_t w = l < 2 ? (uint32_t)h1.z : l < 4 ? (uint32_t)h1.w : l < 6 ? (uint32_t)h2.x : l < 8 ? (uint32_t)h2.y : (uint32_t)h2.z;
+    // The header is CTA-uniform: phase B re-reads it from shared memory (one STS here) instead of every thread carrying
+    // it in registers -- or, at 96 registers, in per-thread local memory -- across the element arithmetic.
+    __shared__ int4 s_hdr[3];
+    if (tid == 0) {
+        s_hdr[0] = h0;
+        s_hdr[1] = h1;
+        s_hdr[2] = h2;
+    }
+    auto row_off_of = [](const int4& a1, const int4& a2, int l) -> int {
+        const uint32_t w = l < 2 ? (uint32_t)a1.z : l < 4 ? (uint32_t)a1.w : l < 6 ? (uint32_t)a2.x : l < 8 ? (uint32_t)a2.y : (uint32_t)a2.z;
         return (int)((w >> (16 * (l & 1))) & 0xffffu);
+    };
+    auto row_of_pair = [&](const int4& a1, const int4& a2, int t) -> int {  // row of pair t inside the slice
+        int l = 0;
+#pragma unroll
+        for (int k = 1; k < C; ++k) l += (t >= row_off_of(a1, a2, k)) ? 1 : 0;
+        return l;
     };
 
     // ---- level 2 (independent loads, issued together): pair records, contribution codes, slot ranges
@@ -189,28 +203,34 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     for (int i = tid + nth; i < nscp; i += nth) scp[i] = (uint16_t)(__ldg(A.cptr + base * C + i) - cbase);
 
     // ---- phase A
-    while (t < np) {
+    int l = row_of_pair(h1, h2, t);  // the pair's record is skewed by its row inside the slice (bank spreading)
+    const int np_a = np;
+    while (t < np_a) {
         reinterpret_cast<CodeVec*>(scode)[t] = chunk;
-        int l = 0;  // row of this pair inside the slice: its record is skewed by l doubles (bank spreading)
-#pragma unroll
-        for (int k = 1; k < C; ++k) l += (t >= row_off(k)) ? 1 : 0;
         if constexpr (FAMILY == 0)
             tet_pair<KIND>(A, nodes, code, stage + (size_t)t * REC + l);
         else
             truss_pair<DIM>(A, nodes, code, stage + (size_t)t * REC + l);
         t += nth;
-        if (t < np) {  // slices with more pairs than threads (high-valence meshes)
-            nodes = __ldg(pn + t);
-            code = __ldg(A.pair_code + p0 + t);
-            chunk = __ldg(cc + t);
+        if (t < np_a) {  // slices with more pairs than threads (high-valence meshes): header again from L1, not from registers
+            const int4* hq = reinterpret_cast<const int4*>(A.hdr + slice);
+            const int64_t pq = (int64_t)(uint32_t)__ldg(hq).x | ((int64_t)__ldg(hq).y << 32);
+            nodes = __ldg(reinterpret_cast<const NodeVec*>(A.pair_nodes) + pq + t);
+            code = __ldg(A.pair_code + pq + t);
+            chunk = __ldg(reinterpret_cast<const CodeVec*>(A.ccode + (uint32_t)(pq * NPE)) + t);
+            l = row_of_pair(__ldg(hq + 1), __ldg(hq + 2), t);
         }
     }
     __syncthreads();
 
-    // ---- phase B
-    const int nK = width * DIM * C;
+    // ---- phase B (header from shared memory)
+    const int4 k0 = s_hdr[0], k1 = s_hdr[1], k2 = s_hdr[2];
+    const int64_t base_b = (int64_t)(uint32_t)k0.z | ((int64_t)k0.w << 32);
+    const int width_b = k1.y;
+    auto row_off = [&](int r) -> int { return row_off_of(k1, k2, r); };
+    const int nK = width_b * DIM * C;
     const int nF = C * DIM;
-    double* const vout = A.val + base * BB * C;
+    double* const vout = A.val + base_b * BB * C;
     for (int w = tid; w < nK + nF; w += nth) {
         if (w < nK) {
             const int lane = w % C;
