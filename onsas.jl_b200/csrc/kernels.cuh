@@ -132,7 +132,7 @@ __device__ __forceinline__ void truss_pair(const AsmArgs& A, const int2 cn, int3
 
 // shared memory of one assembly CTA: [stage: max_pairs*REC doubles][scode: max_pairs*NPE u16][scp: max_width*C+1 u16]
 __host__ __device__ constexpr size_t asm_smem_bytes(int max_pairs, int max_width, int rec, int npe) {
-    return ((size_t)max_pairs * rec + SLICE_ROWS) * 8 + (((size_t)max_pairs * npe * 2 + ((size_t)max_width * SLICE_ROWS + 1) * 2 + 15) / 16) * 16;
+    return ((size_t)max_pairs * rec + ROW_SKEW * SLICE_ROWS) * 8 + (((size_t)max_pairs * npe * 2 + ((size_t)max_width * SLICE_ROWS + 1) * 2 + 15) / 16) * 16;
 }
 
 // One CTA per BSELL slice (8 block rows).
@@ -151,7 +151,7 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     constexpr int NPE = FAMILY == 0 ? 4 : 2;
     constexpr int REC = FAMILY == 0 ? TET_REC : truss_rec(DIM);
     constexpr int FOFF = NPE * BB;
-    uint16_t* scode = reinterpret_cast<uint16_t*>(stage + (size_t)A.max_pairs * REC + C);
+    uint16_t* scode = reinterpret_cast<uint16_t*>(stage + (size_t)A.max_pairs * REC + ROW_SKEW * C);
     uint16_t* scp = scode + (size_t)A.max_pairs * NPE;
     const int tid = threadIdx.x, nth = blockDim.x;
 
@@ -208,9 +208,9 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     while (t < np_a) {
         reinterpret_cast<CodeVec*>(scode)[t] = chunk;
         if constexpr (FAMILY == 0)
-            tet_pair<KIND>(A, nodes, code, stage + (size_t)t * REC + l);
+            tet_pair<KIND>(A, nodes, code, stage + (size_t)t * REC + ROW_SKEW * l);
         else
-            truss_pair<DIM>(A, nodes, code, stage + (size_t)t * REC + l);
+            truss_pair<DIM>(A, nodes, code, stage + (size_t)t * REC + ROW_SKEW * l);
         t += nth;
         if (t < np_a) {  // slices with more pairs than threads (high-valence meshes): header again from L1, not from registers
             const int4* hq = reinterpret_cast<const int4*>(A.hdr + slice);
@@ -259,7 +259,7 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
             const int64_t row = (int64_t)slice * C + lane;
             if (t1 > t0 || !ACCUM) {
                 double acc = 0.0;
-                for (int tt = t0; tt < t1; ++tt) acc += stage[tt * REC + lane + FOFF + r];
+                for (int tt = t0; tt < t1; ++tt) acc += stage[tt * REC + ROW_SKEW * lane + FOFF + r];
                 if (row < A.n_rows_guard) {
                     if (ACCUM) acc += A.F_int[row * DIM + r];
                     A.F_int[row * DIM + r] = acc;

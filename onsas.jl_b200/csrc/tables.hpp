@@ -24,6 +24,7 @@
 namespace onsas {
 
 constexpr int SLICE_ROWS = 8;
+constexpr int ROW_SKEW = 2;  // doubles by which the shared-memory records of consecutive rows of a slice are shifted (bank spreading)
 constexpr int TET_REC = 39;  // shared-memory record of one (row, tet) pair: 4 blocks * 9 + 3 force entries (odd stride)
 constexpr inline int truss_rec(int dim) { return (2 * dim * dim + dim) | 1; }
 
