@@ -24,7 +24,12 @@
 namespace onsas {
 
 constexpr int SLICE_ROWS = 8;
-constexpr int ROW_SKEW = 2;  // doubles by which the shared-memory records of consecutive rows of a slice are shifted (bank spreading)
+constexpr int ROW_SKEW = 2;  // bank spreading of the shared-memory pair records: the records of row l of a slice are shifted by
+// row_skew(l) doubles.  Rows are skewed in PAIRS: on the structured tet mesh (24 pairs per row) every other row boundary
+// falls inside a half-warp of phase A, whose 16 stores stay conflict-free only if both rows have the same skew; a bank
+// model of phase A stores + phase B loads on interior slices gives 1680 wavefronts per slice without skew, 1293 for
+// l, 1161 for 2 l and 1005 for 2 (l / 2) (phase A at its ideal 468).
+constexpr inline int row_skew(int l) { return ROW_SKEW * (l >> 1); }
 constexpr int TET_REC = 39;  // shared-memory record of one (row, tet) pair: 4 blocks * 9 + 3 force entries (odd stride)
 constexpr inline int truss_rec(int dim) { return (2 * dim * dim + dim) | 1; }
 
