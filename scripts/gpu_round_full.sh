@@ -2,7 +2,7 @@
 # One gpurun call: tests, bench (ours + reference arm), launch list, full ncu captures (assembly, streamed CG with the
 # Jacobi and the two-level preconditioner), optional config sweep.
 # usage (from the repo root): gpurun --timeout 1500 -- 'bash scripts/gpu_round_full.sh r13 [sweep]'
-TAG=${1:-r13}
+TAG=${1:-r25}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
