@@ -828,12 +828,14 @@ __device__ __forceinline__ void z_column(int cdof, const double* rho, unsigned m
 }
 template <int BS>
 __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double* E) {
-    extern __shared__ double erow[];  // [CD][nc], then the staged block values [CO_NW][CO_WB][BS*BS]
+    extern __shared__ double erow[];  // [CD][nc]
     constexpr int BB = BS * BS;
     const CoarseArgs& G = A.co;
     const int a = blockIdx.x, tid = threadIdx.x, nc = G.nc, CD = G.cd, warp = tid >> 5, lane = tid & 31;
     const bool rbm = CD > BS;
-    double* sval = erow + (size_t)CD * nc;
+    // the staged block values are a separate (static) array: the apply loop below reads them while it read-modify-writes
+    // erow, and only distinct objects let the compiler hoist those reads over the stores
+    __shared__ double sval[CO_NW * CO_WB * BB];
     __shared__ int s_b[CO_NW][CO_WB];            // aggregate of the block's column (-1: halo column)
     __shared__ unsigned char s_m[CO_NW][CO_WB];  // mask bits of the column node's dofs
     __shared__ double s_rj[CO_NW][CO_WB][3];     // rho of the column node

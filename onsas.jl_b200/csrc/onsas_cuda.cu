@@ -730,7 +730,7 @@ void refresh_coarse(onsas_ctx* c, CgArgs& A) {
     if (c->co.fresh) return;
     const int nc = c->co.nc;
     {
-        const size_t smem = ((size_t)c->co.cd * nc + (size_t)CO_NW * CO_WB * BS * BS) * sizeof(double);
+        const size_t smem = (size_t)c->co.cd * nc * sizeof(double);
         static size_t configured = 0;
         if (smem > configured) {
             CUDA_CHECK(cudaFuncSetAttribute(k_coarse_assemble<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
