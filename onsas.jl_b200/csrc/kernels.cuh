@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double
     for (int k = tid; k < CD * nc; k += CO_THREADS) erow[k] = 0.0;
     __syncthreads();
     // Eight nodes are fetched at a time, one per warp (the four dependent load levels node id -> slice -> column ids
-    // -> aggregate ids overlap across the warps); then the staged blocks are applied in (node, block) order:
+    // -> aggregate ids overlap across the warps); CD*CD threads then apply the staged blocks in (node, block) order:
     // E[a-rows, b-cols] += Z_i^T (M K_ij M) Z_j.
     const int q0 = G.agg_ptr[a], q1 = G.agg_ptr[a + 1];
     for (int qb = q0; qb < q1; qb += CO_NW) {
@@ -883,11 +883,8 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double
             }
             if (rbm && lane < 3 && nb > 0) s_ri[warp][lane] = G.rho[inode * 3 + lane];
             __syncthreads();
-            // apply: warp g owns the target aggregates b with b % CO_NW == g (different targets are different entries of E,
-            // so the warps work side by side); every warp scans the staged blocks in (node, block) order and adds its own,
-            // entry (r, c) per lane (lanes 0..3 take a second entry when CD*CD = 36) -> a fixed summation order per entry
-            for (int e = lane; e < CD * CD; e += 32) {
-                const int r = e / CD, c = e % CD;
+            if (tid < CD * CD) {  // thread (r, c): nodes in ascending order, blocks in storage order -> a fixed summation order
+                const int r = tid / CD, c = tid % CD;
                 for (int w = 0; w < CO_NW; ++w) {
                     const int nbw = s_nb[w];
                     if (nbw == 0) continue;
@@ -895,7 +892,7 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double
                     z_column<BS>(r, s_ri[w], s_mi[w], zi);
                     for (int s = 0; s < nbw; ++s) {
                         const int b = s_b[w][s];
-                        if (b < 0 || b % CO_NW != warp) continue;
+                        if (b < 0) continue;
                         double zj[BS];
                         z_column<BS>(c, s_rj[w][s], s_m[w][s], zj);
                         const double* Kb = sval + ((size_t)w * CO_WB + s) * BB;
