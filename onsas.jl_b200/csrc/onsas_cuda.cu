@@ -378,9 +378,9 @@ void launch_assemble(onsas_ctx* c) {
 // K, F_int and the element records are bitwise what onsas_set_U + onsas_assemble produce (same kernel, same slices).
 void build_host_plan(onsas_ctx* c) {
     auto& H = c->hp;
-    if (H.built && (int)H.node_hi.size() == std::max(1, c->host_chunks)) return;
     const int64_t ns = c->tab.n_slices;
     const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, c->host_chunks), ns));
+    if (H.built && (int)H.node_hi.size() == nch) return;
     // the first and the last range are short (weight 1 against `host_mid_weight` for the others): the first kernel
     // waits for its piece of U and the last piece of F_int leaves after the last kernel -- the two exposed copies
     H.slice0.assign((size_t)nch + 1, 0);

@@ -131,3 +131,61 @@ def test_newton_with_cg_matches_direct(oracle):
     assert rc.iterations == rd.iterations
     _, _, rr, _, _, _ = _uniaxial(oracle, *args, grid=(3, 2, 2), linear="cg")
     assert cases.rel_err(rr.U[-1], rd.U[-1]) < 1e-6
+
+
+def test_two_level_preconditioner_definition(oracle):
+    """The preconditioner the streamed CG applies for precond = 2, restated with numpy on the
+    oracle's K: M^-1 = D^-1 + Z E^-1 Z^T, Z = rigid-body modes (3 translations + 3 rotations about the centroid) of node
+    aggregates restricted to the free dofs, E = Z^T K Z.  It has no counterpart in the reference, so what is pinned here
+    is its definition: M^-1 is symmetric positive definite on the free dofs, PCG with it reaches the direct solution,
+    and it needs fewer iterations than Jacobi and than the translations-only coarse space on the same aggregates."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    m, mesh = cases.box_model(12, 6, 6, mat="neo", jitter=0.1)
+    U = cases.random_U(m, 0.002)
+    asm = oracle.Assembly(m).assemble(U)
+    free = np.asarray(m.free_dofs)
+    K = asm.csr()[free][:, free].tocsr()
+    n = K.shape[0]
+    d = K.diagonal()
+    # aggregates: a 3 x 2 x 2 grid of boxes over the 2 x 1 x 1 domain
+    g = np.minimum((mesh.xyz * [1.5, 2.0, 2.0]).astype(int), [2, 1, 1])
+    agg = g[:, 0] + 3 * (g[:, 1] + 2 * g[:, 2])
+    n_agg = int(agg.max()) + 1
+    cen = np.stack([np.bincount(agg, weights=m.xyz[:, c], minlength=n_agg) for c in range(3)], axis=1) / np.bincount(agg)[:, None]
+
+    def coarse_basis(rotations):
+        cd = 6 if rotations else 3
+        rows, cols, vals = [], [], []
+        for fi, dof in enumerate(free):
+            nd, c = dof // 3, dof % 3
+            rows.append(fi); cols.append(cd * agg[nd] + c); vals.append(1.0)
+            if rotations:
+                rho = m.xyz[nd] - cen[agg[nd]]
+                for k in range(3):                      # u = e_k x rho
+                    u = np.cross(np.eye(3)[k], rho)
+                    rows.append(fi); cols.append(cd * agg[nd] + 3 + k); vals.append(u[c])
+        return sp.csr_matrix((vals, (rows, cols)), shape=(n, cd * n_agg))
+
+    b = np.random.default_rng(8).standard_normal(n)
+    xd = spla.spsolve(K.tocsc(), b)
+
+    def pcg_iters(Minv):
+        it = [0]
+        x, info = spla.cg(K, b, rtol=1e-10, atol=0.0, maxiter=5000, M=Minv, callback=lambda _: it.__setitem__(0, it[0] + 1))
+        assert info == 0 and np.abs(x - xd).max() / np.abs(xd).max() < 1e-7
+        return it[0]
+
+    its = {"jacobi": pcg_iters(spla.LinearOperator((n, n), lambda r: r / d))}
+    for name, rot in (("translations", False), ("rigid_body", True)):
+        Z = coarse_basis(rot)
+        E = (Z.T @ K @ Z).toarray()
+        assert np.allclose(E, E.T, rtol=1e-12, atol=1e-14) and np.linalg.eigvalsh(E).min() > 0
+        Einv = np.linalg.inv(E)
+        Minv = lambda r, Z=Z, Einv=Einv: r / d + Z @ (Einv @ (Z.T @ r))  # noqa: E731
+        # symmetric positive definite: x' M^-1 y = y' M^-1 x and x' M^-1 x > 0 on random vectors
+        rng = np.random.default_rng(1)
+        x1, y1 = rng.standard_normal(n), rng.standard_normal(n)
+        assert x1 @ Minv(y1) == pytest.approx(y1 @ Minv(x1), rel=1e-10) and x1 @ Minv(x1) > 0
+        its[name] = pcg_iters(spla.LinearOperator((n, n), Minv))
+    assert its["rigid_body"] < its["translations"] < its["jacobi"], its
