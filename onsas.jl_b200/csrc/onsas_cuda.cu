@@ -175,13 +175,15 @@ struct onsas_ctx {
     DevBuf<double> co_E, co_w, co_y, co_rowbuf, co_rho;
     // onsas_assemble_host: slice ranges launched one after the other while the copies of U (in) and F_int (out) overlap them
     int64_t asm_first = 0, asm_count = -1;  // slice range of the next assembly launches (-1: all slices)
+    cudaStream_t asm_stream = nullptr;      // stream of the next assembly launches (null: the context's stream)
+    int host_streams = 2;                   // onsas_assemble_host: compute streams the slice ranges alternate on
     int host_chunks = 4, host_mid_weight = 4;
     bool gj_blocked = true;  // coarse inverse by the panel (blocked) Gauss-Jordan kernel; false: one pivot row per grid barrier
     struct HostPlan {
         bool built = false;
         std::vector<int64_t> slice0;   // [n_chunks + 1]
         std::vector<int64_t> node_hi;  // [n_chunks] the chunk's elements touch nodes [0, node_hi) only
-        cudaStream_t s_in = nullptr, s_out = nullptr;
+        cudaStream_t s_in = nullptr, s_out = nullptr, s_k2 = nullptr;
         cudaEvent_t ev_start = nullptr;
         std::vector<cudaEvent_t> ev_in, ev_k;
     } hp;
@@ -264,7 +266,7 @@ void launch_asm_inst(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kern<<<(unsigned)(c->asm_count < 0 ? c->tab.n_slices : c->asm_count), threads, smem, c->stream>>>(A);
+    kern<<<(unsigned)(c->asm_count < 0 ? c->tab.n_slices : c->asm_count), threads, smem, c->asm_stream ? c->asm_stream : c->stream>>>(A);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -276,7 +278,7 @@ void launch_asm_reg(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kern<<<(unsigned)(c->asm_count < 0 ? c->tab.n_slices : c->asm_count), threads, smem, c->stream>>>(A);
+    kern<<<(unsigned)(c->asm_count < 0 ? c->tab.n_slices : c->asm_count), threads, smem, c->asm_stream ? c->asm_stream : c->stream>>>(A);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -412,6 +414,7 @@ void build_host_plan(onsas_ctx* c) {
     if (!H.s_in) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&H.s_in, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&H.s_out, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&H.s_k2, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&H.ev_start, cudaEventDisableTiming));
     }
     while ((int)H.ev_in.size() < nch) {
@@ -444,20 +447,28 @@ void assemble_host(onsas_ctx* c, const double* U, double* F) {
     c->co.fresh = false;
     CUDA_CHECK(cudaEventRecord(H.ev_start, c->stream));  // earlier work on the compute stream may still read U / F_int
     CUDA_CHECK(cudaStreamWaitEvent(H.s_in, H.ev_start, 0));
+    // consecutive ranges alternate between two compute streams: the first CTAs of range k + 1 fill the SMs that the
+    // last wave of range k leaves idle (the ranges write disjoint rows of K, F_int and disjoint element records)
+    const bool two = c->host_streams >= 2 && nch > 1;
+    if (two) CUDA_CHECK(cudaStreamWaitEvent(H.s_k2, H.ev_start, 0));
     int64_t up = 0;  // nodes of U already sent
     for (int k = 0; k < nch; ++k) {
+        cudaStream_t sk = (two && (k & 1)) ? H.s_k2 : c->stream;
         const int64_t hi = k + 1 == nch ? c->n_nodes : H.node_hi[k];  // the last piece takes what no element touches
         if (hi > up) {
             CUDA_CHECK(cudaMemcpyAsync(c->U.p + up * bs, U + up * bs, (size_t)(hi - up) * bs * sizeof(double), cudaMemcpyHostToDevice, H.s_in));
             up = hi;
         }
         CUDA_CHECK(cudaEventRecord(H.ev_in[k], H.s_in));
-        CUDA_CHECK(cudaStreamWaitEvent(c->stream, H.ev_in[k], 0));
+        CUDA_CHECK(cudaStreamWaitEvent(sk, H.ev_in[k], 0));
         c->asm_first = H.slice0[k];
         c->asm_count = H.slice0[k + 1] - H.slice0[k];
+        c->asm_stream = sk;
         if (c->asm_count > 0) launch_assemble_range(c);
-        CUDA_CHECK(cudaEventRecord(H.ev_k[k], c->stream));
+        c->asm_stream = nullptr;
+        CUDA_CHECK(cudaEventRecord(H.ev_k[k], sk));
         CUDA_CHECK(cudaStreamWaitEvent(H.s_out, H.ev_k[k], 0));
+        if (sk != c->stream) CUDA_CHECK(cudaStreamWaitEvent(c->stream, H.ev_k[k], 0));  // later work on the context's stream sees every range
         const int64_t r0 = std::min<int64_t>(H.slice0[k] * SLICE_ROWS, c->n_owned), r1 = std::min<int64_t>(H.slice0[k + 1] * SLICE_ROWS, c->n_owned);
         if (r1 > r0)
             CUDA_CHECK(cudaMemcpyAsync(F + r0 * bs, c->Fint.p + r0 * bs, (size_t)(r1 - r0) * bs * sizeof(double), cudaMemcpyDeviceToHost, H.s_out));
@@ -937,6 +948,7 @@ int32_t onsas_destroy(onsas_ctx* c) {
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->hp.s_in) cudaStreamDestroy(c->hp.s_in);
     if (c->hp.s_out) cudaStreamDestroy(c->hp.s_out);
+    if (c->hp.s_k2) cudaStreamDestroy(c->hp.s_k2);
     if (c->hp.ev_start) cudaEventDestroy(c->hp.ev_start);
     for (auto e : c->hp.ev_in) cudaEventDestroy(e);
     for (auto e : c->hp.ev_k) cudaEventDestroy(e);
@@ -965,6 +977,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_COARSE_RBM: c->coarse_rbm = value != 0; c->co.built = false; c->co.fresh = false; break;
             case ONSAS_OPT_GJ_BLOCKED: c->gj_blocked = value != 0; c->co.fresh = false; break;
             case ONSAS_OPT_HOST_CHUNKS: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "host chunks must be 1..64"); c->host_chunks = (int)value; c->hp.built = false; break;
+            case ONSAS_OPT_HOST_STREAMS: require(value >= 1 && value <= 2, ONSAS_ERR_INVALID_ARG, "host streams must be 1 or 2"); c->host_streams = (int)value; break;
             case ONSAS_OPT_HOST_MID_WEIGHT: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "weight must be 1..64"); c->host_mid_weight = (int)value; c->hp.built = false; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;

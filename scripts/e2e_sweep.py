@@ -17,8 +17,8 @@ hU, hF = bench.pinned(ctx.n_dofs), bench.pinned(ctx.n_dofs)
 hU[:] = U_half
 lib, h = ctx._lib, ctx._h
 K = 50
-for chunks, weight in ((1, 1), (2, 1), (3, 1), (4, 1), (6, 1), (8, 1), (3, 2), (3, 4), (3, 8), (4, 2), (4, 3), (4, 4), (4, 6), (5, 3), (5, 5),
-                       (6, 3), (6, 5), (8, 4)):
+for chunks, weight, streams in ((1, 1, 1), (4, 4, 1), (4, 4, 2), (3, 4, 2), (5, 4, 2), (6, 4, 2), (6, 3, 2), (8, 4, 2), (8, 2, 2), (12, 3, 2), (4, 4, 1), (4, 4, 2)):
+    ctx.set_option(ob._lib.OPT_HOST_STREAMS, streams)
     ctx.set_option(ob._lib.OPT_HOST_CHUNKS, chunks)
     ctx.set_option(ob._lib.OPT_HOST_MID_WEIGHT, weight)
     for _ in range(5):
@@ -27,7 +27,7 @@ for chunks, weight in ((1, 1), (2, 1), (3, 1), (4, 1), (6, 1), (8, 1), (3, 2), (
     for _ in range(K):
         assert lib.onsas_assemble_host(h, hU, hF) == 0
     ms = (time.perf_counter() - t0) * 1e3 / K
-    print(f"chunks={chunks:3d} mid_weight={weight:2d}  {ms:.4f} ms per call  {mesh.n_tets / ms / 1e6:.3f} G tets/s", flush=True)
+    print(f"chunks={chunks:3d} mid_weight={weight:2d} streams={streams}  {ms:.4f} ms per call  {mesh.n_tets / ms / 1e6:.3f} G tets/s", flush=True)
 t0 = time.perf_counter()
 for _ in range(K):
     assert lib.onsas_set_U(h, hU) == 0
@@ -38,6 +38,7 @@ print(f"three calls  {ms:.4f} ms per step  {mesh.n_tets / ms / 1e6:.3f} G tets/s
 # pageable host buffers (no overlap possible): still correct, and how much slower
 pU, pF = np.array(hU), np.empty_like(np.asarray(hF))
 ctx.set_option(ob._lib.OPT_HOST_CHUNKS, 4)
+ctx.set_option(ob._lib.OPT_HOST_MID_WEIGHT, 4)
 t0 = time.perf_counter()
 for _ in range(10):
     assert lib.onsas_assemble_host(h, pU, pF) == 0

@@ -7,5 +7,5 @@ mkdir -p $OUT
 echo "== pytest"; timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest.log; tail -15 $OUT/pytest.log
 echo "== bench"; timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench.json; tail -3 $OUT/bench.err
 echo "== cg probe"; ONSAS_PROF_VERBOSE=1 ONSAS_VERBOSE=1 timeout 300 python scripts/cg_stream_probe.py > $OUT/cg_stream_probe.log 2>&1; grep "prof=\|two-level\|onsas prof" $OUT/cg_stream_probe.log
-echo "== e2e sweep (skipped)"
+echo "== e2e sweep"; timeout 300 python scripts/e2e_sweep.py > $OUT/e2e_sweep.log 2>&1; cat $OUT/e2e_sweep.log
 ls -la $OUT

@@ -438,9 +438,10 @@ def test_assemble_host_is_bitwise_the_three_call_path(ob, oracle, case):
     S0 = ctx.get_stress_strain(ob.FAMILY_TET)
     ref = oracle.Assembly(m).assemble(U)
     assert cases.rel_err(F0, ref.F_int) < 1e-9
-    for chunks in (4, 1, 3, 64):
+    for chunks, streams in ((4, 2), (4, 1), (1, 2), (3, 2), (64, 2), (7, 1)):
         ctx.set_option(ob._lib.OPT_HOST_CHUNKS, chunks)
         ctx.set_option(ob._lib.OPT_HOST_MID_WEIGHT, 1 if chunks == 3 else 3)
+        ctx.set_option(ob._lib.OPT_HOST_STREAMS, streams)
         ctx.set_U(np.zeros_like(U))           # stale state that the call must replace
         ctx.assemble()
         F1 = ctx.assemble_host(U)
