@@ -73,9 +73,9 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_CG_BLOCKS_PER_SM 4 /* persistent CG: resident CTAs per SM the kernel is compiled for: 4, 5 or 6 (default 6); 1-3 shrink the grid */
 #define ONSAS_OPT_CG_PROFILE 5       /* 1 = the persistent CG kernel records per-phase SM-clock cycles (onsas_get_cg_profile) */
 #define ONSAS_OPT_FORCE_MG 6         /* diagnostics: set before onsas_finalize_mesh to run the multi-GPU CG kernel with a single rank */
-#define ONSAS_OPT_HOST_CHUNKS 7      /* onsas_assemble_host: slice ranges the assembly is cut into so that the copies of U and F_int overlap it (default 4; 1 = no overlap) */
+#define ONSAS_OPT_HOST_CHUNKS 7      /* onsas_assemble_host: slice ranges the assembly is cut into so that the copies of U and F_int overlap it (default 12; 1 = no overlap) */
 #define ONSAS_OPT_GJ_BLOCKED 8       /* two-level preconditioner: 1 = coarse inverse by 12-row panels (default), 0 = one pivot row per grid barrier */
-#define ONSAS_OPT_HOST_MID_WEIGHT 9  /* onsas_assemble_host: size of an inner slice range relative to the first / last one (default 4) */
+#define ONSAS_OPT_HOST_MID_WEIGHT 9  /* onsas_assemble_host: size of an inner slice range relative to the first / last one (default 3) */
 #define ONSAS_OPT_COARSE_RBM 10      /* two-level preconditioner in 3D: 1 = rigid-body rotations of every aggregate join the coarse space (default), 0 = translations only */
 #define ONSAS_OPT_HOST_STREAMS 12     /* onsas_assemble_host: compute streams consecutive slice ranges alternate on (1 or 2, default 2) */
 #define ONSAS_OPT_COARSE_FUSED 11    /* two-level preconditioner: 1 = residual update in aggregate order, fused with w = Z^T r (default), 0 = separate pass */

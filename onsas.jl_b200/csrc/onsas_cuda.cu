@@ -177,7 +177,7 @@ struct onsas_ctx {
     int64_t asm_first = 0, asm_count = -1;  // slice range of the next assembly launches (-1: all slices)
     cudaStream_t asm_stream = nullptr;      // stream of the next assembly launches (null: the context's stream)
     int host_streams = 2;                   // onsas_assemble_host: compute streams the slice ranges alternate on
-    int host_chunks = 4, host_mid_weight = 4;
+    int host_chunks = 12, host_mid_weight = 3;  // with two compute streams (sweep: profiles/r29, r30)
     bool gj_blocked = true;  // coarse inverse by the panel (blocked) Gauss-Jordan kernel; false: one pivot row per grid barrier
     struct HostPlan {
         bool built = false;

@@ -17,7 +17,8 @@ hU, hF = bench.pinned(ctx.n_dofs), bench.pinned(ctx.n_dofs)
 hU[:] = U_half
 lib, h = ctx._lib, ctx._h
 K = 50
-for chunks, weight, streams in ((1, 1, 1), (4, 4, 1), (4, 4, 2), (3, 4, 2), (5, 4, 2), (6, 4, 2), (6, 3, 2), (8, 4, 2), (8, 2, 2), (12, 3, 2), (4, 4, 1), (4, 4, 2)):
+for chunks, weight, streams in ((4, 4, 1), (12, 3, 2), (10, 3, 2), (12, 2, 2), (16, 3, 2), (16, 2, 2), (20, 3, 2), (24, 3, 2), (24, 2, 2), (32, 2, 2),
+                                (12, 3, 1), (4, 4, 1), (12, 3, 2), (16, 3, 2), (20, 3, 2), (24, 2, 2)):
     ctx.set_option(ob._lib.OPT_HOST_STREAMS, streams)
     ctx.set_option(ob._lib.OPT_HOST_CHUNKS, chunks)
     ctx.set_option(ob._lib.OPT_HOST_MID_WEIGHT, weight)
