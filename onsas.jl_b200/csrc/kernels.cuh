@@ -208,9 +208,9 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     while (t < np_a) {
         reinterpret_cast<CodeVec*>(scode)[t] = chunk;
         if constexpr (FAMILY == 0)
-            tet_pair<KIND>(A, nodes, code, stage + (size_t)t * REC + row_skew(l));
+            tet_pair<KIND>(A, nodes, code, stage + (size_t)t * REC + row_skew(FAMILY, l));
         else
-            truss_pair<DIM>(A, nodes, code, stage + (size_t)t * REC + row_skew(l));
+            truss_pair<DIM>(A, nodes, code, stage + (size_t)t * REC + row_skew(FAMILY, l));
         t += nth;
         if (t < np_a) {  // slices with more pairs than threads (high-valence meshes): header again from L1, not from registers
             const int4* hq = reinterpret_cast<const int4*>(A.hdr + slice);
@@ -259,7 +259,7 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
             const int64_t row = (int64_t)slice * C + lane;
             if (t1 > t0 || !ACCUM) {
                 double acc = 0.0;
-                for (int tt = t0; tt < t1; ++tt) acc += stage[tt * REC + row_skew(lane) + FOFF + r];
+                for (int tt = t0; tt < t1; ++tt) acc += stage[tt * REC + row_skew(FAMILY, lane) + FOFF + r];
                 if (row < A.n_rows_guard) {
                     if (ACCUM) acc += A.F_int[row * DIM + r];
                     A.F_int[row * DIM + r] = acc;

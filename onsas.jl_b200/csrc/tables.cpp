@@ -177,14 +177,14 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
             uint32_t gbase = (uint32_t)(p0 * F.npe);
             for (size_t k = 0; k <= (size_t)w * C; ++k) F.cptr[base * C + k] = gbase + cnt[k];
             std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
-            // record of local pair lp (row l) sits at lp*rec + row_skew(l): the skew keeps the rows of a structured mesh
+            // record of local pair lp (row l) sits at lp*rec + row_skew(family, l): the skew keeps the rows of a structured mesh
             // (24 pairs * 39 doubles = 8 mod 16 bank pairs apart) on different shared-memory banks (tables.hpp)
             for (int64_t i = r0; i < r1; ++i)
                 for (int64_t p = F.pair_ptr[i]; p < F.pair_ptr[i + 1]; ++p) {
                     const int32_t lp = (int32_t)(p - p0);
                     for (int b = 0; b < F.npe; ++b) {
                         uint16_t slot = slot_of[(size_t)lp * F.npe + b];
-                        F.ccode[gbase + fill[slot]++] = (uint16_t)(lp * F.rec + row_skew((int)(i - r0)) + b * BB);
+                        F.ccode[gbase + fill[slot]++] = (uint16_t)(lp * F.rec + row_skew(f, (int)(i - r0)) + b * BB);
                     }
                 }
         }

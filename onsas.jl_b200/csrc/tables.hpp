@@ -29,7 +29,9 @@ constexpr int ROW_SKEW = 2;  // bank spreading of the shared-memory pair records
 // falls inside a half-warp of phase A, whose 16 stores stay conflict-free only if both rows have the same skew; a bank
 // model of phase A stores + phase B loads on interior slices gives 1680 wavefronts per slice without skew, 1293 for
 // l, 1161 for 2 l and 1005 for 2 (l / 2) (phase A at its ideal 468).
-constexpr inline int row_skew(int l) { return ROW_SKEW * (l >> 1); }
+// The truss records (21 doubles, 14 pairs per row on the braced lattice) need none: the same model gives 294 wavefronts
+// per slice without skew against 423 / 432 for l / 2 (l / 2).  family: 0 = tets, 1 = trusses.
+constexpr inline int row_skew(int family, int l) { return family == 0 ? ROW_SKEW * (l >> 1) : 0; }
 constexpr int TET_REC = 39;  // shared-memory record of one (row, tet) pair: 4 blocks * 9 + 3 force entries (odd stride)
 constexpr inline int truss_rec(int dim) { return (2 * dim * dim + dim) | 1; }
 

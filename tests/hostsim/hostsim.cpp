@@ -176,7 +176,7 @@ int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const i
                     const int32_t* nd = &F.pair_nodes[(p0 + tt) * NPE];
                     int lrow = 0;
                     for (int k = 1; k < C; ++k) lrow += (tt >= H.row_off[k]) ? 1 : 0;
-                    double* rec = stage.data() + (size_t)tt * REC + row_skew(lrow);
+                    double* rec = stage.data() + (size_t)tt * REC + row_skew(fam, lrow);
                     if (fam == 0) {
                         const int64_t e = code >> 2;
                         const int a = code & 3;
@@ -232,7 +232,7 @@ int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const i
                         const int64_t row = sl * C + lane;
                         if (t1 > t0 || !ACCUM) {
                             double acc = 0.0;
-                            for (int tt = t0; tt < t1; ++tt) acc += stage[(size_t)tt * REC + row_skew(lane) + FOFF + r];
+                            for (int tt = t0; tt < t1; ++tt) acc += stage[(size_t)tt * REC + row_skew(fam, lane) + FOFF + r];
                             if (row < t.n_rows) {
                                 if (ACCUM) acc += m->Fint[row * dim + r];
                                 m->Fint[row * dim + r] = acc;
