@@ -77,7 +77,6 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_GJ_BLOCKED 8       /* two-level preconditioner: 1 = coarse inverse by 12-row panels (default), 0 = one pivot row per grid barrier */
 #define ONSAS_OPT_HOST_MID_WEIGHT 9  /* onsas_assemble_host: size of an inner slice range relative to the first / last one (default 3) */
 #define ONSAS_OPT_COARSE_RBM 10      /* two-level preconditioner in 3D: 1 = rigid-body rotations of every aggregate join the coarse space (default), 0 = translations only */
-#define ONSAS_OPT_ASM_PACKED 13       /* tet assembly gathers X and U from 32-byte node records refreshed before every assembly (default 0) */
 #define ONSAS_OPT_HOST_STREAMS 12     /* onsas_assemble_host: compute streams consecutive slice ranges alternate on (1 or 2, default 2) */
 #define ONSAS_OPT_COARSE_FUSED 11    /* two-level preconditioner: 1 = residual update in aggregate order, fused with w = Z^T r (default), 0 = separate pass */
 

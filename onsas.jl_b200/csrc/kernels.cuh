@@ -54,8 +54,6 @@ struct AsmArgs {
     int max_pairs;     // sizes of the shared-memory regions
     int max_width;
     int64_t n_rows_guard;  // number of owned rows (the last slice may be partial)
-    const double* X4;      // optional: X and U as 32-byte node records (4 doubles per node); null = gather from X / U
-    const double* U4;
     int slice0;            // first slice of this launch (CTA b works on slice slice0 + b): onsas_assemble_host launches ranges
 };
 
@@ -65,26 +63,14 @@ __device__ __forceinline__ void tet_pair(const AsmArgs& A, const int4 cn, int32_
     const int a = code & 3;
     const int nd[4] = {cn.x, cn.y, cn.z, cn.w};
     double X[4][3], U[4][3];
-    if (A.U4 != nullptr) {  // node records: one 128-bit + one 64-bit load per node and field (16 requests instead of 24)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double* xp = A.X4 + 4 * (int64_t)nd[k];
-            const double* up = A.U4 + 4 * (int64_t)nd[k];
-            const double2 xa = __ldg(reinterpret_cast<const double2*>(xp));
-            const double2 ua = __ldg(reinterpret_cast<const double2*>(up));
-            X[k][0] = xa.x; X[k][1] = xa.y; X[k][2] = __ldg(xp + 2);
-            U[k][0] = ua.x; U[k][1] = ua.y; U[k][2] = __ldg(up + 2);
-        }
-    } else {
+    for (int k = 0; k < 4; ++k) {
+        const double* xp = A.X + 3 * (int64_t)nd[k];
+        const double* up = A.U + 3 * (int64_t)nd[k];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double* xp = A.X + 3 * (int64_t)nd[k];
-            const double* up = A.U + 3 * (int64_t)nd[k];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                X[k][c] = __ldg(xp + c);
-                U[k][c] = __ldg(up + c);
-            }
+        for (int c = 0; c < 3; ++c) {
+            X[k][c] = __ldg(xp + c);
+            U[k][c] = __ldg(up + c);
         }
     }
     const int m = A.mat_id ? __ldg(A.mat_id + e) : 0;
@@ -1908,14 +1894,6 @@ __global__ void k_pack(const double* __restrict__ v, const int32_t* __restrict__
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_send * bs) return;
     buf[i] = v[(int64_t)send_nodes[i / bs] * bs + (i % bs)];
-}
-
-// 3 doubles per node -> 32-byte node records (the 4th double is never read)
-__global__ void k_pack4(const double* __restrict__ src, double* __restrict__ dst, int64_t first, int64_t count) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= count * 3) return;
-    const int64_t nd = first + i / 3;
-    dst[4 * nd + i % 3] = src[3 * nd + i % 3];
 }
 
 __global__ void k_fill(double* v, int64_t n, double a) {

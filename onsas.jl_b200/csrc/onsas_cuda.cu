@@ -144,8 +144,6 @@ struct onsas_ctx {
     MeshTables tab;
 
     // device
-    DevBuf<double> X4, U4;  // optional 32-byte node records of X and U for the tet assembly (asm_packed)
-    bool asm_packed = false;
     DevBuf<double> X, U, Fext, Fint, val, x, r, p, p_pad, Ap, dinv, rhs, partials, red, tet_out, truss_out, area, mat_params;
     DevBuf<int32_t> tets, tet_mat, trusses, truss_mat, mat_kind, col, diag_slot, pair_code[2], pair_nodes[2], send_nodes;
     DevBuf<int64_t> slice_ptr;
@@ -314,9 +312,6 @@ AsmArgs make_asm_args(onsas_ctx* c, int family) {
     A.elem_out = family == 0 ? c->tet_out.p : c->truss_out.p;
     A.err_flag = c->err_flag.p;
     A.slice0 = (int)c->asm_first;
-    const bool packed = c->asm_packed && family == 0 && c->dim == 3 && c->X4.p != nullptr;
-    A.X4 = packed ? c->X4.p : nullptr;
-    A.U4 = packed ? c->U4.p : nullptr;
     return A;
 }
 
@@ -328,13 +323,6 @@ int round_threads(int pairs) {
 void halo_exchange(onsas_ctx* c, double* v, int gate);
 void download(onsas_ctx* c, double* h, const double* d, size_t n);
 void check_deferred(onsas_ctx* c);
-
-// refreshes the 32-byte node records of U for nodes [first, first + count) (no-op unless the packed gathers are on)
-void pack_U(onsas_ctx* c, int64_t first, int64_t count, cudaStream_t s) {
-    if (!(c->asm_packed && c->n_tets > 0 && c->dim == 3 && c->U4.p != nullptr) || count <= 0) return;
-    k_pack4<<<(unsigned)((count * 3 + 255) / 256), 256, 0, s>>>(c->U.p, c->U4.p, first, count);
-    CUDA_CHECK(cudaGetLastError());
-}
 
 // the assembly kernels of every element family over the slice range [c->asm_first, c->asm_first + c->asm_count)
 void launch_assemble_range(onsas_ctx* c) {
@@ -378,7 +366,6 @@ void launch_assemble(onsas_ctx* c) {
     require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
     c->co.fresh = false;  // K is about to change: the coarse inverse of the two-level preconditioner is stale
     if (c->n_ranks > 1) halo_exchange(c, c->U.p, 0);
-    pack_U(c, 0, c->n_nodes, c->stream);
     c->asm_first = 0;
     c->asm_count = -1;
     launch_assemble_range(c);
@@ -470,7 +457,6 @@ void assemble_host(onsas_ctx* c, const double* U, double* F) {
         const int64_t hi = k + 1 == nch ? c->n_nodes : H.node_hi[k];  // the last piece takes what no element touches
         if (hi > up) {
             CUDA_CHECK(cudaMemcpyAsync(c->U.p + up * bs, U + up * bs, (size_t)(hi - up) * bs * sizeof(double), cudaMemcpyHostToDevice, H.s_in));
-            pack_U(c, up, hi - up, H.s_in);
             up = hi;
         }
         CUDA_CHECK(cudaEventRecord(H.ev_in[k], H.s_in));
@@ -920,7 +906,6 @@ int32_t onsas_create(int32_t device, onsas_ctx** out) {
         CUDA_CHECK(cudaSetDevice(device));
         c = new onsas_ctx();
         c->device = device;
-        if (const char* ev = getenv("ONSAS_ASM_PACKED")) c->asm_packed = atoi(ev) != 0;
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         c->n_sm = prop.multiProcessorCount;
@@ -992,7 +977,6 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_COARSE_RBM: c->coarse_rbm = value != 0; c->co.built = false; c->co.fresh = false; break;
             case ONSAS_OPT_GJ_BLOCKED: c->gj_blocked = value != 0; c->co.fresh = false; break;
             case ONSAS_OPT_HOST_CHUNKS: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "host chunks must be 1..64"); c->host_chunks = (int)value; c->hp.built = false; break;
-            case ONSAS_OPT_ASM_PACKED: c->asm_packed = value != 0; break;
             case ONSAS_OPT_HOST_STREAMS: require(value >= 1 && value <= 2, ONSAS_ERR_INVALID_ARG, "host streams must be 1 or 2"); c->host_streams = (int)value; break;
             case ONSAS_OPT_HOST_MID_WEIGHT: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "weight must be 1..64"); c->host_mid_weight = (int)value; c->hp.built = false; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
@@ -1156,14 +1140,6 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         cudaStream_t s = c->stream;
         const size_t nl = (size_t)c->n_local_dofs(), no = (size_t)c->n_own_dofs();
         c->X.upload(c->h_xyz, s);
-        if (c->dim == 3 && c->n_tets > 0) {  // node records for the packed gathers (ONSAS_OPT_ASM_PACKED)
-            c->X4.alloc((size_t)c->n_nodes * 4);
-            c->U4.alloc((size_t)c->n_nodes * 4);
-            c->X4.zero(s);
-            c->U4.zero(s);
-            k_pack4<<<(unsigned)((c->n_nodes * 3 + 255) / 256), 256, 0, s>>>(c->X.p, c->X4.p, 0, c->n_nodes);
-            CUDA_CHECK(cudaGetLastError());
-        }
         c->mat_kind.upload(c->h_mat_kind, s);
         c->mat_params.upload(c->h_mat_params, s);
         c->tets.upload(c->h_tets, s);
