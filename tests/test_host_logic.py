@@ -395,3 +395,24 @@ def test_write_vtk_from_flat_solution(ob, tmp_path):
     a2, m2 = vtk.read_vtu(p2)
     assert m2["n_cells"] == 2 and a2["types"].tolist() == [3, 3] and a2["offsets"].tolist() == [2, 4]
     assert a2["Points"].shape == (3, 3) and np.all(a2["Points"][:, 2] == 0)
+
+
+# ----------------------------------------------------------------------------- bench.py contract (reference arm runs on CPU)
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the restated CPU algorithm on the host cores) prints exactly one JSON line with the
+    contract's keys; the other ranks of a torchrun launch print nothing."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cells", "6", "--steps", "2", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="0")).stdout.strip().splitlines()
+    assert len(out) == 1
+    d = json.loads(out[0])
+    assert d["impl"] == "reference" and d["metric"] == "tet_fint_Kt_assembled_elements_per_s" and d["unit"] == "tets/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 2 and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "tets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+    silent = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1"))
+    assert silent.returncode == 0 and silent.stdout.strip() == ""
