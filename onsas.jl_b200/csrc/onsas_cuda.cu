@@ -383,34 +383,7 @@ void build_host_plan(onsas_ctx* c) {
     const int64_t ns = c->tab.n_slices;
     const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, c->host_chunks), ns));
     if (H.built && (int)H.node_hi.size() == nch) return;
-    // the first and the last range are short (weight 1 against `host_mid_weight` for the others): the first kernel
-    // waits for its piece of U and the last piece of F_int leaves after the last kernel -- the two exposed copies
-    H.slice0.assign((size_t)nch + 1, 0);
-    {
-        const int wm = std::max(1, c->host_mid_weight);
-        const int64_t wt = nch <= 2 ? nch : 2 + (int64_t)(nch - 2) * wm;
-        int64_t acc = 0;
-        for (int k = 0; k < nch; ++k) {
-            acc += (nch <= 2 || k == 0 || k == nch - 1) ? 1 : wm;
-            H.slice0[k + 1] = ns * acc / wt;
-        }
-    }
-    H.node_hi.assign((size_t)nch, 0);
-    for (int k = 0; k < nch; ++k) {
-        int64_t hi = std::min<int64_t>(H.slice0[k + 1] * SLICE_ROWS, c->n_nodes);  // the rows themselves
-        for (int f = 0; f < 2; ++f) {
-            const FamilyTables& T = c->tab.fam[f];
-            if (T.n_elem == 0 || T.hdr.empty() || H.slice0[k + 1] == H.slice0[k]) continue;
-            const SliceHdr& h0 = T.hdr[(size_t)H.slice0[k]];
-            const SliceHdr& h1 = T.hdr[(size_t)H.slice0[k + 1] - 1];
-            const int64_t q0 = h0.pair_base * T.npe, q1 = (h1.pair_base + h1.n_pairs) * T.npe;
-            int32_t mx = -1;
-#pragma omp parallel for reduction(max : mx)
-            for (int64_t q = q0; q < q1; ++q) mx = std::max(mx, T.pair_nodes[(size_t)q]);
-            hi = std::max<int64_t>(hi, (int64_t)mx + 1);
-        }
-        H.node_hi[k] = std::max(hi, k > 0 ? H.node_hi[k - 1] : 0);
-    }
+    host_range_plan(c->tab, c->host_chunks, c->host_mid_weight, H.slice0, H.node_hi);  // tables.cpp (CPU-tested)
     if (!H.s_in) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&H.s_in, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&H.s_out, cudaStreamNonBlocking));

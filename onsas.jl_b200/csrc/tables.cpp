@@ -231,4 +231,35 @@ void bsell_to_csr_values(const MeshTables& t, const double* val, double* csr_val
     }
 }
 
+void host_range_plan(const MeshTables& t, int chunks, int mid_weight, std::vector<int64_t>& slice0, std::vector<int64_t>& node_hi) {
+    const int64_t ns = t.n_slices;
+    const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, chunks), ns));
+    // the first and the last range are short: the first kernel waits for its piece of U and the last piece of F_int
+    // leaves after the last kernel -- the two exposed copies
+    slice0.assign((size_t)nch + 1, 0);
+    const int wm = std::max(1, mid_weight);
+    const int64_t wt = nch <= 2 ? nch : 2 + (int64_t)(nch - 2) * wm;
+    int64_t acc = 0;
+    for (int k = 0; k < nch; ++k) {
+        acc += (nch <= 2 || k == 0 || k == nch - 1) ? 1 : wm;
+        slice0[k + 1] = ns * acc / wt;
+    }
+    node_hi.assign((size_t)nch, 0);
+    for (int k = 0; k < nch; ++k) {
+        int64_t hi = std::min<int64_t>(slice0[k + 1] * SLICE_ROWS, t.n_nodes);  // the rows themselves
+        for (int f = 0; f < 2; ++f) {
+            const FamilyTables& T = t.fam[f];
+            if (T.n_elem == 0 || T.hdr.empty() || slice0[k + 1] == slice0[k]) continue;
+            const SliceHdr& h0 = T.hdr[(size_t)slice0[k]];
+            const SliceHdr& h1 = T.hdr[(size_t)slice0[k + 1] - 1];
+            const int64_t q0 = h0.pair_base * T.npe, q1 = (h1.pair_base + h1.n_pairs) * T.npe;
+            int32_t mx = -1;
+#pragma omp parallel for reduction(max : mx)
+            for (int64_t q = q0; q < q1; ++q) mx = std::max(mx, T.pair_nodes[(size_t)q]);
+            hi = std::max<int64_t>(hi, (int64_t)mx + 1);
+        }
+        node_hi[k] = std::max(hi, k > 0 ? node_hi[k - 1] : 0);
+    }
+}
+
 }  // namespace onsas

@@ -145,6 +145,15 @@ int64_t hs_stat(HsModel* m, int which) {
     }
 }
 
+// slice ranges of the pipelined host-buffer assembly (tables.cpp::host_range_plan); returns the number of ranges
+int hs_host_plan(HsModel* m, int chunks, int mid_weight, int64_t* slice0 /*[chunks+1]*/, int64_t* node_hi /*[chunks]*/) {
+    std::vector<int64_t> s0, hi;
+    host_range_plan(m->tab, chunks, mid_weight, s0, hi);
+    for (size_t k = 0; k < s0.size(); ++k) slice0[k] = s0[k];
+    for (size_t k = 0; k < hi.size(); ++k) node_hi[k] = hi[k];
+    return (int)hi.size();
+}
+
 // walk k_assemble for both families at displacement Uv; `threads` emulates blockDim.x
 int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const int32_t* trusses, const int32_t* truss_mat,
                 const double* area, int strain_model, const int32_t* kind, const double* params, const double* xyz,

@@ -21,6 +21,8 @@ hs.hs_nnz.restype = C.c_int64
 hs.hs_nnz.argtypes = [_vp]
 hs.hs_stat.restype = C.c_int64
 hs.hs_stat.argtypes = [_vp, C.c_int]
+hs.hs_host_plan.restype = C.c_int
+hs.hs_host_plan.argtypes = [_vp, C.c_int, C.c_int, _lp, _lp]
 hs.hs_assemble.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _ip, _dp, _dp, _dp, C.c_int]
 hs.hs_get.argtypes = [_vp, _lp, _ip, _dp, _dp, _dp, _dp]
 hs.hs_spmv.argtypes = [_vp, _u8, _dp, _dp]
@@ -52,6 +54,12 @@ class HostSim:
 
     def stats(self):
         return [hs.hs_stat(self.h, i) for i in range(5)]
+
+    def host_plan(self, chunks, mid_weight):
+        """(slice0 [n+1], node_hi [n]) of onsas_assemble_host's slice ranges."""
+        s0, hi = np.zeros(chunks + 1, np.int64), np.zeros(chunks, np.int64)
+        n = hs.hs_host_plan(self.h, chunks, mid_weight, s0, hi)
+        return s0[:n + 1], hi[:n]
 
     def assemble(self, U, threads=192):
         m = self.m

@@ -109,3 +109,40 @@ def test_table_limits(hostsim, oracle):
     bad = oracle.FlatModel(xyz=m.xyz, tets=np.array([[0, 1, 2, 999]], np.int32), free_dofs=[0])
     with pytest.raises(ValueError):
         hostsim.HostSim(bad)
+
+
+def test_host_range_plan_of_the_pipelined_assembly(hostsim, oracle):
+    """onsas_assemble_host sends U as growing prefixes: range k may start once nodes [0, node_hi[k]) have arrived.  The plan
+    must cover every slice once, be monotone, and node_hi[k] must bound every node touched by the elements that the
+    slices of range k evaluate (all elements incident to their rows); a banded numbering pipelines (node_hi grows with
+    k), a random numbering needs (almost) all of U at once."""
+    m, mesh = cases.box_model(12, 6, 6, mat="svk")
+    rng = np.random.default_rng(5)
+    n = m.xyz.shape[0]
+    perm = rng.permutation(n)
+    inv = np.empty(n, np.int64)
+    inv[perm] = np.arange(n)
+    shuffled = oracle.FlatModel(xyz=m.xyz[inv], tets=perm[m.tets].astype(np.int32), mat_kind=m.mat_kind, mat_params=m.mat_params,
+                                free_dofs=np.sort(perm[m.free_dofs // 3] * 3 + m.free_dofs % 3))
+    for model, banded in ((m, True), (shuffled, False)):
+        sim = hostsim.HostSim(model)
+        n_slices = sim.stats()[0]
+        tets = np.asarray(model.tets)
+        for chunks, weight in ((1, 1), (2, 3), (4, 4), (12, 3), (1000, 2)):
+            s0, hi = sim.host_plan(chunks, weight)
+            assert s0[0] == 0 and s0[-1] == n_slices and np.all(np.diff(s0) >= 0) and len(hi) == len(s0) - 1
+            assert len(hi) == min(chunks, n_slices) and np.all(np.diff(hi) >= 0) and hi[-1] <= n
+            for k in range(len(hi)):
+                rows = np.arange(8 * s0[k], min(8 * s0[k + 1], n))
+                if len(rows) == 0:
+                    continue
+                touched = tets[np.isin(tets, rows).any(axis=1)]            # elements incident to the range's rows
+                need = max(int(touched.max()) + 1 if len(touched) else 0, int(rows.max()) + 1)
+                assert hi[k] >= need and (k > 0 or hi[k] == need)
+            if chunks == 12:
+                inner = np.diff(s0)[1:-1]
+                assert np.diff(s0)[0] <= inner.min() and np.diff(s0)[-1] <= inner.min() + 1   # short first / last range
+                if banded:
+                    assert hi[0] < 0.35 * n          # the first kernel starts after a small prefix of U
+                else:
+                    assert hi[0] > 0.9 * n           # random numbering: (almost) everything first
