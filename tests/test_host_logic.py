@@ -416,3 +416,22 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert "workload" in d["config"]
     silent = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1"))
     assert silent.returncode == 0 and silent.stdout.strip() == ""
+
+
+# ----------------------------------------------------------------------------- documentation stays in step with the tree
+
+def test_design_md_cites_tests_and_profiles_that_exist():
+    """Every `test_…` name and every `profiles/…` file that DESIGN.md / README.md cite exists in the tree."""
+    import glob
+    text = open(os.path.join(ROOT, "DESIGN.md"), encoding="utf-8").read() + open(os.path.join(ROOT, "README.md"), encoding="utf-8").read()
+    defined = set()
+    for path in glob.glob(os.path.join(ROOT, "tests", "test_*.py")):
+        defined |= set(re.findall(r"^def (test_\w+)", open(path, encoding="utf-8").read(), flags=re.M))
+        defined.add(os.path.basename(path)[:-3])
+    cited = set(re.findall(r"`(?:tests/)?(?:test_\w+\.py::)?(test_\w+?)(?:\[[^\]]*\])?(?:\.py)?`", text))
+    missing = sorted(t for t in cited if t not in defined and not any(d.startswith(t.rstrip("_…")) for d in defined))
+    assert not missing, missing
+    for rel in set(re.findall(r"`(profiles/r\d+/[\w./-]+\.\w+)`", text)):
+        assert os.path.exists(os.path.join(ROOT, rel)), rel
+    for rel in set(re.findall(r"`(profiles/r\d+)`", text)):
+        assert os.path.isdir(os.path.join(ROOT, rel)), rel
