@@ -42,6 +42,7 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_ERR_UNSUPPORTED 5
 #define ONSAS_ERR_COMM 6
 #define ONSAS_ERR_ALLOC 7
+#define ONSAS_ERR_BREAKDOWN 8 /* the CG residual became non-finite (NaN / Inf in K, F_ext or U): the solve stops at once */
 
 /* material kinds: parameters (p0, p1) */
 #define ONSAS_MAT_SVK 0        /* (lambda, G)   Materials/SVKMaterial.jl:25-54 */

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libonsas_cuda.so")
 
 # status codes (include/onsas_cuda.h)
-OK, ERR_INVALID_ARG, ERR_NEGATIVE_VOLUME, ERR_CUDA, ERR_NOT_READY, ERR_UNSUPPORTED, ERR_COMM, ERR_ALLOC = range(8)
+OK, ERR_INVALID_ARG, ERR_NEGATIVE_VOLUME, ERR_CUDA, ERR_NOT_READY, ERR_UNSUPPORTED, ERR_COMM, ERR_ALLOC, ERR_BREAKDOWN = range(9)
 MAT_SVK, MAT_NEOHOOKEAN, MAT_ISOLINEAR = 0, 1, 2
 STRAIN_ROTATED_ENGINEERING, STRAIN_GREEN = 0, 1
 FAMILY_TET, FAMILY_TRUSS = 0, 1

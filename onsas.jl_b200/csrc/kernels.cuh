@@ -37,10 +37,11 @@ constexpr int C = SLICE_ROWS;
 struct AsmArgs {
     const double* X;  // dim per node
     const double* U;  // dim per node
-    const SliceHdr* hdr;        // one 48-byte header per slice
-    const int32_t* pair_nodes;  // npe node ids per pair
-    const int32_t* pair_code;   // e*npe + a per pair
-    const int32_t* mat_id;      // may be null (all elements use material 0)
+    const SliceHdr* hdr;         // one 48-byte header per slice
+    const int32_t* snodes;       // per slice: the distinct nodes its elements touch (ascending)
+    const uint16_t* pair_lnodes; // npe indices into the slice's node list per pair (bit 15 of the first: writes the element record)
+    const int32_t* pair_code;    // e*npe + a per pair
+    const int32_t* mat_id;       // may be null (all elements use material 0)
     const int32_t* mat_kind;
     const double* mat_params;  // 2 per material
     const double* area;        // trusses
@@ -53,24 +54,29 @@ struct AsmArgs {
     int* err_flag;     // set to 1 when an element has non-positive volume
     int max_pairs;     // sizes of the shared-memory regions
     int max_width;
+    int max_snodes;
     int64_t n_rows_guard;  // number of owned rows (the last slice may be partial)
     int slice0;            // first slice of this launch (CTA b works on slice slice0 + b): onsas_assemble_host launches ranges
 };
 
+// shared-memory record of one staged node: X then U, padded to an odd number of doubles (16 consecutive records sit on 16
+// different bank pairs, so a half-warp of 8-byte reads to distinct nodes of a run is conflict-free)
+__host__ __device__ constexpr int snode_rec(int dim) { return 2 * dim + 1; }
+
 template <int KIND>
-__device__ __forceinline__ void tet_pair(const AsmArgs& A, const int4 cn, int32_t code, double* rec) {
+__device__ __forceinline__ void tet_pair(const AsmArgs& A, const double* sn, const uint2 ln, int32_t code, double* rec) {
     const int64_t e = code >> 2;
     const int a = code & 3;
-    const int nd[4] = {cn.x, cn.y, cn.z, cn.w};
+    const unsigned li[4] = {ln.x & 0x7fffu, ln.x >> 16, ln.y & 0xffffu, ln.y >> 16};
+    const bool writer = (ln.x & 0x8000u) != 0;
     double X[4][3], U[4][3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const double* xp = A.X + 3 * (int64_t)nd[k];
-        const double* up = A.U + 3 * (int64_t)nd[k];
+        const double* np = sn + li[k] * snode_rec(3);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            X[k][c] = __ldg(xp + c);
-            U[k][c] = __ldg(up + c);
+            X[k][c] = np[c];
+            U[k][c] = np[3 + c];
         }
     }
     const int m = A.mat_id ? __ldg(A.mat_id + e) : 0;
@@ -84,7 +90,7 @@ __device__ __forceinline__ void tet_pair(const AsmArgs& A, const int4 cn, int32_
         TetCommon c;
         tet_common<K>(X, U, p0, p1, c);
         vol = c.vol;
-        if (a == 0) {  // the owner of the element's first node also writes its stress / strain record
+        if (writer) {  // the pair of the element's first owned node also writes its stress / strain record
             double out[16];
             tet_stress_out<K>(c, p0, p1, out);
             double2* o = reinterpret_cast<double2*>(A.elem_out + 16 * e);
@@ -103,16 +109,19 @@ __device__ __forceinline__ void tet_pair(const AsmArgs& A, const int4 cn, int32_
 }
 
 template <int DIM>
-__device__ __forceinline__ void truss_pair(const AsmArgs& A, const int2 cn, int32_t code, double* rec) {
+__device__ __forceinline__ void truss_pair(const AsmArgs& A, const double* sn, const uint32_t ln, int32_t code, double* rec) {
     const int64_t e = code >> 1;
     const int a = code & 1;
+    const double* n0 = sn + (ln & 0x7fffu) * snode_rec(DIM);
+    const double* n1 = sn + (ln >> 16) * snode_rec(DIM);
+    const bool writer = (ln & 0x8000u) != 0;
     double X[2][3], U[2][3];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) {
-        X[0][c] = __ldg(A.X + DIM * (int64_t)cn.x + c);
-        X[1][c] = __ldg(A.X + DIM * (int64_t)cn.y + c);
-        U[0][c] = __ldg(A.U + DIM * (int64_t)cn.x + c);
-        U[1][c] = __ldg(A.U + DIM * (int64_t)cn.y + c);
+        X[0][c] = n0[c];
+        X[1][c] = n1[c];
+        U[0][c] = n0[DIM + c];
+        U[1][c] = n1[DIM + c];
     }
     const int m = A.mat_id ? __ldg(A.mat_id + e) : 0;
     const double Emod = truss_modulus(__ldg(A.mat_kind + m), __ldg(A.mat_params + 2 * m), __ldg(A.mat_params + 2 * m + 1));
@@ -124,22 +133,26 @@ __device__ __forceinline__ void truss_pair(const AsmArgs& A, const int2 cn, int3
         for (int k = 0; k < DIM * DIM; ++k) rec[b * DIM * DIM + k] = blk[b][k];
 #pragma unroll
     for (int r = 0; r < DIM; ++r) rec[2 * DIM * DIM + r] = f[r];
-    if (a == 0) {
+    if (writer) {
         A.elem_out[2 * e] = se[0];
         A.elem_out[2 * e + 1] = se[1];
     }
 }
 
-// shared memory of one assembly CTA: [stage: max_pairs*REC doubles][scode: max_pairs*NPE u16][scp: max_width*C+1 u16]
-__host__ __device__ constexpr size_t asm_smem_bytes(int max_pairs, int max_width, int rec, int npe) {
-    return ((size_t)max_pairs * rec + ROW_SKEW * SLICE_ROWS) * 8 + (((size_t)max_pairs * npe * 2 + ((size_t)max_width * SLICE_ROWS + 1) * 2 + 15) / 16) * 16;
+// shared memory of one assembly CTA:
+// [stage: max_pairs*REC (+ skew) doubles][nodes: max_snodes * (2 dim + 1) doubles][scode: max_pairs*NPE u16][scp: max_width*C+1 u16]
+__host__ __device__ constexpr size_t asm_smem_bytes(int max_pairs, int max_width, int max_snodes, int rec, int npe, int dim) {
+    return ((size_t)max_pairs * rec + ROW_SKEW * SLICE_ROWS + (size_t)max_snodes * snode_rec(dim)) * 8 +
+           (((size_t)max_pairs * npe * 2 + ((size_t)max_width * SLICE_ROWS + 1) * 2 + 15) / 16) * 16;
 }
 
 // One CTA per BSELL slice (8 block rows).
-//  Phase A: one thread per (row, element) pair.  Loads are arranged in three dependent levels only:
-//           slice header -> {pair node ids, pair code, contribution codes, slot ranges} -> {X, U gathers};
-//           the thread evaluates block-row a of K_e and f_a straight into its shared-memory record and
-//           stages the slice's contribution lists in shared memory on the way.
+//  Staging: the slice's node list (the distinct nodes its elements touch, ascending ids -> runs of consecutive nodes) is read
+//           once and X, U of those nodes land in shared memory with coalesced loads; the pairs address them by 16-bit index.
+//           Four dependent load levels: slice header -> {node list, pair records, contribution codes, slot ranges} ->
+//           {X, U of the listed nodes} -> barrier.
+//  Phase A: one thread per (row, element) pair: evaluates block-row a of K_e and f_a from the staged nodes straight into
+//           its shared-memory record and stages the slice's contribution lists in shared memory on the way.
 //  Phase B: one thread per (block slot, block row r): sums the DIM entries of that row of the block over the
 //           slot's contributions in ascending element order (register accumulators, indices from shared memory)
 //           and writes K exactly once in 64-byte segments; the last C*DIM items do the same for F_int.
@@ -151,7 +164,9 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     constexpr int NPE = FAMILY == 0 ? 4 : 2;
     constexpr int REC = FAMILY == 0 ? TET_REC : truss_rec(DIM);
     constexpr int FOFF = NPE * BB;
-    uint16_t* scode = reinterpret_cast<uint16_t*>(stage + (size_t)A.max_pairs * REC + ROW_SKEW * C);
+    constexpr int NS = snode_rec(DIM);
+    double* const snd = stage + (size_t)A.max_pairs * REC + ROW_SKEW * C;
+    uint16_t* scode = reinterpret_cast<uint16_t*>(snd + (size_t)A.max_snodes * NS);
     uint16_t* scp = scode + (size_t)A.max_pairs * NPE;
     const int tid = threadIdx.x, nth = blockDim.x;
 
@@ -162,6 +177,8 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     const int64_t p0 = (int64_t)(uint32_t)h0.x | ((int64_t)h0.y << 32);
     const int64_t base = (int64_t)(uint32_t)h0.z | ((int64_t)h0.w << 32);
     const int np = h1.x, width = h1.y;
+    const int nsn = (int)(((uint32_t)h2.z >> 16) & 0xffffu);
+    const uint32_t sn0 = (uint32_t)h2.w;
     const uint32_t cbase = (uint32_t)(p0 * NPE);
     const int nscp = width * C + 1;
     // The header is CTA-uniform: phase B re-reads it from shared memory (one STS here) instead of every thread carrying
@@ -183,15 +200,17 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
         return l;
     };
 
-    // ---- level 2 (independent loads, issued together): pair records, contribution codes, slot ranges
-    using NodeVec = typename std::conditional<FAMILY == 0, int4, int2>::type;
+    // ---- level 2 (independent loads, issued together): node list, pair records, contribution codes, slot ranges
+    using NodeVec = typename std::conditional<FAMILY == 0, uint2, uint32_t>::type;  // NPE u16 local node indices
     using CodeVec = typename std::conditional<FAMILY == 0, uint2, uint32_t>::type;  // NPE u16 codes of "pair t's chunk"
-    const NodeVec* pn = reinterpret_cast<const NodeVec*>(A.pair_nodes) + p0;
+    const NodeVec* pn = reinterpret_cast<const NodeVec*>(A.pair_lnodes) + p0;
     const CodeVec* cc = reinterpret_cast<const CodeVec*>(A.ccode + cbase);
     int t = tid;
     NodeVec nodes = NodeVec();
     CodeVec chunk = CodeVec();
     int32_t code = 0;
+    int64_t gnode = -1;
+    if (tid < nsn) gnode = __ldg(A.snodes + sn0 + tid);
     if (t < np) {
         nodes = __ldg(pn + t);
         code = __ldg(A.pair_code + p0 + t);
@@ -199,8 +218,33 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     }
     uint32_t cp0 = 0;
     if (tid < nscp) cp0 = __ldg(A.cptr + base * C + tid);
+    // ---- level 3: X, U of the listed nodes -> shared memory (consecutive threads hold consecutive list entries)
+    {
+        double xv[DIM], uv[DIM];
+        if (gnode >= 0) {
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) {
+                xv[c] = __ldg(A.X + gnode * DIM + c);
+                uv[c] = __ldg(A.U + gnode * DIM + c);
+            }
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) {
+                snd[tid * NS + c] = xv[c];
+                snd[tid * NS + DIM + c] = uv[c];
+            }
+        }
+        for (int i = tid + nth; i < nsn; i += nth) {  // lists longer than the CTA (high-valence meshes)
+            const int64_t g = __ldg(A.snodes + sn0 + i);
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) {
+                snd[i * NS + c] = __ldg(A.X + g * DIM + c);
+                snd[i * NS + DIM + c] = __ldg(A.U + g * DIM + c);
+            }
+        }
+    }
     if (tid < nscp) scp[tid] = (uint16_t)(cp0 - cbase);
     for (int i = tid + nth; i < nscp; i += nth) scp[i] = (uint16_t)(__ldg(A.cptr + base * C + i) - cbase);
+    __syncthreads();
 
     // ---- phase A
     int l = row_of_pair(h1, h2, t);  // the pair's record is skewed by its row inside the slice (bank spreading)
@@ -208,14 +252,14 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     while (t < np_a) {
         reinterpret_cast<CodeVec*>(scode)[t] = chunk;
         if constexpr (FAMILY == 0)
-            tet_pair<KIND>(A, nodes, code, stage + (size_t)t * REC + row_skew(FAMILY, l));
+            tet_pair<KIND>(A, snd, nodes, code, stage + (size_t)t * REC + row_skew(FAMILY, l));
         else
-            truss_pair<DIM>(A, nodes, code, stage + (size_t)t * REC + row_skew(FAMILY, l));
+            truss_pair<DIM>(A, snd, nodes, code, stage + (size_t)t * REC + row_skew(FAMILY, l));
         t += nth;
         if (t < np_a) {  // slices with more pairs than threads (high-valence meshes): header again from L1, not from registers
             const int4* hq = reinterpret_cast<const int4*>(A.hdr + slice);
             const int64_t pq = (int64_t)(uint32_t)__ldg(hq).x | ((int64_t)__ldg(hq).y << 32);
-            nodes = __ldg(reinterpret_cast<const NodeVec*>(A.pair_nodes) + pq + t);
+            nodes = __ldg(reinterpret_cast<const NodeVec*>(A.pair_lnodes) + pq + t);
             code = __ldg(A.pair_code + pq + t);
             chunk = __ldg(reinterpret_cast<const CodeVec*>(A.ccode + (uint32_t)(pq * NPE)) + t);
             l = row_of_pair(__ldg(hq + 1), __ldg(hq + 2), t);
@@ -706,7 +750,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A, P2PA
             tprev = tn;                     \
         }                                   \
     }
-    while (!(it >= A.maxiter || res <= tol)) {
+    while (!(it >= A.maxiter || res <= tol || res != res)) {  // a non-finite residual (breakdown) ends the solve: err = 4
         const double beta = rho / rho_prev;
         // ---- p = z + beta p on owned dofs; on halo dofs z comes from the neighbours' pushes of epoch hepoch
         cg_update_p_body(A, gtid, gsz, beta);
@@ -794,6 +838,7 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A, P2PA
         st->dd = dd;
         st->it = it;
         st->done = 1;
+        if (res != res) *A.err = 4;
         if (mg) {
             P.epochs[0] = repoch;
             P.epochs[1] = hepoch;
@@ -1440,7 +1485,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         }
     }
     const int lrow = lane & 7, qpart = lane >> 3;
-    while (!(it >= A.maxiter || res <= tol)) {
+    while (!(it >= A.maxiter || res <= tol || res != res)) {  // a non-finite residual (breakdown) ends the solve: err = 4
         // ---- p = z + beta p (owned dofs; halo dofs from the neighbours' pushes of epoch hepoch)
         {
             const double beta = rho / rho_prev;
@@ -1734,6 +1779,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         st->dd = dd1[0];
         st->it = it;
         st->done = 1;
+        if (res != res) *A.err = 4;
         if (mg) {
             P.epochs[0] = repoch;
             P.epochs[1] = hepoch;
@@ -1783,7 +1829,8 @@ __global__ void k_cg_init_state(CgArgs A, const double* red) {
     st->tol = fmax(A.reltol * st->res, A.abstol);
     st->it = 0;
     st->dd = 0.0;
-    st->done = (0 >= A.maxiter || st->res <= st->tol) ? 1 : 0;
+    st->done = (0 >= A.maxiter || st->res <= st->tol || st->res != st->res) ? 1 : 0;
+    if (st->res != st->res) *A.err = 4;
 }
 
 __global__ void __launch_bounds__(CG_THREADS) k_cg_update_p(CgArgs A) {
@@ -1826,7 +1873,8 @@ __global__ void k_cg_advance(CgArgs A, const double* red) {
     st->rho = red[P_RZ];
     st->res = sqrt(red[P_RR]);
     st->it += 1;
-    if (st->it >= A.maxiter || st->res <= st->tol) st->done = 1;
+    if (st->it >= A.maxiter || st->res <= st->tol || st->res != st->res) st->done = 1;
+    if (st->res != st->res) *A.err = 4;
 }
 
 __global__ void __launch_bounds__(CG_THREADS) k_cg_epilogue(CgArgs A) {

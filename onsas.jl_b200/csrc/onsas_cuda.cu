@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -145,7 +147,8 @@ struct onsas_ctx {
 
     // device
     DevBuf<double> X, U, Fext, Fint, val, x, r, p, p_pad, Ap, dinv, rhs, partials, red, tet_out, truss_out, area, mat_params;
-    DevBuf<int32_t> tets, tet_mat, trusses, truss_mat, mat_kind, col, diag_slot, pair_code[2], pair_nodes[2], send_nodes;
+    DevBuf<int32_t> tets, tet_mat, trusses, truss_mat, mat_kind, col, diag_slot, pair_code[2], snodes[2], send_nodes;
+    DevBuf<uint16_t> pair_lnodes[2];
     DevBuf<int64_t> slice_ptr;
     DevBuf<SliceHdr> hdr[2];
     DevBuf<uint32_t> cptr[2];
@@ -248,6 +251,20 @@ void require(bool cond, int code, const char* msg) {
     if (!cond) throw OnsasError(code, msg);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (kernel, DEVICE) and is shared by every context of the
+// process: keep a running maximum per (device, kernel) under a lock, so that a second context -- on the same device with
+// a narrower mesh, or on another device -- can neither lower the limit under a live context nor skip setting it.
+void ensure_dyn_smem(int device, const void* kern, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> configured;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = configured[std::make_pair(device, kern)];
+    if (smem > have) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
+}
+
 // device mask = bit 0: free dof (onsas_set_free_dofs), bit 1: interface dof (onsas_p2p_import)
 void upload_mask(onsas_ctx* c) {
     std::vector<uint8_t> m(c->h_mask);
@@ -261,11 +278,7 @@ void upload_mask(onsas_ctx* c) {
 template <int FAMILY, int KIND, int DIM, bool ACCUM, int MAXT, int MINB>
 void launch_asm_inst(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
     auto kern = k_assemble<FAMILY, KIND, DIM, ACCUM, MAXT, MINB>;
-    static size_t configured = 0;  // per instantiation
-    if (smem > configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    ensure_dyn_smem(c->device, (const void*)kern, smem);
     kern<<<(unsigned)(c->asm_count < 0 ? c->tab.n_slices : c->asm_count), threads, smem, c->asm_stream ? c->asm_stream : c->stream>>>(A);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -273,11 +286,7 @@ void launch_asm_inst(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
 template <int FAMILY, int KIND, int DIM, bool ACCUM, int REGS>
 void launch_asm_reg(onsas_ctx* c, const AsmArgs& A, int threads, size_t smem) {
     auto kern = k_assemble_reg<FAMILY, KIND, DIM, ACCUM, REGS>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    ensure_dyn_smem(c->device, (const void*)kern, smem);
     kern<<<(unsigned)(c->asm_count < 0 ? c->tab.n_slices : c->asm_count), threads, smem, c->asm_stream ? c->asm_stream : c->stream>>>(A);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -296,9 +305,11 @@ AsmArgs make_asm_args(onsas_ctx* c, int family) {
     A.X = c->X.p;
     A.U = c->U.p;
     A.hdr = c->hdr[family].p;
-    A.pair_nodes = c->pair_nodes[family].p;
+    A.snodes = c->snodes[family].p;
+    A.pair_lnodes = c->pair_lnodes[family].p;
     A.max_pairs = std::max(c->tab.fam[family].max_pairs_per_slice, 1);
     A.max_width = std::max(c->tab.max_width, 1);
+    A.max_snodes = std::max(c->tab.fam[family].max_snodes, 1);
     A.mat_id = family == 0 ? (c->tet_has_mat ? c->tet_mat.p : nullptr) : (c->truss_has_mat ? c->truss_mat.p : nullptr);
     A.mat_kind = c->mat_kind.p;
     A.mat_params = c->mat_params.p;
@@ -331,7 +342,7 @@ void launch_assemble_range(onsas_ctx* c) {
         AsmArgs A = make_asm_args(c, 0);
         const int mp = c->tab.fam[0].max_pairs_per_slice;
         const int threads = round_threads(mp);
-        const size_t smem = asm_smem_bytes(A.max_pairs, A.max_width, TET_REC, 4);
+        const size_t smem = asm_smem_bytes(A.max_pairs, A.max_width, A.max_snodes, TET_REC, 4, 3);
         switch (c->tet_kind) {
             case MAT_SVK: launch_asm_tets_kind<MAT_SVK>(c, A, threads, smem); break;
             case MAT_NEOHOOKEAN: launch_asm_tets_kind<MAT_NEOHOOKEAN>(c, A, threads, smem); break;
@@ -344,7 +355,7 @@ void launch_assemble_range(onsas_ctx* c) {
         AsmArgs A = make_asm_args(c, 1);
         const int mp = c->tab.fam[1].max_pairs_per_slice;
         const int threads = round_threads(mp);
-        const size_t smem = asm_smem_bytes(A.max_pairs, A.max_width, truss_rec(c->dim), 2);
+        const size_t smem = asm_smem_bytes(A.max_pairs, A.max_width, A.max_snodes, truss_rec(c->dim), 2, c->dim);
         if (wrote) {
             if (c->dim == 3) launch_asm_inst<1, 0, 3, true, 256, 2>(c, A, threads, smem);
             else if (c->dim == 2) launch_asm_inst<1, 0, 2, true, 256, 2>(c, A, threads, smem);
@@ -368,6 +379,7 @@ void launch_assemble(onsas_ctx* c) {
     if (c->n_ranks > 1) halo_exchange(c, c->U.p, 0);
     c->asm_first = 0;
     c->asm_count = -1;
+    c->asm_stream = nullptr;
     launch_assemble_range(c);
 }
 
@@ -415,6 +427,14 @@ void assemble_host(onsas_ctx* c, const double* U, double* F) {
     }
     build_host_plan(c);
     auto& H = c->hp;
+    struct Restore {  // the range / stream of "the next assembly launch" never outlives this call, whatever throws
+        onsas_ctx* c;
+        ~Restore() {
+            c->asm_first = 0;
+            c->asm_count = -1;
+            c->asm_stream = nullptr;
+        }
+    } restore{c};
     const int nch = (int)H.node_hi.size();
     const int bs = c->dim;
     c->co.fresh = false;
@@ -589,7 +609,7 @@ bool plan_stream(onsas_ctx* c) {
     const size_t smem = slot_bytes * (size_t)n_cw * depth;
     void* kern = cw_max == 12 ? (void*)cg_stream<BS, 12> : (void*)cg_stream<BS, 8>;
     const int threads = (cw_max + 1) * 32;
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ensure_dyn_smem(c->device, kern, smem);
     int occ = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ < 1) return false;
@@ -715,22 +735,14 @@ void refresh_coarse(onsas_ctx* c, CgArgs& A) {
     const int nc = c->co.nc;
     {
         const size_t smem = (size_t)c->co.cd * nc * sizeof(double);
-        static size_t configured = 0;
-        if (smem > configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(k_coarse_assemble<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        ensure_dyn_smem(c->device, (const void*)k_coarse_assemble<BS>, smem);
         k_coarse_assemble<BS><<<c->co.n_agg, CO_THREADS, smem, c->stream>>>(A, c->co_E.p);
         CUDA_CHECK(cudaGetLastError());
     }
     if (c->gj_blocked && (nc + GJ_B - 1) / GJ_B <= c->n_sm) {  // panels of 12 rows: nc / 12 grid barriers
         const int grid = (nc + GJ_B - 1) / GJ_B;
         const size_t smem = ((size_t)GJ_B * nc + 2 * GJ_B * GJ_B) * sizeof(double);
-        static size_t configured = 0;
-        if (smem > configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(k_gj_invert_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        ensure_dyn_smem(c->device, (const void*)k_gj_invert_blocked, smem);
         double* M = c->co_E.p;
         int ncv = nc;
         double* rb = c->co_rowbuf.p;
@@ -741,11 +753,7 @@ void refresh_coarse(onsas_ctx* c, CgArgs& A) {
         require(rows <= GJ_MAX_ROWS, ONSAS_ERR_UNSUPPORTED, "coarse space too large for the Gauss-Jordan kernel");
         const int grid = (nc + rows - 1) / rows;
         const size_t smem = (size_t)rows * nc * sizeof(double);
-        static size_t configured = 0;
-        if (smem > configured) {
-            CUDA_CHECK(cudaFuncSetAttribute(k_gj_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        ensure_dyn_smem(c->device, (const void*)k_gj_invert, smem);
         double* M = c->co_E.p;
         int ncv = nc, rowsv = rows;
         double* rb = c->co_rowbuf.p;
@@ -832,6 +840,7 @@ void check_deferred(onsas_ctx* c) {
         *c->h_flag = 0;
         if (f == 2) throw OnsasError(ONSAS_ERR_COMM, "peer-memory CG: timed out waiting for another rank");
         if (f == 3) throw OnsasError(ONSAS_ERR_CUDA, "streamed CG: a shared-memory stage of K never arrived");
+        if (f == 4) throw OnsasError(ONSAS_ERR_BREAKDOWN, "linear solve broke down: the CG residual is not finite (NaN in K, F or U)");
         throw OnsasError(ONSAS_ERR_NEGATIVE_VOLUME, "Element with negative volume, check connectivity.");
     }
 }
@@ -1096,8 +1105,8 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
             if (bad) throw OnsasError(ONSAS_ERR_NEGATIVE_VOLUME, "Element with negative volume, check connectivity.");
         }
         const size_t max_smem = 227 * 1024;
-        require(asm_smem_bytes(std::max(c->tab.fam[0].max_pairs_per_slice, 1), std::max(c->tab.max_width, 1), TET_REC, 4) <= max_smem &&
-                    asm_smem_bytes(std::max(c->tab.fam[1].max_pairs_per_slice, 1), std::max(c->tab.max_width, 1), truss_rec(c->dim), 2) <= max_smem,
+        require(asm_smem_bytes(std::max(c->tab.fam[0].max_pairs_per_slice, 1), std::max(c->tab.max_width, 1), std::max(c->tab.fam[0].max_snodes, 1), TET_REC, 4, 3) <= max_smem &&
+                    asm_smem_bytes(std::max(c->tab.fam[1].max_pairs_per_slice, 1), std::max(c->tab.max_width, 1), std::max(c->tab.fam[1].max_snodes, 1), truss_rec(c->dim), 2, c->dim) <= max_smem,
                 ONSAS_ERR_UNSUPPORTED, "node valence too high: a slice of 8 nodes has more element pairs than fit in shared memory");
 
         // diagonal block position per row
@@ -1127,7 +1136,8 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->diag_slot.upload(dslot, s);
         for (int f = 0; f < 2; ++f) {
             c->pair_code[f].upload(c->tab.fam[f].pair_code, s);
-            c->pair_nodes[f].upload(c->tab.fam[f].pair_nodes, s);
+            c->snodes[f].upload(c->tab.fam[f].snodes, s);
+            c->pair_lnodes[f].upload(c->tab.fam[f].pair_lnodes, s);
             c->hdr[f].upload(c->tab.fam[f].hdr, s);
             c->cptr[f].upload(c->tab.fam[f].cptr, s);
             c->ccode[f].upload(c->tab.fam[f].ccode, s);

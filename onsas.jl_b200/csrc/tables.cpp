@@ -62,12 +62,6 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
             int32_t nd = conn[f][q];
             if (nd < n_rows) F.pair_code[fill[nd]++] = (int32_t)q;  // q = e*npe + a
         }
-        F.pair_nodes.resize(F.pair_code.size() * (size_t)npe[f]);
-#pragma omp parallel for schedule(static)
-        for (int64_t p = 0; p < (int64_t)F.pair_code.size(); ++p) {
-            const int64_t e = F.pair_code[p] / npe[f];
-            for (int b = 0; b < npe[f]; ++b) F.pair_nodes[p * npe[f] + b] = conn[f][e * npe[f] + b];
-        }
     }
 
     // ---- 2. block pattern: count, slice widths, fill
@@ -124,6 +118,40 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
         F.cptr.assign(n_slots + 1, 0);
         F.ccode.assign(n_contrib, 0);
         F.hdr.assign(t.n_slices, SliceHdr());
+        // slice node lists: the distinct nodes the elements of a slice touch.  The assembly CTA stages X and U of exactly
+        // these nodes in shared memory once (runs of consecutive ids -> coalesced loads) and its pairs address them with
+        // 16-bit local indices, instead of every pair gathering its element's nodes from global memory.
+        std::vector<uint32_t> sn_ptr((size_t)t.n_slices + 1, 0);
+        {
+            int32_t max_sn = 0;
+#pragma omp parallel
+            {
+                std::vector<int32_t> buf;
+#pragma omp for schedule(static) reduction(max : max_sn)
+                for (int64_t sl = 0; sl < t.n_slices; ++sl) {
+                    const int64_t r0 = sl * C, r1 = std::min<int64_t>(r0 + C, n_rows);
+                    buf.clear();
+                    for (int64_t p = F.pair_ptr[r0]; p < F.pair_ptr[r1]; ++p) {
+                        const int64_t e = F.pair_code[p] / F.npe;
+                        for (int b = 0; b < F.npe; ++b) buf.push_back(conn[f][e * F.npe + b]);
+                    }
+                    std::sort(buf.begin(), buf.end());
+                    const int32_t n = (int32_t)(std::unique(buf.begin(), buf.end()) - buf.begin());
+                    sn_ptr[sl + 1] = (uint32_t)n;
+                    max_sn = std::max(max_sn, n);
+                }
+            }
+            if (max_sn > 0x7fff) return "too many distinct nodes in one 8-row slice (node valence too high)";
+            uint64_t tot = 0;
+            for (int64_t sl = 0; sl < t.n_slices; ++sl) {
+                tot += sn_ptr[sl + 1];
+                sn_ptr[sl + 1] = (uint32_t)tot;
+            }
+            if (tot >= 0xffffffffull) return "slice node lists exceed 32-bit offsets";
+            F.max_snodes = max_sn;
+            F.snodes.assign((size_t)tot, 0);
+            F.pair_lnodes.assign((size_t)n_contrib, 0);
+        }
         const int BB = dim * dim;
         int32_t max_pairs = 0;
         bool overflow = false;
@@ -144,6 +172,34 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
             H.slot_base = base;
             H.n_pairs = np;
             H.width = w;
+            {
+                int32_t* sn = F.snodes.data() + sn_ptr[sl];
+                const int32_t nsn = (int32_t)(sn_ptr[sl + 1] - sn_ptr[sl]);
+                H.snode_base = sn_ptr[sl];
+                H.n_snodes = (uint16_t)nsn;
+                (void)nsn;
+                std::vector<int32_t> buf;
+                buf.reserve((size_t)np * F.npe);
+                for (int64_t p = p0; p < p1; ++p) {
+                    const int64_t e = F.pair_code[p] / F.npe;
+                    for (int b = 0; b < F.npe; ++b) buf.push_back(conn[f][e * F.npe + b]);
+                }
+                std::sort(buf.begin(), buf.end());
+                buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+                std::copy(buf.begin(), buf.end(), sn);
+                for (int64_t p = p0; p < p1; ++p) {
+                    const int64_t e = F.pair_code[p] / F.npe;
+                    const int a = (int)(F.pair_code[p] % F.npe);
+                    int first_owned = 0;
+                    while (first_owned < F.npe && conn[f][e * F.npe + first_owned] >= n_rows) ++first_owned;
+                    for (int b = 0; b < F.npe; ++b) {
+                        const int32_t nd = conn[f][e * F.npe + b];
+                        uint16_t li = (uint16_t)(std::lower_bound(buf.begin(), buf.end(), nd) - buf.begin());
+                        if (b == 0 && a == first_owned) li |= 0x8000u;
+                        F.pair_lnodes[(size_t)p * F.npe + b] = li;
+                    }
+                }
+            }
             for (int l = 0; l <= C; ++l) H.row_off[l] = (uint16_t)(F.pair_ptr[std::min<int64_t>(r0 + l, r1)] - p0);
             std::vector<uint32_t> cnt((size_t)w * C + 1, 0);
             std::vector<uint16_t> slot_of((size_t)np * F.npe);
@@ -250,12 +306,11 @@ void host_range_plan(const MeshTables& t, int chunks, int mid_weight, std::vecto
         for (int f = 0; f < 2; ++f) {
             const FamilyTables& T = t.fam[f];
             if (T.n_elem == 0 || T.hdr.empty() || slice0[k + 1] == slice0[k]) continue;
-            const SliceHdr& h0 = T.hdr[(size_t)slice0[k]];
-            const SliceHdr& h1 = T.hdr[(size_t)slice0[k + 1] - 1];
-            const int64_t q0 = h0.pair_base * T.npe, q1 = (h1.pair_base + h1.n_pairs) * T.npe;
-            int32_t mx = -1;
-#pragma omp parallel for reduction(max : mx)
-            for (int64_t q = q0; q < q1; ++q) mx = std::max(mx, T.pair_nodes[(size_t)q]);
+            int32_t mx = -1;  // the slice node lists are ascending: the last entry of each is its largest node id
+            for (int64_t sl = slice0[k]; sl < slice0[k + 1]; ++sl) {
+                const SliceHdr& h = T.hdr[(size_t)sl];
+                if (h.n_snodes) mx = std::max(mx, T.snodes[(size_t)h.snode_base + h.n_snodes - 1]);
+            }
             hi = std::max<int64_t>(hi, (int64_t)mx + 1);
         }
         node_hi[k] = std::max(hi, k > 0 ? node_hi[k - 1] : 0);

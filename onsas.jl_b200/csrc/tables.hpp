@@ -42,7 +42,8 @@ struct alignas(16) SliceHdr {
     int32_t n_pairs;
     int32_t width;                      // blocks per row of the slice (padded)
     uint16_t row_off[SLICE_ROWS + 1];   // pair range of each row, relative to pair_base
-    uint16_t pad[3];
+    uint16_t n_snodes;                  // distinct nodes the slice's elements touch (staged in shared memory by the CTA)
+    uint32_t snode_base;                // first entry of the slice in snodes
 };
 static_assert(sizeof(SliceHdr) == 48, "SliceHdr must be 48 bytes");
 
@@ -52,7 +53,11 @@ struct FamilyTables {
     int64_t n_elem = 0;
     std::vector<int64_t> pair_ptr;   // [n_rows+1] pairs of row i
     std::vector<int32_t> pair_code;  // [n_pairs] e*npe + a, ascending e within a row
-    std::vector<int32_t> pair_nodes; // [n_pairs*npe] the element's node ids, copied next to the pair (one load level less)
+    std::vector<uint16_t> pair_lnodes; // [n_pairs*npe] the element's nodes as indices into the slice's node list; bit 15 of the
+                                     // first one: this pair writes the element's stress / strain record (the pair of the
+                                     // element's first OWNED node, so every local element is written on every rank)
+    std::vector<int32_t> snodes;     // per slice: the distinct (local) node ids its elements touch, ascending
+    int32_t max_snodes = 0;          // largest such list
     std::vector<SliceHdr> hdr;       // [n_slices]
     std::vector<uint32_t> cptr;      // [n_slots+1] contribution ranges per block slot (slot = slice_ptr*C + s*C + lane)
     std::vector<uint16_t> ccode;     // [n_pairs*npe] shared-memory offset of the contributing block: local_pair*rec + b*dim*dim

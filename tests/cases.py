@@ -100,3 +100,16 @@ def clamped_truss(N=100):
         Fv[-1] = F * t
         return Fv
     return m, fext, dict(E=E, A=A, L=Ltot, F=F)
+
+
+def svk_uniaxial_state(traction, E=1.0, nu=0.3):
+    """Stretches (alpha, beta) of an SVK bar under the nominal traction P11 = traction with free lateral faces:
+    alpha^3 - alpha = 2 traction / E (the reference's load_factors_analytic, examples/uniaxial_extension/
+    uniaxial_extension.jl:151-154), beta^2 = 1 - nu (alpha^2 - 1)."""
+    a = 1.0 + traction / E
+    for _ in range(100):
+        f, df = a ** 3 - a - 2.0 * traction / E, 3 * a * a - 1.0
+        a, d = a - f / df, f / df
+        if abs(d) < 1e-16 * abs(a):
+            break
+    return float(a), float(np.sqrt(1.0 - nu * (a * a - 1.0)))

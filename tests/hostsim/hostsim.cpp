@@ -182,7 +182,9 @@ int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const i
                 for (int tt = tid; tt < np; tt += threads) {
                     for (int b = 0; b < NPE; ++b) scode[(size_t)tt * NPE + b] = F.ccode[cbase + (size_t)tt * NPE + b];
                     const int32_t code = F.pair_code[p0 + tt];
-                    const int32_t* nd = &F.pair_nodes[(p0 + tt) * NPE];
+                    int32_t nd[4];  // the element's nodes through the slice node list, as the kernel addresses them
+                    for (int b = 0; b < NPE; ++b) nd[b] = F.snodes[(size_t)H.snode_base + (F.pair_lnodes[(size_t)(p0 + tt) * NPE + b] & 0x7fffu)];
+                    const bool writer = (F.pair_lnodes[(size_t)(p0 + tt) * NPE] & 0x8000u) != 0;
                     int lrow = 0;
                     for (int k = 1; k < C; ++k) lrow += (tt >= H.row_off[k]) ? 1 : 0;
                     double* rec = stage.data() + (size_t)tt * REC + row_skew(fam, lrow);
@@ -197,7 +199,7 @@ int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const i
                             }
                         const int mm = tet_mat ? tet_mat[e] : 0;
                         tet_pair(kind[mm], X, U, params[2 * mm], params[2 * mm + 1], a, rec,
-                                 a == 0 ? m->tet_out.data() + 16 * e : nullptr);
+                                 writer ? m->tet_out.data() + 16 * e : nullptr);
                     } else {
                         const int64_t e = code >> 1;
                         const int a = code & 1;
@@ -213,7 +215,7 @@ int hs_assemble(HsModel* m, const int32_t* tets, const int32_t* tet_mat, const i
                         if (dim == 3) truss_pair_d<3>(strain_model, X, U, Emod, area[e], a, rec, se);
                         else if (dim == 2) truss_pair_d<2>(strain_model, X, U, Emod, area[e], a, rec, se);
                         else truss_pair_d<1>(strain_model, X, U, Emod, area[e], a, rec, se);
-                        if (a == 0) {
+                        if (writer) {
                             m->truss_out[2 * e] = se[0];
                             m->truss_out[2 * e + 1] = se[1];
                         }

@@ -301,3 +301,80 @@ def test_device_side_external_loads_match_host_apply(ob):
     c3.add_face_load(cyl.faces["inner"], 1, [1.0])
     c3.apply_loads([10.0])
     np.testing.assert_allclose(c3.get_Fext(), mg.pressure_face_load(cyl.n_nodes, cyl.xyz, cyl.faces["inner"], 10.0), rtol=1e-13, atol=1e-13)
+
+
+def test_million_tet_svk_uniaxial_extension_full_solve(ob):
+    """The target sentence of BASELINE.json at size: examples/uniaxial_extension (SVK, E = 1, nu = 0.3, p = 3, Lx x Ly x Lz =
+    2 x 1 x 1, NSTEPS = 8, tolerances 1e-8, max_iter 30 -- uniaxial_extension.jl:11-24,116-120) on 88 x 44 x 44 cells =
+    1 022 208 tetrahedra, solved from U = 0 through Structure / NonLinearStaticAnalysis / NewtonRaphson / solve
+    (NonLinearStaticAnalyses.jl:70-104).  The deformation is homogeneous, so the analytic answer of the shipped example is
+    exact on every mesh: Newton iteration counts [6,5,5,4,4,4,5,5] (the reference's, = oracle direct-solve Newton on the 6-tet
+    cube), alpha = 2, beta = sqrt(0.1) to 1e-8, the reactions at x = 0 sum to -p A, P and C the analytic tensors in every element."""
+    import time
+    mesh = mg.box_tet_mesh(88, 44, 44, 2.0, 1.0, 1.0)
+    assert mesh.n_tets == 1_022_208
+    free = mg.free_dofs_from_fixed(mesh.n_nodes, 3, mg.uniaxial_fixed(mesh))
+    unit = mg.global_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["x1"], (3.0, 0.0, 0.0))
+    s = ob.Structure.from_arrays(mesh.xyz, tets=mesh.tets, materials=[ob.SVK(E=1.0, nu=0.3)], free_dofs=free, fext=lambda t: unit * t)
+    sa = ob.NonLinearStaticAnalysis(s, NSTEPS=8)
+    nr = ob.NewtonRaphson(ob.ConvergenceSettings(1e-8, 1e-8, 30), preconditioner="two_level", cg_reltol=1e-10)
+    t0 = time.perf_counter()
+    sol = ob.solve_(sa, nr)
+    wall = time.perf_counter() - t0
+    cg = [sum(c) for c in sol.cg_iterations]
+    print(f"\n[full solve] {mesh.n_tets} tets, 8 load steps, Newton iterations {sol.iterations()}, CG iterations per step {cg}, wall {wall:.2f} s")
+    assert sol.iterations() == G.UNIAXIAL_EXTENSION_ITERS == [6, 5, 5, 4, 4, 4, 5, 5]
+    alpha, beta = 2.0, math.sqrt(0.1)
+    U = sol.U[-1]
+    Ua = mg.homogeneous_field(mesh.xyz, alpha, beta)
+    assert np.abs(U - Ua).max() < 1e-8 * np.abs(Ua).max()
+    corner = int(np.argmax(mesh.xyz @ np.ones(3)))
+    assert 1 + U[3 * corner] / 2.0 == pytest.approx(alpha, rel=1e-8)
+    assert 1 + U[3 * corner + 1] / 1.0 == pytest.approx(beta, rel=1e-8)
+    Rx = sol.reactions()[-1].reshape(-1, 3)[mesh.node_sets["x0"], 0].sum()
+    assert Rx == pytest.approx(-3.0, rel=1e-8)                       # -p * A, A = Ly * Lz = 1
+    # P = F S with S = lambda tr(E) I + 2 G E at F = diag(alpha, beta, beta): P11 = p, P22 = P33 = 0; C = F'F
+    P, Cg = sol.tet_stress[-1], sol.tet_strain[-1]
+    assert np.abs(P[:, 0] - 3.0).max() < 1e-7 and np.abs(P[:, 4]).max() < 1e-7 and np.abs(P[:, 8]).max() < 1e-7
+    np.testing.assert_allclose(Cg[:, [0, 4, 8]], np.tile([alpha ** 2, beta ** 2, beta ** 2], (len(Cg), 1)), rtol=1e-8)
+    # every intermediate load step sits on its own analytic state too (uniaxial_extension.jl:151-154: the cubic in alpha)
+    for k, lam in enumerate(sa.load_factors()):
+        a_k, b_k = cases.svk_uniaxial_state(3.0 * lam, 1.0, 0.3)
+        Uk = mg.homogeneous_field(mesh.xyz, a_k, b_k)
+        assert np.abs(sol.U[k] - Uk).max() < 1e-7 * np.abs(Uk).max(), k
+
+
+def test_gpu_solve_to_vtu(ob, tmp_path):
+    """SURVEY.md 8f-2 on the GPU path: solve on the device -> Solution (flat arrays from onsas_get_stress_strain) -> write_vtk
+    -> parse the .vtu: point / cell data equal what the device returned, and the cell-data label set is the reference's
+    (Interfaces/VTK.jl:158-164: sigma / tau and epsilon / gamma components, 9 + 9)."""
+    from onsas_jl_b200 import vtk
+    m, mesh = cases.box_model(6, 3, 3, mat="neo")
+    unit = mg.global_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["x1"], (-1.0, 0.0, 0.0))
+    s = ob.Structure.from_arrays(m.xyz, tets=m.tets, materials=[ob.NeoHookean(E=1.0, nu=0.3)], free_dofs=m.free_dofs, fext=lambda t: unit * t)
+    sa = ob.NonLinearStaticAnalysis(s, NSTEPS=3)
+    sol = ob.solve_(sa, ob.NewtonRaphson(ob.ConvergenceSettings(1e-10, 1e-10, 20), cg_reltol=1e-13))
+    ctx = sa._ctx
+    sig_dev, eps_dev = ctx.get_stress_strain(ob.FAMILY_TET)      # state of the last stored step, straight from the device
+    U_dev = ctx.get_U()
+    path = ob.write_vtk(sol, str(tmp_path / "compression"), 3)
+    arrays, meta = vtk.read_vtu(path)
+    assert meta["n_points"] == mesh.n_nodes and meta["n_cells"] == mesh.n_tets
+    np.testing.assert_array_equal(arrays["Points"], mesh.xyz)
+    np.testing.assert_array_equal(arrays["connectivity"].reshape(-1, 4), mesh.tets)
+    assert set(arrays["types"].tolist()) == {10}
+    np.testing.assert_array_equal(arrays["Displacement"], U_dev.reshape(-1, 3))
+    sig = sig_dev.reshape(-1, 3, 3).transpose(0, 2, 1)           # column-major 3x3 -> [e, i, j]
+    eps = eps_dev.reshape(-1, 3, 3).transpose(0, 2, 1)
+    ij = {"x": 0, "y": 1, "z": 2}
+    for lab in vtk.STRESS_LABELS:
+        np.testing.assert_array_equal(arrays[lab], sig[:, ij[lab[1]], ij[lab[2]]])
+    for lab in vtk.STRAIN_LABELS:
+        np.testing.assert_array_equal(arrays[lab], eps[:, ij[lab[1]], ij[lab[2]]])
+    assert {k for k in arrays if k[0] in "στϵγ"} == set(vtk.STRESS_LABELS) | set(vtk.STRAIN_LABELS)
+    assert vtk.STRESS_LABELS == ["σxx", "σyy", "σzz", "τyz", "τxz", "τxy", "τzy", "τzx", "τyx"]      # VTK.jl:158-161
+    assert vtk.STRAIN_LABELS == ["ϵxx", "ϵyy", "ϵzz", "γyz", "γxz", "γxy", "γzy", "γzx", "γyx"]      # VTK.jl:162-164
+    # analytic check of what landed on disk: P11 = -1 (the traction), P22 = 0, homogeneous in every cell
+    assert np.abs(arrays["σxx"] + 1.0).max() < 1e-8 and np.abs(arrays["σyy"]).max() < 1e-8
+    pvd = ob.write_vtk(sol, str(tmp_path / "series"))
+    assert open(pvd, encoding="utf-8").read().count("<DataSet") == 3
