@@ -220,6 +220,37 @@ int32_t onsas_get_table_stats(onsas_ctx* ctx, int64_t out[8]);
  * [3] grid sync, [4] x/r update + dots, [5] grid sync, [6] scalar reductions (needs ONSAS_OPT_CG_PROFILE = 1). */
 int32_t onsas_get_cg_profile(onsas_ctx* ctx, int64_t out[8]);
 
+/* ---------------------------------------------------------------- multi-GPU, one process driving all devices
+ *
+ * The reference's solve is a single process (StructuralSolvers.jl:201-222); a multi-device context keeps that calling
+ * convention on N GPUs of one box.  onsas_create_multi returns an ordinary onsas_ctx*: EVERY entry point above takes the
+ * GLOBAL mesh and GLOBAL dof vectors in the caller's own numbering, as on one device.  onsas_finalize_mesh partitions the
+ * mesh element-wise (recursive coordinate bisection of the nodes into contiguous owned ranges, interface elements
+ * evaluated on both sides, halo nodes as extra columns), uploads one part per device, enables peer access and wires the
+ * peer-memory solver; one host thread then drives all devices (every call enqueues all devices before it waits for any).
+ * Not available on such a context: onsas_set_stream, ONSAS_OPT_CG_MODE = 1, the one-process-per-GPU calls below. */
+int32_t onsas_create_multi(const int32_t* devices, int32_t ndev, onsas_ctx** ctx);
+int32_t onsas_device_count(onsas_ctx* ctx); /* 1 for onsas_create, ndev for onsas_create_multi */
+
+/* The partitioner on its own, for the one-process-per-GPU binding: every process builds the same partition of the global
+ * mesh (deterministic) and loads ITS rank into its context -- onsas_part_load = onsas_set_nodes + onsas_set_tets +
+ * onsas_set_trusses + onsas_set_free_dofs + onsas_set_halo of that rank (materials are set separately, before
+ * onsas_finalize_mesh).  onsas_part_local_to_global gives, per local node (owned first, then halo), the caller's node id:
+ * local vectors are v_local[dim*i + c] = v_global[dim*l2g[i] + c].  onsas_part_sizes: out = {n_local_nodes, n_owned_nodes,
+ * n_local_tets, n_local_trusses, n_free_local, n_neighbours, n_send_nodes, n_free_global}.  A context loaded from a
+ * partition knows the remote halo offsets itself: pass NULL for them to onsas_p2p_import. */
+typedef struct onsas_part onsas_part;
+int32_t onsas_part_create(int32_t dim, int64_t n_nodes, const double* xyz, int64_t n_tets, const int32_t* tets, const int32_t* tet_mat,
+                          int64_t n_trusses, const int32_t* trusses, const int32_t* truss_mat, const double* area, int64_t n_free,
+                          const int64_t* free_dofs, int32_t n_ranks, onsas_part** part);
+int32_t onsas_part_destroy(onsas_part* part);
+int32_t onsas_part_sizes(onsas_part* part, int32_t rank, int64_t out[8]);
+int32_t onsas_part_local_to_global(onsas_part* part, int32_t rank, int32_t* l2g);
+int32_t onsas_part_local_elements(onsas_part* part, int32_t rank, int32_t family, int64_t* global_ids);
+int32_t onsas_part_halo_plan(onsas_part* part, int32_t rank, int32_t* nbr_rank, int64_t* send_ptr, int32_t* send_nodes,
+                             int64_t* recv_ptr, int64_t* remote_halo_off); /* any pointer may be NULL */
+int32_t onsas_part_load(onsas_part* part, int32_t rank, onsas_ctx* ctx, int32_t truss_strain_model);
+
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU) */
 
 /* NCCL bootstrap: rank 0 calls onsas_comm_unique_id and the host broadcasts the 128 bytes

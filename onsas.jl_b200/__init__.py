@@ -8,7 +8,7 @@ interface for the path and the ctypes binding.  There is no CPU fallback.
 from . import _lib, meshgen  # noqa: F401
 from ._lib import (FAMILY_TET, FAMILY_TRUSS, MAT_ISOLINEAR, MAT_NEOHOOKEAN, MAT_SVK, PRECOND_JACOBI,  # noqa: F401
                    PRECOND_NONE, PRECOND_TWO_LEVEL, STRAIN_GREEN, STRAIN_ROTATED_ENGINEERING)
-from .device import DeviceContext, NegativeVolumeError, OnsasError, context_from_flat  # noqa: F401
+from .device import DeviceContext, NativePartition, NegativeVolumeError, OnsasError, context_from_flat  # noqa: F401
 from .model import (SVK, Circle, FixedField, GenericCrossSection, GlobalLoad, GreenStrain,  # noqa: F401
                     IsotropicLinearElastic, Mesh, NeoHookean, Node, Pressure, Rectangle, RotatedEngineeringStrain,
                     Square, StructuralBoundaryCondition, StructuralMaterial, Structure, Tetrahedron, TriangularFace,

@@ -74,6 +74,16 @@ SIGNATURES = {
     "onsas_get_stress_strain": (C.c_int32, [_vp, C.c_int32, _dp, _dp]),
     "onsas_get_table_stats": (C.c_int32, [_vp, _i64p]),
     "onsas_get_cg_profile": (C.c_int32, [_vp, _i64p]),
+    "onsas_create_multi": (C.c_int32, [_i32p, C.c_int32, C.POINTER(_vp)]),
+    "onsas_device_count": (C.c_int32, [_vp]),
+    "onsas_part_create": (C.c_int32, [C.c_int32, C.c_int64, _dp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp,
+                                      C.c_int32, C.POINTER(_vp)]),
+    "onsas_part_destroy": (C.c_int32, [_vp]),
+    "onsas_part_sizes": (C.c_int32, [_vp, C.c_int32, _i64p]),
+    "onsas_part_local_to_global": (C.c_int32, [_vp, C.c_int32, _i32p]),
+    "onsas_part_local_elements": (C.c_int32, [_vp, C.c_int32, C.c_int32, _i64p]),
+    "onsas_part_halo_plan": (C.c_int32, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "onsas_part_load": (C.c_int32, [_vp, C.c_int32, _vp, C.c_int32]),
     "onsas_comm_unique_id": (C.c_int32, [_vp]),
     "onsas_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp]),
     "onsas_set_halo": (C.c_int32, [_vp, C.c_int32, _vp, _vp, _vp, _vp]),

@@ -721,7 +721,10 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A, P2PA
         ++hepoch;
         for (int64_t i = gtid; i < A.n; i += gsz)
             if (A.mask[i] & 2) p2p_push(P, i, A.r[i] * A.dinv[i], hepoch);
-        for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) A.p[i] = 0.0;  // halo part of the search direction
+        for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) {  // halo part of the search direction and of the solution
+            A.p[i] = 0.0;
+            A.x[i] = 0.0;
+        }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -794,6 +797,8 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A, P2PA
             s2[1] += ri * zi;
             if (mg && (A.mask[i] & 2)) p2p_push(P, i, zi, hepoch);
         }
+        if (mg)  // the solution on the halo dofs follows from the halo search directions: no exchange of U after the solve
+            for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) A.x[i] += alpha * A.p[i];
         const double b0 = block_sum<CG_THREADS>(s2[0], sh);
         const double b1 = block_sum<CG_THREADS>(s2[1], sh);
         if (threadIdx.x == 0) {
@@ -819,6 +824,8 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A, P2PA
     }
 
     double dd = cg_epilogue_body(A, gtid, gsz);
+    if (mg && A.update_U)
+        for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) A.U[i] += A.x[i];
     dd = block_sum<CG_THREADS>(dd, sh);
     if (threadIdx.x == 0) part[P_DD * ps + blockIdx.x] = dd;
     grid.sync();
@@ -1451,6 +1458,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
             if (A.mask[i] & 2) p2p_push(P, i, A.r[i] * A.dinv[i], hepoch);
     }
     for (int64_t i = gtid, np = ((A.n + (mg ? P.n_halo_dofs : 0)) / BS) * PS; i < np; i += gsz) A.p_pad[i] = 0.0;
+    if (mg)
+        for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) A.x[i] = 0.0;  // the solution on the halo dofs (see the update)
 #pragma unroll
     for (int k = 0; k < 4; ++k) g4[k] = block_sum<ST_THREADS>(g4[k], sh);
     grid_reduce(g4);
@@ -1743,6 +1752,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                 }
             }
         }
+        // multi-GPU: x on the halo dofs is accumulated from the halo search directions with the same alpha, in the same
+        // order and with the same fused multiply-add as on the owner, so after the epilogue U is consistent across ranks
+        // without any exchange (the next assembly reads the halo part of U directly)
+        if (mg)
+            for (int64_t h = gtid; h < P.n_halo_dofs; h += gsz) A.x[A.n + h] += alpha * A.p_pad[pad_of(A.n + h)];
         if (two_level) {  // r.z = sum r^2 d + w.y
             if (!fused_w) coarse_w_pass();
             s2[1] += coarse_solve();
@@ -1763,6 +1777,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     if (!is_producer && n_my > 0)
         for (int k = 0; k < D; ++k, ++q_done) mbar_wait(&full[cw][q_done % D], (uint32_t)((q_done / D) & 1), A.err);
 
+    if (mg && A.update_U)
+        for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) A.U[i] += A.x[i];
     double dd1[1] = {block_sum<ST_THREADS>(cg_epilogue_body(A, gtid, gsz), sh)};
     grid_reduce(dd1);
     if (mg) p2p_allreduce<1>(P, dd1, repoch, sh4);

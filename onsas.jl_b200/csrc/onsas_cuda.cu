@@ -17,6 +17,7 @@
 
 #include "../../include/onsas_cuda.h"
 #include "kernels.cuh"
+#include "partition.hpp"
 #include "tables.hpp"
 
 using namespace onsas;
@@ -208,6 +209,7 @@ struct onsas_ctx {
     std::vector<void*> ipc_opened;
     bool p2p_ready = false;
     std::vector<int32_t> h_send_nodes;
+    std::vector<int64_t> remote_halo_off;  // per neighbour: where this rank's values start inside ITS halo (contexts loaded from a partition)
     // device-side load patterns (unit nodal vectors of the load boundary conditions), n_local_dofs each
     DevBuf<double> patterns, factors;
     int n_patterns = 0;
@@ -216,8 +218,20 @@ struct onsas_ctx {
     DevBuf<unsigned long long*> d_push_dst, d_peer_slots;
 
 
+    // one process driving several devices (onsas_create_multi): this context holds the GLOBAL mesh and vectors in the
+    // caller's numbering and owns one ordinary context per device (group.inc)
+    struct Group* grp = nullptr;
+
     int64_t n_local_dofs() const { return n_nodes * dim; }
     int64_t n_own_dofs() const { return n_owned * dim; }
+};
+
+struct Group {
+    std::vector<onsas_ctx*> sub;          // one context per device, rank r = sub[r]
+    Partition part;                       // the global partition (freed down to what the vector traffic needs after finalize)
+    std::vector<LocalPart> lp;            // per rank: l2g, element ids, sizes (connectivity arrays released after upload)
+    std::vector<std::vector<double>> hA, hB;  // per-rank host staging of local vectors
+    int64_t n_free = 0;
 };
 
 namespace {
@@ -272,6 +286,37 @@ void upload_mask(onsas_ctx* c) {
         if (c->h_iface[i]) m[i] |= 2;
     c->mask.upload(m, c->stream);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// material ids in range, the element kind(s) in use (one kernel instantiation per uniform kind), truss materials hyperelastic
+void derive_element_kinds(onsas_ctx* c) {
+    const int nm = (int)c->h_mat_kind.size();
+    auto check_mat = [&](const std::vector<int32_t>& ids, int64_t n) {
+        for (int64_t e = 0; e < (int64_t)ids.size() && e < n; ++e)
+            require(ids[e] >= 0 && ids[e] < nm, ONSAS_ERR_INVALID_ARG, "element material id out of range");
+    };
+    if (c->tet_has_mat) check_mat(c->h_tet_mat, c->n_tets);
+    if (c->truss_has_mat) check_mat(c->h_truss_mat, c->n_trusses);
+    // kinds in use
+    if (c->n_tets > 0) {
+        int kind = -1;
+        bool mixed = false;
+        if (!c->tet_has_mat) kind = c->h_mat_kind[0];
+        else
+            for (int64_t e = 0; e < c->n_tets; ++e) {
+                int k = c->h_mat_kind[c->h_tet_mat[e]];
+                if (kind < 0) kind = k;
+                else if (k != kind) { mixed = true; break; }
+            }
+        c->tet_kind = mixed ? MAT_MIXED : kind;
+    }
+    if (c->n_trusses > 0) {
+        for (int64_t e = 0; e < c->n_trusses; ++e) {
+            int k = c->h_mat_kind[c->truss_has_mat ? c->h_truss_mat[e] : 0];
+            // Trusses.jl:126,159 dispatch on AbstractHyperElasticMaterial only
+            require(k != MAT_ISOLINEAR, ONSAS_ERR_UNSUPPORTED, "trusses need a hyperelastic material (SVK / NeoHookean)");
+        }
+    }
 }
 
 // ---------------------------------------------------------------- assembly launch
@@ -334,6 +379,33 @@ int round_threads(int pairs) {
 void halo_exchange(onsas_ctx* c, double* v, int gate);
 void download(onsas_ctx* c, double* h, const double* d, size_t n);
 void check_deferred(onsas_ctx* c);
+void p2p_wire(onsas_ctx* c, const std::vector<unsigned char*>& win, const int64_t* remote_halo_off);
+void derive_element_kinds(onsas_ctx* c);
+// group.inc: the same entry points on a multi-device context (global vectors in the caller's numbering)
+void grp_destroy(onsas_ctx* g);
+void grp_set_option(onsas_ctx* g, int32_t key, int64_t value);
+void grp_materials_changed(onsas_ctx* g);
+void grp_free_dofs_changed(onsas_ctx* g);
+void grp_finalize(onsas_ctx* g);
+void grp_set_vec(onsas_ctx* g, int which, const double* v);
+void grp_get_vec(onsas_ctx* g, int which, double* v);
+void grp_add_face_load(onsas_ctx* g, int64_t n_faces, const int32_t* tri, int32_t kind, const double* values, int32_t* pattern_id);
+void grp_add_nodal_load(onsas_ctx* g, int64_t n, const int32_t* nodes, const double* values, int32_t* pattern_id);
+void grp_apply_loads(onsas_ctx* g, int32_t n_factors, const double* factors);
+void grp_clear_loads(onsas_ctx* g);
+void grp_assemble(onsas_ctx* g);
+void grp_assemble_host(onsas_ctx* g, const double* U, double* F);
+void grp_eval_elements(onsas_ctx* g, int32_t family, int64_t first, int64_t count, double* f, double* K, double* sig, double* eps);
+void grp_step(onsas_ctx* g, bool assemble, int32_t precond, double reltol, double abstol, int64_t maxiter, int update_U, onsas_step_info* info);
+void grp_pcg(onsas_ctx* g, const double* b, double* x, int32_t precond, double reltol, double abstol, int64_t maxiter, int64_t* iters, double* residual);
+void grp_spmv(onsas_ctx* g, const double* x, double* y);
+void grp_spmv_resident(onsas_ctx* g);
+void grp_synchronize(onsas_ctx* g);
+void grp_get_csr_size(onsas_ctx* g, int64_t* n_rows, int64_t* nnz);
+void grp_get_csr(onsas_ctx* g, int64_t* rowptr, int32_t* col, double* val);
+void grp_get_stress_strain(onsas_ctx* g, int32_t family, double* sig, double* eps);
+void grp_get_table_stats(onsas_ctx* g, int64_t out[8]);
+enum : int { VEC_U = 0, VEC_FEXT = 1, VEC_FINT = 2, VEC_DU = 3 };
 
 // the assembly kernels of every element family over the slice range [c->asm_first, c->asm_first + c->asm_count)
 void launch_assemble_range(onsas_ctx* c) {
@@ -376,7 +448,10 @@ void launch_assemble_range(onsas_ctx* c) {
 void launch_assemble(onsas_ctx* c) {
     require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
     c->co.fresh = false;  // K is about to change: the coarse inverse of the two-level preconditioner is stale
-    if (c->n_ranks > 1) halo_exchange(c, c->U.p, 0);
+    // Multi-GPU: with the peer-memory solver the halo part of U is always current (onsas_set_U / onsas_assemble_host bring
+    // it from the host, and the solver updates it together with the owned part); only the NCCL per-phase solver leaves it
+    // stale, and then it is exchanged here.
+    if (c->n_ranks > 1 && !(c->p2p_ready && c->cg_mode != 1)) halo_exchange(c, c->U.p, 0);
     c->asm_first = 0;
     c->asm_count = -1;
     c->asm_stream = nullptr;
@@ -415,8 +490,8 @@ void build_host_plan(onsas_ctx* c) {
 void assemble_host(onsas_ctx* c, const double* U, double* F) {
     require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
     const size_t nl = (size_t)c->n_local_dofs(), no = (size_t)c->n_own_dofs();
-    if (c->n_ranks > 1 || c->host_chunks <= 1 || c->tab.n_slices == 0 || (c->n_tets == 0 && c->n_trusses == 0)) {
-        // multi-GPU (the halo of U is exchanged first) or pipelining switched off: copy in, assemble, copy out
+    if (c->host_chunks <= 1 || c->tab.n_slices == 0 || (c->n_tets == 0 && c->n_trusses == 0)) {
+        // pipelining switched off: copy in, assemble, copy out.  (Multi-GPU pipelines too: U arrives with its halo part.)
         CUDA_CHECK(cudaMemcpyAsync(c->U.p, U, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         launch_assemble(c);
         if (nl > no) std::fill(F + no, F + nl, 0.0);
@@ -444,10 +519,12 @@ void assemble_host(onsas_ctx* c, const double* U, double* F) {
     // last wave of range k leaves idle (the ranges write disjoint rows of K, F_int and disjoint element records)
     const bool two = c->host_streams >= 2 && nch > 1;
     if (two) CUDA_CHECK(cudaStreamWaitEvent(H.s_k2, H.ev_start, 0));
-    int64_t up = 0;  // nodes of U already sent
+    int64_t up = 0;  // owned nodes of U already sent
+    if (c->n_nodes > c->n_owned)  // multi-GPU: the halo block first (small; every range near the interface reads it)
+        CUDA_CHECK(cudaMemcpyAsync(c->U.p + c->n_owned * bs, U + c->n_owned * bs, (size_t)(c->n_nodes - c->n_owned) * bs * sizeof(double), cudaMemcpyHostToDevice, H.s_in));
     for (int k = 0; k < nch; ++k) {
         cudaStream_t sk = (two && (k & 1)) ? H.s_k2 : c->stream;
-        const int64_t hi = k + 1 == nch ? c->n_nodes : H.node_hi[k];  // the last piece takes what no element touches
+        const int64_t hi = k + 1 == nch ? c->n_owned : H.node_hi[k];  // the last piece takes what no element touches
         if (hi > up) {
             CUDA_CHECK(cudaMemcpyAsync(c->U.p + up * bs, U + up * bs, (size_t)(hi - up) * bs * sizeof(double), cudaMemcpyHostToDevice, H.s_in));
             up = hi;
@@ -468,6 +545,7 @@ void assemble_host(onsas_ctx* c, const double* U, double* F) {
     }
     c->asm_first = 0;
     c->asm_count = -1;
+    if (nl > no) std::fill(F + no, F + nl, 0.0);  // halo part of F_int: not assembled on this rank
     CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, H.s_out));
     CUDA_CHECK(cudaStreamSynchronize(H.s_out));  // the last kernel has finished too: the compute stream is idle
     check_deferred(c);
@@ -476,6 +554,7 @@ void assemble_host(onsas_ctx* c, const double* U, double* F) {
 // ---------------------------------------------------------------- halo exchange (NCCL send/recv)
 void halo_exchange(onsas_ctx* c, double* v, int gate) {
     if (c->n_ranks <= 1 || c->nbr_rank.empty()) return;
+    require(c->comm != nullptr, ONSAS_ERR_COMM, "this multi-GPU context has no NCCL communicator (peer-memory solver only: ONSAS_OPT_CG_MODE 0 or 2)");
     const int bs = c->dim;
     const int64_t n_send = c->send_ptr.back();
     if (n_send > 0) {
@@ -494,6 +573,7 @@ void halo_exchange(onsas_ctx* c, double* v, int gate) {
 
 void allreduce(onsas_ctx* c, double* d, int count) {
     if (c->n_ranks <= 1) return;
+    require(c->comm != nullptr, ONSAS_ERR_COMM, "this multi-GPU context has no NCCL communicator (peer-memory solver only: ONSAS_OPT_CG_MODE 0 or 2)");
     NCCL_CHECK(g_nccl.AllReduce(d, d, (size_t)count, ncclDouble, ncclSum, c->comm, c->stream));
 }
 
@@ -827,6 +907,45 @@ void run_cg(onsas_ctx* c, const CgArgs& A) {
     }
 }
 
+// Wires the peer-memory solver once every rank's window address is known (CUDA IPC mappings with one process per GPU,
+// plain peer pointers when one process drives all devices): the push map -- for every owned dof the LL slots inside the
+// neighbours' receive buffers that want its value -- the peers' scalar slots, and the interface bit of the dof mask.
+void p2p_wire(onsas_ctx* c, const std::vector<unsigned char*>& win, const int64_t* remote_halo_off) {
+    const int nn = (int)c->nbr_rank.size();
+    std::vector<unsigned long long*> slots(c->n_ranks);
+    for (int r = 0; r < c->n_ranks; ++r) slots[r] = win_slots(win[r]);
+    const int bs = c->dim;
+    const int64_t nd = c->n_own_dofs();
+    std::vector<long long> pptr(nd + 1, 0);
+    for (int k = 0; k < nn; ++k)
+        for (int64_t j = c->send_ptr[k]; j < c->send_ptr[k + 1]; ++j)
+            for (int q = 0; q < bs; ++q) pptr[(int64_t)c->h_send_nodes[j] * bs + q + 1]++;
+    for (int64_t i = 0; i < nd; ++i) pptr[i + 1] += pptr[i];
+    std::vector<unsigned long long*> pdst((size_t)pptr[nd]);
+    std::vector<long long> fill(pptr.begin(), pptr.end() - 1);
+    for (int k = 0; k < nn; ++k) {
+        unsigned long long* zh = win_zh(win[c->nbr_rank[k]]);
+        for (int64_t j = c->send_ptr[k]; j < c->send_ptr[k + 1]; ++j)
+            for (int q = 0; q < bs; ++q) {
+                const int64_t i = (int64_t)c->h_send_nodes[j] * bs + q;
+                const int64_t remote_dof = (remote_halo_off[k] + (j - c->send_ptr[k])) * bs + q;
+                pdst[fill[i]++] = zh + 2 * remote_dof;
+            }
+    }
+    if (pdst.empty()) pdst.push_back(nullptr);
+    cudaStream_t s = c->stream;
+    c->d_push_ptr.upload(pptr, s);
+    c->d_push_dst.upload(pdst, s);
+    c->d_peer_slots.upload(slots, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    // mark the interface dofs (mask bit 1): only they look the push map up inside the solver
+    c->h_iface.assign((size_t)nd, 0);
+    for (int64_t i = 0; i < nd; ++i)
+        if (pptr[i + 1] > pptr[i]) c->h_iface[i] = 1;
+    upload_mask(c);
+    c->p2p_ready = true;
+}
+
 void fetch_state(onsas_ctx* c) {
     CUDA_CHECK(cudaMemcpyAsync(c->h_st, c->st.p, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -920,6 +1039,7 @@ int32_t onsas_create(int32_t device, onsas_ctx** out) {
 
 int32_t onsas_destroy(onsas_ctx* c) {
     if (!c) return ONSAS_OK;
+    if (c->grp) grp_destroy(c);
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (void* b : c->ipc_opened) cudaIpcCloseMemHandle(b);
@@ -942,6 +1062,7 @@ int32_t onsas_destroy(onsas_ctx* c) {
 int32_t onsas_set_stream(onsas_ctx* c, void* s) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        require(!c->grp, ONSAS_ERR_UNSUPPORTED, "a multi-device context runs on its own streams (one per device)");
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         c->stream = s ? (cudaStream_t)s : c->own_stream;
     });
@@ -965,6 +1086,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
         }
+        if (c->grp) grp_set_option(c, key, value);
     });
 }
 
@@ -992,11 +1114,14 @@ int32_t onsas_set_materials(onsas_ctx* c, int32_t n, const int32_t* kind, const 
         for (int i = 0; i < n; ++i) require(kind[i] >= 0 && kind[i] <= 2, ONSAS_ERR_INVALID_ARG, "unknown material kind");
         c->h_mat_kind.assign(kind, kind + n);
         c->h_mat_params.assign(params, params + 2 * n);
-        if (c->finalized) {  // material swap on a finalized mesh (replace!(s, material), Structures.jl)
+        if (c->finalized) {  // material swap on a finalized mesh (replace!(s, material), Structures.jl): the element kinds
+            // are re-derived in place -- the tables, U, F_ext and the load patterns of the mesh stay as they are
+            if (c->grp) return grp_materials_changed(c);
+            derive_element_kinds(c);
             c->mat_kind.upload(c->h_mat_kind, c->stream);
             c->mat_params.upload(c->h_mat_params, c->stream);
             CUDA_CHECK(cudaStreamSynchronize(c->stream));
-            c->finalized = false;  // element kinds must be re-derived
+            c->co.fresh = false;
         }
     });
 }
@@ -1045,6 +1170,7 @@ int32_t onsas_set_free_dofs(onsas_ctx* c, int64_t n_free, const int64_t* free_do
         c->n_free = n_free;
         c->n_free_global = n_free_global > 0 ? n_free_global : n_free;
         c->have_free = true;
+        if (c->finalized && c->grp) return grp_free_dofs_changed(c);
         if (c->finalized) upload_mask(c);
     });
 }
@@ -1052,36 +1178,11 @@ int32_t onsas_set_free_dofs(onsas_ctx* c, int64_t n_free, const int64_t* free_do
 int32_t onsas_finalize_mesh(onsas_ctx* c) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_finalize(c);
         require(c->have_nodes, ONSAS_ERR_NOT_READY, "onsas_set_nodes has not been called");
         require(!c->h_mat_kind.empty(), ONSAS_ERR_NOT_READY, "onsas_set_materials has not been called");
         require(c->have_free, ONSAS_ERR_NOT_READY, "onsas_set_free_dofs has not been called");
-        const int nm = (int)c->h_mat_kind.size();
-        auto check_mat = [&](const std::vector<int32_t>& ids, int64_t n) {
-            for (int64_t e = 0; e < (int64_t)ids.size() && e < n; ++e)
-                require(ids[e] >= 0 && ids[e] < nm, ONSAS_ERR_INVALID_ARG, "element material id out of range");
-        };
-        if (c->tet_has_mat) check_mat(c->h_tet_mat, c->n_tets);
-        if (c->truss_has_mat) check_mat(c->h_truss_mat, c->n_trusses);
-        // kinds in use
-        if (c->n_tets > 0) {
-            int kind = -1;
-            bool mixed = false;
-            if (!c->tet_has_mat) kind = c->h_mat_kind[0];
-            else
-                for (int64_t e = 0; e < c->n_tets; ++e) {
-                    int k = c->h_mat_kind[c->h_tet_mat[e]];
-                    if (kind < 0) kind = k;
-                    else if (k != kind) { mixed = true; break; }
-                }
-            c->tet_kind = mixed ? MAT_MIXED : kind;
-        }
-        if (c->n_trusses > 0) {
-            for (int64_t e = 0; e < c->n_trusses; ++e) {
-                int k = c->h_mat_kind[c->truss_has_mat ? c->h_truss_mat[e] : 0];
-                // Trusses.jl:126,159 dispatch on AbstractHyperElasticMaterial only
-                require(k != MAT_ISOLINEAR, ONSAS_ERR_UNSUPPORTED, "trusses need a hyperelastic material (SVK / NeoHookean)");
-            }
-        }
+        derive_element_kinds(c);
         std::string msg = build_mesh_tables(c->dim, c->n_nodes, c->n_owned, c->n_tets, c->h_tets.data(), c->n_trusses,
                                             c->h_trusses.data(), c->tab);
         if (!msg.empty()) throw OnsasError(ONSAS_ERR_INVALID_ARG, msg);
@@ -1158,7 +1259,7 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
             c->p2p_ready = false;
         }
         c->rhs.alloc(nl); c->rhs.zero(s);
-        c->x.alloc(no); c->x.zero(s);
+        c->x.alloc(nl); c->x.zero(s);  // owned + halo dofs: the peer-memory CG keeps the solution consistent on the halo
         c->r.alloc(no); c->r.zero(s);
         c->Ap.alloc(no); c->Ap.zero(s);
         c->dinv.alloc(no); c->dinv.zero(s);
@@ -1180,6 +1281,7 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
 int32_t onsas_set_U(onsas_ctx* c, const double* U) {
     if (!c || !U) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_set_vec(c, VEC_U, U);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         CUDA_CHECK(cudaMemcpyAsync(c->U.p, U, c->n_local_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));  // the caller may free U right after return
@@ -1188,6 +1290,7 @@ int32_t onsas_set_U(onsas_ctx* c, const double* U) {
 int32_t onsas_get_U(onsas_ctx* c, double* U) {
     if (!c || !U) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_get_vec(c, VEC_U, U);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         download(c, U, c->U.p, (size_t)c->n_local_dofs());
     });
@@ -1195,6 +1298,7 @@ int32_t onsas_get_U(onsas_ctx* c, double* U) {
 int32_t onsas_set_Fext(onsas_ctx* c, const double* F) {
     if (!c || !F) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_set_vec(c, VEC_FEXT, F);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         CUDA_CHECK(cudaMemcpyAsync(c->Fext.p, F, c->n_local_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1203,6 +1307,7 @@ int32_t onsas_set_Fext(onsas_ctx* c, const double* F) {
 int32_t onsas_get_Fint(onsas_ctx* c, double* F) {
     if (!c || !F) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_get_vec(c, VEC_FINT, F);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         if (c->n_local_dofs() > c->n_own_dofs()) std::fill(F + c->n_own_dofs(), F + c->n_local_dofs(), 0.0);  // halo part
         // one stream synchronisation for the vector and the deferred-error flag
@@ -1214,6 +1319,7 @@ int32_t onsas_get_Fint(onsas_ctx* c, double* F) {
 int32_t onsas_get_dU(onsas_ctx* c, double* dU) {
     if (!c || !dU) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_get_vec(c, VEC_DU, dU);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         std::fill(dU, dU + c->n_local_dofs(), 0.0);
         download(c, dU, c->x.p, (size_t)c->n_own_dofs());
@@ -1241,6 +1347,7 @@ double* append_pattern(onsas_ctx* c) {
 int32_t onsas_add_face_load(onsas_ctx* c, int64_t n_faces, const int32_t* tri, int32_t kind, const double* values, int32_t* pattern_id) {
     if (!c || !pattern_id) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_add_face_load(c, n_faces, tri, kind, values, pattern_id);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         require(c->dim == 3, ONSAS_ERR_UNSUPPORTED, "face loads need a 3-D mesh");
         require(kind == 0 || kind == 1, ONSAS_ERR_INVALID_ARG, "unknown load kind");
@@ -1280,6 +1387,7 @@ int32_t onsas_add_face_load(onsas_ctx* c, int64_t n_faces, const int32_t* tri, i
 int32_t onsas_add_nodal_load(onsas_ctx* c, int64_t n, const int32_t* nodes, const double* values, int32_t* pattern_id) {
     if (!c || !pattern_id) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_add_nodal_load(c, n, nodes, values, pattern_id);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         require(n >= 0 && (n == 0 || nodes) && values, ONSAS_ERR_INVALID_ARG, "bad node list");
         std::vector<double> h((size_t)c->n_local_dofs(), 0.0);
@@ -1297,6 +1405,7 @@ int32_t onsas_add_nodal_load(onsas_ctx* c, int64_t n, const int32_t* nodes, cons
 int32_t onsas_apply_loads(onsas_ctx* c, int32_t n_factors, const double* factors) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_apply_loads(c, n_factors, factors);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         require(n_factors == c->n_patterns && (n_factors == 0 || factors), ONSAS_ERR_INVALID_ARG,
                 "one factor per load pattern is required");
@@ -1315,6 +1424,7 @@ int32_t onsas_apply_loads(onsas_ctx* c, int32_t n_factors, const double* factors
 int32_t onsas_clear_loads(onsas_ctx* c) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_clear_loads(c);
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         c->n_patterns = 0;
         c->patterns.release();
@@ -1324,6 +1434,7 @@ int32_t onsas_clear_loads(onsas_ctx* c) {
 int32_t onsas_get_Fext(onsas_ctx* c, double* F) {
     if (!c || !F) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_get_vec(c, VEC_FEXT, F);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         download(c, F, c->Fext.p, (size_t)c->n_local_dofs());
     });
@@ -1332,18 +1443,25 @@ int32_t onsas_get_Fext(onsas_ctx* c, double* F) {
 // ---------------------------------------------------------------- hot path
 int32_t onsas_assemble(onsas_ctx* c) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
-    return guard(c, [&] { launch_assemble(c); });  // asynchronous; errors surface at the next synchronizing call
+    return guard(c, [&] {  // asynchronous; errors surface at the next synchronizing call
+        if (c->grp) return grp_assemble(c);
+        launch_assemble(c);
+    });
 }
 
 int32_t onsas_assemble_host(onsas_ctx* c, const double* U, double* F_int) {
     if (!c || !U || !F_int) return ONSAS_ERR_INVALID_ARG;
-    return guard(c, [&] { assemble_host(c, U, F_int); });
+    return guard(c, [&] {
+        if (c->grp) return grp_assemble_host(c, U, F_int);
+        assemble_host(c, U, F_int);
+    });
 }
 
 int32_t onsas_eval_elements(onsas_ctx* c, int32_t family, int64_t first, int64_t count, double* f, double* K, double* sig,
                             double* eps) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_eval_elements(c, family, first, count, f, K, sig, eps);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         require(family == 0 || family == 1, ONSAS_ERR_INVALID_ARG, "unknown element family");
         const int64_t ne = family == 0 ? c->n_tets : c->n_trusses;
@@ -1379,10 +1497,9 @@ int32_t onsas_eval_elements(onsas_ctx* c, int32_t family, int64_t first, int64_t
     });
 }
 
-static void step_impl(onsas_ctx* c, bool assemble, int32_t precond, double reltol, double abstol, int64_t maxiter,
-                      int update_U, onsas_step_info* info) {
+// one Newton iteration in two halves, so that a multi-device context can enqueue every device's work before it waits for any
+static void step_launch(onsas_ctx* c, bool assemble, int32_t precond, double reltol, double abstol, int64_t maxiter, int update_U) {
     require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
-    require(info != nullptr, ONSAS_ERR_INVALID_ARG, "info is NULL");
     require(precond >= 0 && precond <= 2, ONSAS_ERR_INVALID_ARG, "unknown preconditioner");
     CUDA_CHECK(cudaEventRecord(c->ev[0], c->stream));
     if (assemble) launch_assemble(c);
@@ -1390,12 +1507,21 @@ static void step_impl(onsas_ctx* c, bool assemble, int32_t precond, double relto
     CgArgs A = make_cg_args(c, precond, reltol, abstol, maxiter, false, update_U);
     run_cg(c, A);
     CUDA_CHECK(cudaEventRecord(c->ev[2], c->stream));
+}
+static void step_finish(onsas_ctx* c, onsas_step_info* info) {
     fetch_state(c);
     float ms_a = 0, ms_s = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms_a, c->ev[0], c->ev[1]));
     CUDA_CHECK(cudaEventElapsedTime(&ms_s, c->ev[1], c->ev[2]));
     check_deferred(c);
     fill_info(c, info, ms_a, ms_s);
+}
+static void step_impl(onsas_ctx* c, bool assemble, int32_t precond, double reltol, double abstol, int64_t maxiter,
+                      int update_U, onsas_step_info* info) {
+    require(info != nullptr, ONSAS_ERR_INVALID_ARG, "info is NULL");
+    if (c->grp) return grp_step(c, assemble, precond, reltol, abstol, maxiter, update_U, info);
+    step_launch(c, assemble, precond, reltol, abstol, maxiter, update_U);
+    step_finish(c, info);
 }
 
 int32_t onsas_newton_step(onsas_ctx* c, int32_t precond, double cg_reltol, double cg_abstol, int64_t cg_maxiter,
@@ -1414,6 +1540,7 @@ int32_t onsas_pcg(onsas_ctx* c, const double* b, double* x, int32_t precond, dou
                   int64_t* iters, double* residual) {
     if (!c || !b || !x) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_pcg(c, b, x, precond, reltol, abstol, maxiter, iters, residual);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         require(precond >= 0 && precond <= 2, ONSAS_ERR_INVALID_ARG, "unknown preconditioner");
         CUDA_CHECK(cudaMemcpyAsync(c->rhs.p, b, c->n_local_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1430,6 +1557,7 @@ int32_t onsas_pcg(onsas_ctx* c, const double* b, double* x, int32_t precond, dou
 int32_t onsas_spmv(onsas_ctx* c, const double* x, double* y) {
     if (!c || !x || !y) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_spmv(c, x, y);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         CUDA_CHECK(cudaMemcpyAsync(c->p.p, x, c->n_local_dofs() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CgArgs A = make_cg_args(c, 0, 0, 0, 1, false, 0);
@@ -1450,6 +1578,7 @@ int32_t onsas_spmv(onsas_ctx* c, const double* x, double* y) {
 int32_t onsas_spmv_resident(onsas_ctx* c) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_spmv_resident(c);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         CgArgs A = make_cg_args(c, 0, 0, 0, 1, false, 0);
         const int Gr = spmv_grid(c);
@@ -1466,6 +1595,7 @@ int32_t onsas_spmv_resident(onsas_ctx* c) {
 int32_t onsas_synchronize(onsas_ctx* c) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_synchronize(c);
         CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         check_deferred(c);
@@ -1476,6 +1606,7 @@ int32_t onsas_synchronize(onsas_ctx* c) {
 int32_t onsas_get_csr_size(onsas_ctx* c, int64_t* n_rows, int64_t* nnz) {
     if (!c || !n_rows || !nnz) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_get_csr_size(c, n_rows, nnz);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         *n_rows = c->n_own_dofs();
         *nnz = c->tab.nnz_blocks * c->dim * c->dim;
@@ -1485,6 +1616,7 @@ int32_t onsas_get_csr_size(onsas_ctx* c, int64_t* n_rows, int64_t* nnz) {
 int32_t onsas_get_csr(onsas_ctx* c, int64_t* rowptr, int32_t* col, double* val) {
     if (!c || !rowptr || !col || !val) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_get_csr(c, rowptr, col, val);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         std::vector<int64_t> rp;
         std::vector<int32_t> ci;
@@ -1500,6 +1632,7 @@ int32_t onsas_get_csr(onsas_ctx* c, int64_t* rowptr, int32_t* col, double* val) 
 int32_t onsas_get_stress_strain(onsas_ctx* c, int32_t family, double* sig, double* eps) {
     if (!c || !sig || !eps) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_get_stress_strain(c, family, sig, eps);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         require(family == 0 || family == 1, ONSAS_ERR_INVALID_ARG, "unknown element family");
         if (family == 0) {
@@ -1528,6 +1661,7 @@ int32_t onsas_get_stress_strain(onsas_ctx* c, int32_t family, double* sig, doubl
 int32_t onsas_get_cg_profile(onsas_ctx* c, int64_t out[8]) {
     if (!c || !out) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return (void)onsas_get_cg_profile(c->grp->sub[0], out);
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         std::vector<long long> h(16 + 4096);
         CUDA_CHECK(cudaMemcpy(h.data(), c->prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -1555,6 +1689,7 @@ int32_t onsas_get_cg_profile(onsas_ctx* c, int64_t out[8]) {
 int32_t onsas_get_table_stats(onsas_ctx* c, int64_t out[8]) {
     if (!c || !out) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return grp_get_table_stats(c, out);
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         out[0] = c->tab.n_slices;
         out[1] = c->tab.n_slots();
@@ -1592,6 +1727,7 @@ int32_t onsas_comm_unique_id(void* id128) {
 int32_t onsas_comm_init(onsas_ctx* c, int32_t n_ranks, int32_t rank, const void* id128) {
     if (!c || !id128) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return throw OnsasError(ONSAS_ERR_INVALID_ARG, "a multi-device context manages its own ranks");
         require(n_ranks >= 1 && rank >= 0 && rank < n_ranks, ONSAS_ERR_INVALID_ARG, "bad rank / n_ranks");
         std::string err;
         if (!g_nccl.load(err)) throw OnsasError(ONSAS_ERR_COMM, err);
@@ -1607,6 +1743,7 @@ int32_t onsas_set_halo(onsas_ctx* c, int32_t n_nbr, const int32_t* nbr_rank, con
                        const int32_t* send_nodes, const int64_t* recv_ptr) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return throw OnsasError(ONSAS_ERR_INVALID_ARG, "a multi-device context manages its own halo plan");
         require(n_nbr >= 0, ONSAS_ERR_INVALID_ARG, "bad neighbour count");
         require(n_nbr == 0 || (nbr_rank && send_ptr && recv_ptr), ONSAS_ERR_INVALID_ARG, "NULL halo arrays");
         c->nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
@@ -1628,6 +1765,7 @@ int32_t onsas_set_halo(onsas_ctx* c, int32_t n_nbr, const int32_t* nbr_rank, con
 int32_t onsas_p2p_export(onsas_ctx* c, void* handle64, int64_t* offset) {
     if (!c || !handle64 || !offset) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return throw OnsasError(ONSAS_ERR_INVALID_ARG, "a multi-device context wires its own peer windows");
         require(c->finalized && c->window.p, ONSAS_ERR_NOT_READY,
                 "onsas_comm_init and onsas_finalize_mesh must precede onsas_p2p_export");
         cudaIpcMemHandle_t h;
@@ -1651,10 +1789,13 @@ int32_t onsas_p2p_export(onsas_ctx* c, void* handle64, int64_t* offset) {
 int32_t onsas_p2p_import(onsas_ctx* c, const void* handles, const int64_t* offsets, const int64_t* remote_halo_off) {
     if (!c || !handles || !offsets) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (c->grp) return throw OnsasError(ONSAS_ERR_INVALID_ARG, "a multi-device context wires its own peer windows");
         require(c->finalized && c->window.p, ONSAS_ERR_NOT_READY, "window not allocated");
         require(c->n_ranks <= P2P_MAXR, ONSAS_ERR_UNSUPPORTED, "peer-memory CG supports at most 16 ranks");
         const int nn = (int)c->nbr_rank.size();
-        require(nn == 0 || remote_halo_off, ONSAS_ERR_INVALID_ARG, "NULL remote halo offsets");
+        // a context loaded from a partition (onsas_part_load) knows where its values start inside every neighbour's halo
+        const int64_t* rho = remote_halo_off ? remote_halo_off : (c->remote_halo_off.size() == (size_t)nn ? c->remote_halo_off.data() : nullptr);
+        require(nn == 0 || rho, ONSAS_ERR_INVALID_ARG, "NULL remote halo offsets");
         std::vector<unsigned char*> win(c->n_ranks, nullptr);
         for (int r = 0; r < c->n_ranks; ++r) {
             if (r == c->rank) {
@@ -1668,40 +1809,10 @@ int32_t onsas_p2p_import(onsas_ctx* c, const void* handles, const int64_t* offse
             c->ipc_opened.push_back(base);
             win[r] = (unsigned char*)base + offsets[r];
         }
-        std::vector<unsigned long long*> slots(c->n_ranks);
-        for (int r = 0; r < c->n_ranks; ++r) slots[r] = win_slots(win[r]);
-        // push map: for every owned dof the LL slots (in the neighbours' receive buffers) that want its z value
-        const int bs = c->dim;
-        const int64_t nd = c->n_own_dofs();
-        std::vector<long long> pptr(nd + 1, 0);
-        for (int k = 0; k < nn; ++k)
-            for (int64_t j = c->send_ptr[k]; j < c->send_ptr[k + 1]; ++j)
-                for (int q = 0; q < bs; ++q) pptr[(int64_t)c->h_send_nodes[j] * bs + q + 1]++;
-        for (int64_t i = 0; i < nd; ++i) pptr[i + 1] += pptr[i];
-        std::vector<unsigned long long*> pdst((size_t)pptr[nd]);
-        std::vector<long long> fill(pptr.begin(), pptr.end() - 1);
-        for (int k = 0; k < nn; ++k) {
-            unsigned long long* zh = win_zh(win[c->nbr_rank[k]]);
-            for (int64_t j = c->send_ptr[k]; j < c->send_ptr[k + 1]; ++j)
-                for (int q = 0; q < bs; ++q) {
-                    const int64_t i = (int64_t)c->h_send_nodes[j] * bs + q;
-                    const int64_t remote_dof = (remote_halo_off[k] + (j - c->send_ptr[k])) * bs + q;
-                    pdst[fill[i]++] = zh + 2 * remote_dof;
-                }
-        }
-        if (pdst.empty()) pdst.push_back(nullptr);
-        cudaStream_t s = c->stream;
-        c->d_push_ptr.upload(pptr, s);
-        c->d_push_dst.upload(pdst, s);
-        c->d_peer_slots.upload(slots, s);
-        CUDA_CHECK(cudaStreamSynchronize(s));
-        // mark the interface dofs (mask bit 1): only they look the push map up inside the solver
-        c->h_iface.assign((size_t)nd, 0);
-        for (int64_t i = 0; i < nd; ++i)
-            if (pptr[i + 1] > pptr[i]) c->h_iface[i] = 1;
-        upload_mask(c);
-        c->p2p_ready = true;
+        p2p_wire(c, win, rho);
     });
 }
 
 }  // extern "C"
+
+#include "group.inc"

@@ -302,14 +302,17 @@ void host_range_plan(const MeshTables& t, int chunks, int mid_weight, std::vecto
     }
     node_hi.assign((size_t)nch, 0);
     for (int k = 0; k < nch; ++k) {
-        int64_t hi = std::min<int64_t>(slice0[k + 1] * SLICE_ROWS, t.n_nodes);  // the rows themselves
+        int64_t hi = std::min<int64_t>(slice0[k + 1] * SLICE_ROWS, t.n_rows);  // the rows themselves
         for (int f = 0; f < 2; ++f) {
             const FamilyTables& T = t.fam[f];
             if (T.n_elem == 0 || T.hdr.empty() || slice0[k + 1] == slice0[k]) continue;
             int32_t mx = -1;  // the slice node lists are ascending: the last entry of each is its largest node id
             for (int64_t sl = slice0[k]; sl < slice0[k + 1]; ++sl) {
                 const SliceHdr& h = T.hdr[(size_t)sl];
-                if (h.n_snodes) mx = std::max(mx, T.snodes[(size_t)h.snode_base + h.n_snodes - 1]);
+                // halo nodes (ids >= n_rows, multi-GPU) are not part of the prefix: their values travel first, as one block
+                const int32_t* b = T.snodes.data() + h.snode_base;
+                const int32_t* e = std::lower_bound(b, b + h.n_snodes, (int32_t)std::min<int64_t>(t.n_rows, 0x7fffffff));
+                if (e > b) mx = std::max(mx, e[-1]);
             }
             hi = std::max<int64_t>(hi, (int64_t)mx + 1);
         }

@@ -85,7 +85,8 @@ std::string build_mesh_tables(int dim, int64_t n_nodes, int64_t n_rows, int64_t 
 
 // Slice ranges for a pipelined assembly with host buffers (onsas_assemble_host): `chunks` ranges, the first and the last
 // of weight 1 against `mid_weight` for the inner ones; slice0[k] .. slice0[k+1] are the slices of range k and the elements
-// evaluated by those slices touch nodes [0, node_hi[k]) only (node_hi is non-decreasing, so U can travel as prefixes).
+// evaluated by those slices touch the OWNED nodes [0, node_hi[k]) only (node_hi is non-decreasing, so U can travel as
+// prefixes); halo nodes (multi-GPU: ids >= n_rows) are outside this accounting -- their block of U is sent first.
 void host_range_plan(const MeshTables& t, int chunks, int mid_weight, std::vector<int64_t>& slice0, std::vector<int64_t>& node_hi);
 
 // Scalar CSR (n_rows*dim rows, n_nodes*dim columns, sorted columns) index arrays of the same pattern.

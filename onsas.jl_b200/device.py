@@ -31,10 +31,19 @@ def _ptr(a):
 
 
 class DeviceContext:
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """`device`: one CUDA device index, or a sequence of them -- then ONE host process drives all of them behind the
+        same interface (onsas_create_multi): global mesh and global vectors in, partitioning / halo plan / peer-memory
+        wiring inside onsas_finalize_mesh."""
         self._lib = L.lib()
         h = C.c_void_p()
-        st = self._lib.onsas_create(int(device), C.byref(h))
+        if np.ndim(device) > 0:
+            devs = _as(device, np.int32).ravel()
+            st = self._lib.onsas_create_multi(devs, len(devs), C.byref(h))
+            self.devices = [int(d) for d in devs]
+        else:
+            st = self._lib.onsas_create(int(device), C.byref(h))
+            self.devices = [int(device)]
         if st != L.OK:
             raise OnsasError(st, (self._lib.onsas_last_error(None) or b"").decode())
         self._h = h
@@ -284,11 +293,86 @@ class DeviceContext:
         self._check(self._lib.onsas_p2p_export(self._h, C.cast(buf, C.c_void_p), C.byref(off)))
         return buf.raw, off.value
 
-    def p2p_import(self, handles, offsets, remote_halo_node_off):
+    def p2p_import(self, handles, offsets, remote_halo_node_off=None):
+        """`remote_halo_node_off` may be None for a context loaded from a NativePartition (it knows the offsets)."""
         blob = C.create_string_buffer(b"".join(handles), 64 * len(handles))
         offs = _as(offsets, np.int64)
-        rem = _as(remote_halo_node_off, np.int64)
-        self._check(self._lib.onsas_p2p_import(self._h, C.cast(blob, C.c_void_p), offs, _ptr(rem) if len(rem) else None))
+        rem = None if remote_halo_node_off is None else _as(remote_halo_node_off, np.int64)
+        self._check(self._lib.onsas_p2p_import(self._h, C.cast(blob, C.c_void_p), offs, _ptr(rem) if rem is not None and len(rem) else None))
+
+    def load_part(self, part: "NativePartition", rank: int, truss_strain: int = 0):
+        """Nodes, elements, free dofs and halo plan of `rank` from a native partition (onsas_part_load)."""
+        self._check(self._lib.onsas_part_load(part._h, int(rank), self._h, int(truss_strain)))
+        sz = part.sizes(rank)
+        self.n_nodes, self.n_owned, self.n_tets, self.n_trusses = sz["n_local"], sz["n_owned"], sz["n_tets"], sz["n_trusses"]
+        self.dim = part.dim
+
+
+class NativePartition:
+    """The library's partitioner (csrc/partition.cpp) on its own: recursive coordinate bisection of the global mesh into
+    `n_ranks` parts, the halo plan of every rank.  Used by the one-process-per-GPU binding (every process builds the same
+    partition and loads its own rank); a multi-device DeviceContext runs the same code inside onsas_finalize_mesh."""
+
+    def __init__(self, xyz, n_ranks: int, tets=None, tet_mat=None, trusses=None, truss_mat=None, truss_area=None, free_dofs=None):
+        self._lib = L.lib()
+        xyz = _as(xyz, np.float64)
+        if xyz.ndim == 1:
+            xyz = xyz.reshape(-1, 1)
+        self.n_nodes, self.dim = xyz.shape
+        self.n_ranks = int(n_ranks)
+        tets = None if tets is None or len(tets) == 0 else _as(tets, np.int32).reshape(-1, 4)
+        trusses = None if trusses is None or len(trusses) == 0 else _as(trusses, np.int32).reshape(-1, 2)
+        tm = None if tet_mat is None else _as(tet_mat, np.int32)
+        bm = None if truss_mat is None else _as(truss_mat, np.int32)
+        ar = None if truss_area is None else _as(truss_area, np.float64)
+        fd = np.arange(self.n_nodes * self.dim, dtype=np.int64) if free_dofs is None else _as(free_dofs, np.int64).ravel()
+        h = C.c_void_p()
+        st = self._lib.onsas_part_create(self.dim, self.n_nodes, xyz.ravel(), 0 if tets is None else len(tets), _ptr(tets), _ptr(tm),
+                                         0 if trusses is None else len(trusses), _ptr(trusses), _ptr(bm), _ptr(ar), len(fd), _ptr(fd),
+                                         self.n_ranks, C.byref(h))
+        if st != L.OK:
+            raise OnsasError(st, (self._lib.onsas_last_error(None) or b"").decode())
+        self._h = h
+
+    def _check(self, st):
+        if st != L.OK:
+            raise OnsasError(st, (self._lib.onsas_last_error(None) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.onsas_part_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sizes(self, rank: int) -> dict:
+        out = np.zeros(8, np.int64)
+        self._check(self._lib.onsas_part_sizes(self._h, int(rank), out))
+        keys = ["n_local", "n_owned", "n_tets", "n_trusses", "n_free", "n_nbr", "n_send", "n_free_global"]
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def local_to_global(self, rank: int) -> np.ndarray:
+        l2g = np.empty(self.sizes(rank)["n_local"], np.int32)
+        self._check(self._lib.onsas_part_local_to_global(self._h, int(rank), l2g))
+        return l2g
+
+    def local_elements(self, rank: int, family: int = L.FAMILY_TET) -> np.ndarray:
+        sz = self.sizes(rank)
+        gid = np.empty(sz["n_tets"] if family == L.FAMILY_TET else sz["n_trusses"], np.int64)
+        self._check(self._lib.onsas_part_local_elements(self._h, int(rank), int(family), gid))
+        return gid
+
+    def halo_plan(self, rank: int) -> dict:
+        sz = self.sizes(rank)
+        nn = sz["n_nbr"]
+        nbr, sp, sn = np.empty(nn, np.int32), np.empty(nn + 1, np.int64), np.empty(sz["n_send"], np.int32)
+        rp, ro = np.empty(nn + 1, np.int64), np.empty(nn, np.int64)
+        self._check(self._lib.onsas_part_halo_plan(self._h, int(rank), _ptr(nbr), _ptr(sp), _ptr(sn), _ptr(rp), _ptr(ro)))
+        return dict(nbr_rank=nbr, send_ptr=sp, send_nodes=sn, recv_ptr=rp, remote_halo_off=ro)
 
 
 def context_from_flat(xyz, tets=None, trusses=None, truss_area=None, truss_strain=0, mat_kind=(0,), mat_params=((1.0, 1.0),),

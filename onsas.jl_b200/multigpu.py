@@ -10,23 +10,30 @@ from .device import DeviceContext
 
 def make_distributed_context(part, mat_kind, mat_params, dist, local_rank: int, p2p: bool = True,
                              truss_strain: int = 0) -> DeviceContext:
-    """`part` is a partition.LocalPart; `dist` an initialised torch.distributed (NCCL backend)."""
+    """`part` is a partition.LocalPart (the numpy restatement) or a device.NativePartition (the library's partitioner:
+    every process built the same partition and loads its own rank); `dist` an initialised torch.distributed (NCCL)."""
     import torch
+    from .device import NativePartition
     rank, world = dist.get_rank(), dist.get_world_size()
+    native = isinstance(part, NativePartition)
     ctx = DeviceContext(local_rank)
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
         uid.copy_(torch.frombuffer(bytearray(DeviceContext.comm_unique_id()), dtype=torch.uint8))
     dist.broadcast(uid, 0)
     ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
-    ctx.set_nodes(part.xyz, part.n_owned)
-    ctx.set_materials(mat_kind, mat_params)
-    if len(part.tets):
-        ctx.set_tets(part.tets, part.tet_mat)
-    if len(part.trusses):
-        ctx.set_trusses(part.trusses, part.truss_area, part.truss_mat, truss_strain)
-    ctx.set_free_dofs(part.free_dofs, part.n_free_global)
-    ctx.set_halo(part.nbr_rank, part.send_ptr, part.send_nodes, part.recv_ptr)
+    if native:
+        ctx.set_materials(mat_kind, mat_params)
+        ctx.load_part(part, rank, truss_strain)
+    else:
+        ctx.set_nodes(part.xyz, part.n_owned)
+        ctx.set_materials(mat_kind, mat_params)
+        if len(part.tets):
+            ctx.set_tets(part.tets, part.tet_mat)
+        if len(part.trusses):
+            ctx.set_trusses(part.trusses, part.truss_area, part.truss_mat, truss_strain)
+        ctx.set_free_dofs(part.free_dofs, part.n_free_global)
+        ctx.set_halo(part.nbr_rank, part.send_ptr, part.send_nodes, part.recv_ptr)
     ctx.finalize()
     if p2p and world > 1:
         # every rank must take the same path: export first, agree on success, then import
@@ -41,6 +48,10 @@ def make_distributed_context(part, mat_kind, mat_params, dist, local_rank: int, 
         if int(flag.item()) == 0:
             return ctx
         meta = [None] * world
+        if native:   # the partition knows where this rank's values start inside every neighbour's halo
+            dist.all_gather_object(meta, dict(handle=handle, offset=offset))
+            ctx.p2p_import([m["handle"] for m in meta], [m["offset"] for m in meta], None)
+            return ctx
         dist.all_gather_object(meta, dict(handle=handle, offset=offset, n_owned=int(part.n_owned),
                                           nbr=[int(r) for r in part.nbr_rank], recv_ptr=[int(v) for v in part.recv_ptr]))
         remote = []

@@ -99,17 +99,54 @@ def main():
             dr_rel = info.norm_r / info.norm_Fext
             it += 1
         iters.append(it)
-    Ul = ctx.get_U()[:len(own)]
+    Uloc = ctx.get_U()
+    Ul = Uloc[:len(own)]
     e_u = np.abs(Ul - refn.U[-1][own]).max() / np.abs(refn.U[-1]).max()
-    errs = torch.tensor([e_f, e_k, e_y, e_x, e_u, e_x2], dtype=torch.float64, device="cuda")
+    # the solver keeps the halo part of U current without any exchange: it must equal the owners' values bit for bit
+    Ug = torch.zeros(gm.n_dofs, dtype=torch.float64, device="cuda")
+    Ug[torch.as_tensor(own, device="cuda")] = torch.as_tensor(Ul, device="cuda")
+    dist.all_reduce(Ug)
+    Ug = Ug.cpu().numpy()
+    halo_ok = np.array_equal(Uloc, part.scatter_global(Ug, 3))
+    # ---- the same solve through the library's own partitioner (onsas_part_*): caller numbering in, bitwise the same U
+    ctx.close()
+    P = ob.NativePartition(m2.xyz, world, tets=m2.tets, free_dofs=m2.free_dofs)
+    from onsas_jl_b200 import multigpu
+    ctx = multigpu.make_distributed_context(P, m.mat_kind, m.mat_params, dist, local_rank, p2p=True)
+    l2g = P.local_to_global(rank)
+    Fo = mg.global_face_load(mesh2.n_nodes, mesh2.xyz, mesh2.faces["x1"], (-1.0, 0.0, 0.0)).reshape(-1, 3)
+    ctx.set_U(np.zeros(len(l2g) * 3))
+    iters_n = []
+    for t in lfs:
+        ctx.set_Fext((Fo[l2g] * t).ravel())
+        dU_rel = dr_rel = 1e12
+        it = 0
+        while O.criterion(dU_rel, dr_rel, it, tols) == "NotConvergedYet":
+            info = ctx.newton_step(ob.PRECOND_JACOBI, 1e-13)
+            dU_rel = info.norm_dU / info.norm_U if info.norm_U > 0 else math.inf
+            dr_rel = info.norm_r / info.norm_Fext
+            it += 1
+        iters_n.append(it)
+    n_own = P.sizes(rank)["n_owned"]
+    Un = torch.zeros((mesh2.n_nodes, 3), dtype=torch.float64, device="cuda")
+    Un[torch.as_tensor(l2g[:n_own].astype(np.int64), device="cuda")] = torch.as_tensor(ctx.get_U().reshape(-1, 3)[:n_own], device="cuda")
+    dist.all_reduce(Un)
+    Un = Un.cpu().numpy()
+    native_ok = np.array_equal(Un[order].ravel(), Ug) and iters_n == iters
+    if rank == 0 and os.environ.get("ONSAS_MULTI_DUMP"):
+        np.save(os.environ["ONSAS_MULTI_DUMP"], Un)      # caller numbering: compared with the one-process multi-device context
+    errs = torch.tensor([e_f, e_k, e_y, e_x, e_u, e_x2, 0.0 if halo_ok else 1.0, 0.0 if native_ok else 1.0], dtype=torch.float64, device="cuda")
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     ok = True
     if rank == 0:
-        e_f, e_k, e_y, e_x, e_u, e_x2 = errs.tolist()
+        e_f, e_k, e_y, e_x, e_u, e_x2, bad_halo, bad_native = errs.tolist()
+        halo_ok, native_ok = bad_halo == 0.0, bad_native == 0.0
         print(f"multi-gpu check world={world}: two-level pcg x {e_x2:.2e} (its {its2} vs jacobi {its[0]})", flush=True)
         print(f"multi-gpu check world={world}: F_int {e_f:.2e}  K {e_k:.2e}  spmv {e_y:.2e}  pcg x {e_x:.2e} (its {its} vs {ito})  "
               f"newton U {e_u:.2e} iters {iters} vs {refn.iterations}", flush=True)
+        print(f"multi-gpu check world={world}: halo part of U bitwise current after the solves: {halo_ok}; native partitioner bitwise equal: {native_ok}", flush=True)
         ok = e_f < 1e-12 and e_k < 1e-12 and e_y < 1e-12 and e_x < 1e-8 and e_u < 1e-8 and iters == refn.iterations and e_x2 < 1e-8
+        ok = ok and halo_ok and native_ok
         print("MULTI_GPU_CHECK_OK" if ok else "MULTI_GPU_CHECK_FAILED", flush=True)
     dist.barrier()          # never leave the other ranks waiting on a failed assertion
     dist.destroy_process_group()
