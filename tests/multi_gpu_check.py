@@ -77,9 +77,12 @@ def main():
     # ---- distributed Newton solve of the compression example (9 load steps, tol 1e-10, as the reference ships it)
     #      vs the oracle's direct-solve Newton, on the undistorted mesh of the same grid
     m2, mesh2 = cases.box_model(12, 6, 6, mat="neo")
-    xyz2 = m2.xyz[order]
+    order, ranges = pt.rcb_order(m2.xyz, world)          # the partition of THIS mesh (the jittered one above splits elsewhere)
+    xyz2, tets, inv = pt.renumber(order, m2.xyz, m2.tets)
+    free = np.sort(inv[m2.free_dofs // 3] * 3 + m2.free_dofs % 3)
     gm = O.FlatModel(xyz=xyz2, tets=tets, mat_kind=m.mat_kind, mat_params=m.mat_params, free_dofs=free)
     part = pt.build_local_part(rank, ranges, xyz2, tets=tets, free_dofs=free)
+    own = part.owned_global_dofs(3)
     ctx.close()
     ctx = make_ctx(part, m.mat_kind, m.mat_params, rank, world, local_rank)
     Fg = mg.global_face_load(mesh2.n_nodes, mesh2.xyz, mesh2.faces["x1"], (-1.0, 0.0, 0.0)).reshape(-1, 3)[order].ravel()
