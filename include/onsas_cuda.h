@@ -106,7 +106,8 @@ int32_t onsas_set_tets(onsas_ctx* ctx, int64_t n, const int32_t* conn, const int
 /* conn: 2 x n; area[n] = area(cross_section(e)).  Entities/Trusses.jl:54-72. */
 int32_t onsas_set_trusses(onsas_ctx* ctx, int64_t n, const int32_t* conn, const int32_t* mat_id, const double* area,
                           int32_t strain_model);
-/* free dofs of the owned nodes (Structures.jl:129-142 free_dofs), any order, local numbering.
+/* free dofs of the owned nodes (Structures.jl:129-142 free_dofs), any order, local numbering (multi-GPU: free dofs of
+ * halo nodes may be listed too, so that the solver updates U on them exactly like their owner does).
  * n_free_global = number of free dofs of the whole structure (= n_free on one GPU); it is the CG
  * default maxiter (StructuralSolvers.jl:229-234). */
 int32_t onsas_set_free_dofs(onsas_ctx* ctx, int64_t n_free, const int64_t* free_dofs, int64_t n_free_global);
@@ -182,7 +183,9 @@ int32_t onsas_newton_step(onsas_ctx* ctx, int32_t precond, double cg_reltol, dou
                           onsas_step_info* info);
 
 /* step! without the assembly: residual, solve, update, norms on the K / F_int already assembled.
- * update_U = 0 leaves U untouched (dU still available through onsas_get_dU). */
+ * update_U = 0 leaves U untouched (dU still available through onsas_get_dU); 1: U[free] += dU (the Newton update);
+ * 2: the step! of a LinearStaticAnalysis (LinearStaticAnalyses.jl:117-153): r = F_ext[free] (F_int is not subtracted),
+ * U[free] = dU. */
 int32_t onsas_step(onsas_ctx* ctx, int32_t precond, double cg_reltol, double cg_abstol, int64_t cg_maxiter,
                    int32_t update_U, onsas_step_info* info);
 

@@ -597,7 +597,8 @@ __device__ __forceinline__ double cg_epilogue_body(const CgArgs& A, int64_t gtid
     for (int64_t i = gtid; i < A.n; i += gsz) {
         const double dx = A.x[i];
         dd += dx * dx;
-        if (A.update_U) A.U[i] += dx;  // NonLinearStaticAnalyses.jl:144 (x is zero at fixed dofs)
+        if (A.update_U == 1) A.U[i] += dx;  // NonLinearStaticAnalyses.jl:144 (x is zero at fixed dofs)
+        else if (A.update_U == 2 && (A.mask[i] & 1)) A.U[i] = dx;  // LinearStaticAnalyses.jl:151-152: U[free] = dU
     }
     return dd;
 }
@@ -824,8 +825,11 @@ __global__ void __launch_bounds__(CG_THREADS, MINB) cg_persistent(CgArgs A, P2PA
     }
 
     double dd = cg_epilogue_body(A, gtid, gsz);
-    if (mg && A.update_U)
-        for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) A.U[i] += A.x[i];
+    if (mg && A.update_U)  // halo dofs: the same update as on their owner (the mask carries the free bit of halo dofs too)
+        for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) {
+            if (A.update_U == 1) A.U[i] += A.x[i];
+            else if (A.mask[i] & 1) A.U[i] = A.x[i];
+        }
     dd = block_sum<CG_THREADS>(dd, sh);
     if (threadIdx.x == 0) part[P_DD * ps + blockIdx.x] = dd;
     grid.sync();
@@ -1777,8 +1781,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     if (!is_producer && n_my > 0)
         for (int k = 0; k < D; ++k, ++q_done) mbar_wait(&full[cw][q_done % D], (uint32_t)((q_done / D) & 1), A.err);
 
-    if (mg && A.update_U)
-        for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) A.U[i] += A.x[i];
+    if (mg && A.update_U)  // halo dofs: the same update as on their owner (the mask carries the free bit of halo dofs too)
+        for (int64_t i = A.n + gtid; i < A.n + P.n_halo_dofs; i += gsz) {
+            if (A.update_U == 1) A.U[i] += A.x[i];
+            else if (A.mask[i] & 1) A.U[i] = A.x[i];
+        }
     double dd1[1] = {block_sum<ST_THREADS>(cg_epilogue_body(A, gtid, gsz), sh)};
     grid_reduce(dd1);
     if (mg) p2p_allreduce<1>(P, dd1, repoch, sh4);

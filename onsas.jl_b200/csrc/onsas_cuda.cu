@@ -1161,12 +1161,15 @@ int32_t onsas_set_free_dofs(onsas_ctx* c, int64_t n_free, const int64_t* free_do
     return guard(c, [&] {
         require(c->have_nodes, ONSAS_ERR_NOT_READY, "onsas_set_nodes must be called first");
         require(n_free >= 0 && (n_free == 0 || free_dofs), ONSAS_ERR_INVALID_ARG, "bad free dof list");
-        const int64_t nd = c->n_own_dofs();
-        c->h_mask.assign((size_t)c->n_local_dofs(), 0);
-        for (int64_t k = 0; k < n_free; ++k) {
-            require(free_dofs[k] >= 0 && free_dofs[k] < nd, ONSAS_ERR_INVALID_ARG, "free dof out of the owned range");
+        const int64_t nd = c->n_own_dofs(), nl = c->n_local_dofs();
+        c->h_mask.assign((size_t)nl, 0);
+        int64_t n_own_free = 0;
+        for (int64_t k = 0; k < n_free; ++k) {  // dofs of halo nodes may be listed too: the solver then updates U on them like their owner does
+            require(free_dofs[k] >= 0 && free_dofs[k] < nl, ONSAS_ERR_INVALID_ARG, "free dof out of range");
             c->h_mask[free_dofs[k]] = 1;
+            n_own_free += free_dofs[k] < nd ? 1 : 0;
         }
+        n_free = n_own_free;
         c->n_free = n_free;
         c->n_free_global = n_free_global > 0 ? n_free_global : n_free;
         c->have_free = true;
@@ -1505,6 +1508,7 @@ static void step_launch(onsas_ctx* c, bool assemble, int32_t precond, double rel
     if (assemble) launch_assemble(c);
     CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
     CgArgs A = make_cg_args(c, precond, reltol, abstol, maxiter, false, update_U);
+    if (update_U == 2) A.rhs = c->Fext.p;  // the step! of a LinearStaticAnalysis: r = F_ext[free], U[free] = dU (LinearStaticAnalyses.jl:117-153)
     run_cg(c, A);
     CUDA_CHECK(cudaEventRecord(c->ev[2], c->stream));
 }
@@ -1533,7 +1537,10 @@ int32_t onsas_newton_step(onsas_ctx* c, int32_t precond, double cg_reltol, doubl
 int32_t onsas_step(onsas_ctx* c, int32_t precond, double cg_reltol, double cg_abstol, int64_t cg_maxiter, int32_t update_U,
                    onsas_step_info* info) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
-    return guard(c, [&] { step_impl(c, false, precond, cg_reltol, cg_abstol, cg_maxiter, update_U ? 1 : 0, info); });
+    return guard(c, [&] {
+        require(update_U >= 0 && update_U <= 2, ONSAS_ERR_INVALID_ARG, "update_U must be 0, 1 or 2");
+        step_impl(c, false, precond, cg_reltol, cg_abstol, cg_maxiter, update_U, info);
+    });
 }
 
 int32_t onsas_pcg(onsas_ctx* c, const double* b, double* x, int32_t precond, double reltol, double abstol, int64_t maxiter,

@@ -221,6 +221,9 @@ void build_local_part(const Partition& P, int rank, LocalPart& L) {
     for (int64_t g = lo; g < hi; ++g)
         for (int d = 0; d < dim; ++d)
             if (P.free_mask[(size_t)g * dim + d]) L.free_dofs.push_back((g - lo) * dim + d);
+    for (size_t h = 0; h < halo.size(); ++h)  // and of the halo nodes (after the owned ones): the solver updates U there too
+        for (int d = 0; d < dim; ++d)
+            if (P.free_mask[(size_t)halo[h] * dim + d]) L.free_dofs.push_back((L.n_owned + (int64_t)h) * dim + d);
     L.n_free_global = P.n_free;
 }
 

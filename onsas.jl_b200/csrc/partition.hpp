@@ -49,7 +49,7 @@ struct LocalPart {
     std::vector<int32_t> tets, tet_mat, trusses, truss_mat;   // local node ids
     std::vector<int64_t> tet_global, truss_global;            // global element id of each local element (ascending)
     std::vector<double> area;
-    std::vector<int64_t> free_dofs; // local dofs of owned nodes that are free
+    std::vector<int64_t> free_dofs; // local dofs that are free: those of the owned nodes first, then those of the halo nodes
     int64_t n_free_global = 0;
     std::vector<int32_t> nbr_rank;  // neighbours, ascending
     std::vector<int64_t> send_ptr, recv_ptr;   // [n_nbr+1]

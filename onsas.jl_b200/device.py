@@ -213,6 +213,7 @@ class DeviceContext:
         if cg_reltol is None:
             cg_reltol = float(np.sqrt(np.finfo(np.float64).eps))
         info = L.StepInfo()
+        # update_U: False / 0 = leave U, True / 1 = U[free] += dU, 2 = the linear-analysis step (r = F_ext[free], U[free] = dU)
         self._check(self._lib.onsas_step(self._h, precond, cg_reltol, cg_abstol, cg_maxiter, int(update_U), C.byref(info)))
         return info
 

@@ -18,7 +18,8 @@ using ..Utils, ..Nodes, ..Entities, ..Tetrahedrons, ..Trusses, ..CrossSections
 using ..Materials, ..SVKMaterial, ..NeoHookeanMaterial, ..IsotropicLinearElasticMaterial
 using ..Meshes, ..Structures, ..StructuralBoundaryConditions
 using ..StructuralSolvers, ..Solvers, ..Solutions
-using ..StructuralAnalyses, ..StaticStates, ..StaticAnalyses, ..NonLinearStaticAnalyses
+using ..StructuralAnalyses, ..StaticStates, ..StaticAnalyses, ..NonLinearStaticAnalyses, ..LinearStaticAnalyses
+using ..BoundaryConditions, ..LocalLoadBoundaryConditions, ..TriangularFaces
 
 import ..StructuralSolvers: _solve!, tolerances
 
@@ -34,9 +35,16 @@ const ONSAS_ERR_NEGATIVE_VOLUME = Int32(2)
 "Device-resident analogue of FullStaticState (StaticStates.jl:33-102): an opaque onsas_ctx*."
 mutable struct CudaContext
     handle::Ptr{Cvoid}
-    function CudaContext(device::Integer = 0)
+    function CudaContext(device::Union{Integer, AbstractVector{<:Integer}} = 0)
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        st = ccall((:onsas_create, LIB[]), Int32, (Int32, Ref{Ptr{Cvoid}}), device, h)
+        st = if device isa Integer
+            ccall((:onsas_create, LIB[]), Int32, (Int32, Ref{Ptr{Cvoid}}), device, h)
+        else
+            # one Julia process drives all the listed devices: global mesh and global vectors in, the partitioning,
+            # the halo plan and the peer-memory wiring happen inside onsas_finalize_mesh (onsas_create_multi)
+            devs = collect(Int32, device)
+            GC.@preserve devs ccall((:onsas_create_multi, LIB[]), Int32, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), devs, length(devs), h)
+        end
         st == ONSAS_OK || error(unsafe_string(ccall((:onsas_last_error, LIB[]), Cstring, (Ptr{Cvoid},), C_NULL)))
         ctx = new(h[])
         finalizer(c -> (c.handle != C_NULL && ccall((:onsas_destroy, LIB[]), Int32, (Ptr{Cvoid},), c.handle);
@@ -65,7 +73,7 @@ Base.@kwdef struct NewtonRaphsonCUDA <: AbstractSolver
     cg_reltol::Float64 = sqrt(eps())    # StructuralSolvers.jl:229-234
     cg_abstol::Float64 = 0.0
     cg_maxiter::Int = 0                 # 0 -> number of free dofs
-    device::Int = 0
+    device::Union{Int, Vector{Int}} = 0 # one CUDA device, or several: `device = collect(0:7)` runs the same solve on 8 GPUs
 end
 NewtonRaphsonCUDA(tol::ConvergenceSettings; kw...) = NewtonRaphsonCUDA(; tol, kw...)
 precond_code(alg::NewtonRaphsonCUDA) = Int32(alg.preconditioner === :none ? 0 : alg.preconditioner === :two_level ? 2 : 1)
@@ -115,7 +123,10 @@ function upload!(ctx::CudaContext, s::AbstractStructure)
                 append!(tets, ids); push!(tet_mat, mi - 1); push!(tet_elems, e)
             elseif e isa Truss
                 append!(bars, ids); push!(bar_mat, mi - 1); push!(areas, area(cross_section(e))); push!(bar_elems, e)
-                strain = strain_code(strain_model(e))
+                sc = strain_code(strain_model(e))
+                isempty(bar_mat) || length(bar_mat) == 1 || sc == strain ||
+                    error("libonsas_cuda evaluates all trusses of a structure with one strain model")
+                strain = sc
             else
                 error("element type $(typeof(e)) is outside the GPU hot path")
             end
@@ -132,7 +143,7 @@ function upload!(ctx::CudaContext, s::AbstractStructure)
         check(ctx, ccall((:onsas_set_free_dofs, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Int64), h, length(free0), free0, length(free0)))
         check(ctx, ccall((:onsas_finalize_mesh, LIB[]), Int32, (Ptr{Cvoid},), h))
     end
-    tet_elems, bar_elems
+    tet_elems, bar_elems, node_index
 end
 
 # mirror of onsas_step_info
@@ -144,10 +155,11 @@ end
 "Copy device results into the reference's state so that store!, Solution accessors and write_vtk keep working."
 function download!(ctx::CudaContext, state::FullStaticState, tet_elems, bar_elems)
     h = ctx.handle
-    U = displacements(state); Fint = internal_forces(state)
-    GC.@preserve U Fint begin
+    U = displacements(state); Fint = internal_forces(state); Fext = external_forces(state)
+    GC.@preserve U Fint Fext begin
         check(ctx, ccall((:onsas_get_U, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), h, U))
         check(ctx, ccall((:onsas_get_Fint, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), h, Fint))
+        check(ctx, ccall((:onsas_get_Fext, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), h, Fext))   # built on the device when the loads are face loads
     end
     for (family, elems) in ((Int32(0), tet_elems), (Int32(1), bar_elems))
         isempty(elems) && continue
@@ -161,24 +173,27 @@ function download!(ctx::CudaContext, state::FullStaticState, tet_elems, bar_elem
 end
 
 """
-Optional device-side `apply!` (SURVEY 8f-1): registers one load pattern per `Pressure` BC and one per component of a
-`GlobalLoad` BC whose entities are all `TriangularFace`s; returns the closures `t -> factor` in pattern order, or
-`nothing` when some load is not a face load (the host `apply!` + `onsas_set_Fext` path is used then).
+Device-side `apply!` (SURVEY 8f-1): registers one load pattern per `Pressure` BC and one per component of a `GlobalLoad` BC
+whose entities are all `TriangularFace`s; returns the closures `t -> factor` in pattern order, or `nothing` when some load
+is not a face load (the host `apply!` + `onsas_set_Fext` path is used then).  `node_index` is the 0-BASED node -> id map that
+`upload!` returns (the ids the C ABI uses).
 """
 function register_loads!(ctx::CudaContext, s::AbstractStructure, node_index::AbstractDict)
     factors = Function[]
-    for (bc, ents) in pairs(load_bcs(boundary_conditions(s)))
-        all(e -> e isa TriangularFace, ents) || return nothing
-        tri = Int32[node_index[n] - 1 for e in ents for n in nodes(e)]          # 3 x n_faces, 0-based
+    lbcs = load_bcs(boundary_conditions(s))
+    all(ents -> all(e -> e isa TriangularFace, ents), values(lbcs)) || return nothing   # decide before anything is registered
+    for (bc, ents) in pairs(lbcs)
+        tri = Int32[node_index[n] for e in ents for n in nodes(e)]              # 3 x n_faces, already 0-based
         pid = Ref{Int32}(-1)
         if bc isa Pressure
-            GC.@preserve tri check(ctx, ccall((:onsas_add_face_load, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Int32}, Int32, Ptr{Float64}, Ref{Int32}),
-                ctx.handle, length(ents), tri, Int32(1), [1.0, 0.0, 0.0], pid))
+            vals = [1.0, 0.0, 0.0]
+            GC.@preserve tri vals check(ctx, ccall((:onsas_add_face_load, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Int32}, Int32, Ptr{Float64}, Ref{Int32}),
+                ctx.handle, length(ents), tri, Int32(1), vals, pid))
             push!(factors, t -> bc(t))
         else
             for c in 1:3
                 e_c = [Float64(c == k) for k in 1:3]
-                GC.@preserve tri check(ctx, ccall((:onsas_add_face_load, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Int32}, Int32, Ptr{Float64}, Ref{Int32}),
+                GC.@preserve tri e_c check(ctx, ccall((:onsas_add_face_load, LIB[]), Int32, (Ptr{Cvoid}, Int64, Ptr{Int32}, Int32, Ptr{Float64}, Ref{Int32}),
                     ctx.handle, length(ents), tri, Int32(0), e_c, pid))
                 push!(factors, t -> bc(t)[c])
             end
@@ -187,12 +202,27 @@ function register_loads!(ctx::CudaContext, s::AbstractStructure, node_index::Abs
     factors
 end
 
+"`apply!(sa, load_bcs)` of this load step: on the device when every load is a face load, else on the host (StructuralAnalyses.jl:228-241)."
+function apply_loads!(ctx::CudaContext, sa, factors)
+    state = current_state(sa)
+    if factors === nothing
+        external_forces(state) .= 0
+        apply!(sa, load_bcs(boundary_conditions(structure(sa))))
+        Fext = external_forces(state)
+        GC.@preserve Fext check(ctx, ccall((:onsas_set_Fext, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.handle, Fext))
+    else
+        f = Float64[g(current_time(sa)) for g in factors]
+        GC.@preserve f check(ctx, ccall((:onsas_apply_loads, LIB[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), ctx.handle, length(f), f))
+    end
+end
+
 "Drop-in replacement of `_solve!(::NonLinearStaticAnalysis, ::AbstractSolver, ...)` (NonLinearStaticAnalyses.jl:70-104)."
 function _solve!(sa::NonLinearStaticAnalysis, alg::NewtonRaphsonCUDA, linear_solver::LinearSolver = nothing;
         linear_solve_inplace::Bool = false)
     s = structure(sa)
     ctx = CudaContext(alg.device)                    # created lazily here: `solve` has already deep-copied `sa`
-    tet_elems, bar_elems = upload!(ctx, s)
+    tet_elems, bar_elems, node_index = upload!(ctx, s)
+    factors = register_loads!(ctx, s, node_index)    # device-side F_ext when every load is a face load
     state = current_state(sa)
     U = displacements(state)
     GC.@preserve U check(ctx, ccall((:onsas_set_U, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.handle, U))
@@ -201,10 +231,7 @@ function _solve!(sa::NonLinearStaticAnalysis, alg::NewtonRaphsonCUDA, linear_sol
     while !is_done(sa)
         step = sa.current_step
         reset!(current_iteration(sa))                                            # :83
-        external_forces(state) .= 0
-        apply!(sa, load_bcs(boundary_conditions(s)))                             # :86-87, stays on the host
-        Fext = external_forces(state)
-        GC.@preserve Fext check(ctx, ccall((:onsas_set_Fext, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.handle, Fext))
+        apply_loads!(ctx, sa, factors)                                           # :86-87
         while isconverged!(current_iteration(sa), tolerances(alg)) isa NotConvergedYet   # :90
             # assemble!(s, sa) + step!(sa, alg, linear_solver) in one call (:92-95, :107-148)
             check(ctx, ccall((:onsas_newton_step, LIB[]), Int32, (Ptr{Cvoid}, Int32, Float64, Float64, Int64, Ref{StepInfo}),
@@ -215,6 +242,43 @@ function _solve!(sa::NonLinearStaticAnalysis, alg::NewtonRaphsonCUDA, linear_sol
         download!(ctx, state, tet_elems, bar_elems)
         store!(sol, state, step)                                                 # :98
         next!(sa)                                                                # :101
+    end
+    sol
+end
+
+"""
+Drop-in replacement of `_solve!(::LinearStaticAnalysis, ::Nothing, linear_solver)` (LinearStaticAnalyses.jl:78-113) in the
+reference's own sequence: K assembled at the first load step only (:93-96), `step!` (:117-153) = `onsas_step` with
+`update_U = 2` (r = F_ext[free], U[free] = dU), then `assemble!` again for stress / strain (:101-102).
+Usage: `solve!(LinearStaticAnalysis(s; NSTEPS), NewtonRaphsonCUDA())`.
+"""
+function _solve!(sa::LinearStaticAnalysis, alg::NewtonRaphsonCUDA, linear_solver::LinearSolver = nothing;
+        linear_solve_inplace::Bool = false)
+    s = structure(sa)
+    ctx = CudaContext(alg.device)
+    tet_elems, bar_elems, node_index = upload!(ctx, s)
+    factors = register_loads!(ctx, s, node_index)
+    state = current_state(sa)
+    U0 = copy(displacements(state))
+    GC.@preserve U0 check(ctx, ccall((:onsas_set_U, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.handle, U0))
+    k_is_constant = isempty(bar_elems) && all(m -> m isa IsotropicLinearElastic, keys(materials(s)))
+    sol = Solution(sa, alg)
+    info = Ref{StepInfo}()
+    while !is_done(sa)
+        step = sa.current_step
+        apply_loads!(ctx, sa, factors)                                           # :89-90
+        if step == 1 || !k_is_constant
+            # :93-96 K of the initial state.  The reference solves later steps with the copy it froze at step 1; the device
+            # holds one K, so a K that depends on U is re-evaluated at the initial state (same matrix, same result)
+            step == 1 || GC.@preserve U0 check(ctx, ccall((:onsas_set_U, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.handle, U0))
+            check(ctx, ccall((:onsas_assemble, LIB[]), Int32, (Ptr{Cvoid},), ctx.handle))
+        end
+        check(ctx, ccall((:onsas_step, LIB[]), Int32, (Ptr{Cvoid}, Int32, Float64, Float64, Int64, Int32, Ref{StepInfo}),
+            ctx.handle, precond_code(alg), alg.cg_reltol, alg.cg_abstol, alg.cg_maxiter, Int32(2), info))   # :99
+        check(ctx, ccall((:onsas_assemble, LIB[]), Int32, (Ptr{Cvoid},), ctx.handle))                       # :101-102
+        download!(ctx, state, tet_elems, bar_elems)
+        store!(sol, state, step)                                                 # :105
+        next!(sa)                                                                # :108
     end
     sol
 end

@@ -58,7 +58,7 @@ class LocalPart:
     truss_global: np.ndarray
     truss_mat: np.ndarray
     truss_area: np.ndarray
-    free_dofs: np.ndarray         # local dofs of owned nodes that are free
+    free_dofs: np.ndarray         # free local dofs: of the owned nodes first, then of the halo nodes
     n_free_global: int
     nbr_rank: np.ndarray          # neighbours, ascending
     send_ptr: np.ndarray
@@ -132,6 +132,8 @@ def build_local_part(rank: int, ranges: np.ndarray, xyz: np.ndarray, tets=None, 
     fmask = np.zeros(xyz.shape[0] * dim, bool)
     fmask[free_dofs] = True
     own_free = np.nonzero(fmask[lo * dim: hi * dim])[0].astype(np.int64)  # local dof = global dof - lo*dim
+    halo_free = np.nonzero(fmask.reshape(-1, dim)[halo].ravel())[0].astype(np.int64) + (hi - lo) * dim
+    own_free = np.concatenate([own_free, halo_free])   # halo dofs after the owned ones: the solver updates U there too
     return LocalPart(
         rank=rank, n_ranks=n_ranks, n_owned=hi - lo, local_to_global=l2g, xyz=np.ascontiguousarray(xyz[l2g]),
         tets=lut[tets[te]].astype(np.int32).reshape(-1, 4), tet_global=te,

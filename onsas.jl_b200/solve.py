@@ -309,22 +309,31 @@ def _solve_nonlinear(sa: NonLinearStaticAnalysis, alg: NewtonRaphson) -> Solutio
 
 
 def _solve_linear(sa: LinearStaticAnalysis, alg: NewtonRaphson) -> Solution:
-    """_solve!(::LinearStaticAnalysis, ...) (LinearStaticAnalyses.jl:78-153): K assembled once at U = 0,
-    one linear solve per load step (U = K \\ F_ext(t)), elements re-evaluated at U for stress / strain."""
+    """_solve!(::LinearStaticAnalysis, ...) (LinearStaticAnalyses.jl:78-153) in the reference's own sequence: K is assembled
+    at the FIRST load step only (:93-96); every step solves K dU = F_ext(t)[free] and SETS U[free] = dU (step!, :117-153:
+    onsas_step with update_U = 2), then the elements are re-evaluated at U for stress / strain (:101-102).  The reference
+    solves with the copy of K it froze at step 1; the device holds one K, so when K depends on U (a hyperelastic material in
+    a linear analysis) it is re-evaluated at the initial state before each later solve -- the same matrix, hence the same
+    result; for IsotropicLinearElastic K does not depend on U and nothing is re-assembled."""
     s = sa.s
     ctx = sa.device_context(alg.device)
     sol = Solution(sa, alg)
-    n = s.flat.n_dofs
+    U0 = ctx.get_U()
+    k_is_constant = all(int(k) == L.MAT_ISOLINEAR for k in s.flat.mat_kind) and len(s.flat.trusses) == 0
+    first = True
     while not sa.is_done():
-        ctx.set_U(np.zeros(n))
-        ctx.assemble()                                   # tangent at U = 0; F_int = 0
-        s.flat.apply_loads(ctx, sa.current_time())
-        info = ctx.step(alg.precond_code, alg.cg_reltol, alg.cg_abstol, alg.cg_maxiter, update_U=True)
-        ctx.assemble()                                   # stress / strain / F_int at the solved U (:123-131)
+        s.flat.apply_loads(ctx, sa.current_time())       # :89-90
+        if first or not k_is_constant:
+            if not first:
+                ctx.set_U(U0)
+            ctx.assemble()                               # :93-96 K at the initial state
+        info = ctx.step(alg.precond_code, alg.cg_reltol, alg.cg_abstol, alg.cg_maxiter, update_U=2)   # :99, :117-153
+        ctx.assemble()                                   # stress / strain / F_int at the solved U (:101-102)
         ctx.synchronize()
         _store(sol, ctx, sa)
         sol._iterations.append(1)
         sol._criteria.append(ResidualForceCriterion())   # LinearResidualsIterationStep reset! :128-132
         sol.cg_iterations.append([int(info.cg_iters)])
         sa.next()
+        first = False
     return sol
