@@ -79,6 +79,12 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_HOST_MID_WEIGHT 9  /* onsas_assemble_host: size of an inner slice range relative to the first / last one (default 3) */
 #define ONSAS_OPT_COARSE_RBM 10      /* two-level preconditioner in 3D: 1 = rigid-body rotations of every aggregate join the coarse space (default), 0 = translations only */
 #define ONSAS_OPT_HOST_STREAMS 12     /* onsas_assemble_host: compute streams consecutive slice ranges alternate on (1 or 2, default 2) */
+#define ONSAS_OPT_REORDER 13         /* set before onsas_finalize_mesh: 1 = the nodes are renumbered along the Z-curve of their coordinates inside the
+                                        library (per device on a multi-device context), so that an arbitrary caller numbering (a Gmsh mesh,
+                                        Interfaces/Gmsh.jl:25-83) gets the slice locality of a structured one; invisible to the caller: every vector,
+                                        dof list, face list and result stays in the caller's numbering.  2 = aggregate-major: the nodes of every aggregate of the
+                                        two-level preconditioner are numbered consecutively (Z-curve inside an aggregate), so its aggregate-ordered
+                                        passes stream through memory.  0 (default) keeps the caller's order */
 #define ONSAS_OPT_COARSE_FUSED 11    /* two-level preconditioner: 1 = residual update in aggregate order, fused with w = Z^T r (default), 0 = separate pass */
 
 /* ---------------------------------------------------------------- life cycle */
@@ -245,7 +251,7 @@ int32_t onsas_device_count(onsas_ctx* ctx); /* 1 for onsas_create, ndev for onsa
 typedef struct onsas_part onsas_part;
 int32_t onsas_part_create(int32_t dim, int64_t n_nodes, const double* xyz, int64_t n_tets, const int32_t* tets, const int32_t* tet_mat,
                           int64_t n_trusses, const int32_t* trusses, const int32_t* truss_mat, const double* area, int64_t n_free,
-                          const int64_t* free_dofs, int32_t n_ranks, onsas_part** part);
+                          const int64_t* free_dofs, int32_t n_ranks, int32_t reorder /* see ONSAS_OPT_REORDER */, onsas_part** part);
 int32_t onsas_part_destroy(onsas_part* part);
 int32_t onsas_part_sizes(onsas_part* part, int32_t rank, int64_t out[8]);
 int32_t onsas_part_local_to_global(onsas_part* part, int32_t rank, int32_t* l2g);

@@ -22,6 +22,7 @@ FAMILY_TET, FAMILY_TRUSS = 0, 1
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_TWO_LEVEL = 0, 1, 2
 OPT_CG_MODE, OPT_ASM_MINBLOCKS, OPT_CG_CHECK_EVERY, OPT_CG_BLOCKS_PER_SM, OPT_CG_PROFILE, OPT_FORCE_MG = 1, 2, 3, 4, 5, 6
 OPT_HOST_CHUNKS, OPT_GJ_BLOCKED, OPT_HOST_MID_WEIGHT, OPT_COARSE_RBM, OPT_COARSE_FUSED, OPT_HOST_STREAMS = 7, 8, 9, 10, 11, 12
+OPT_REORDER = 13
 
 
 class StepInfo(C.Structure):
@@ -77,7 +78,7 @@ SIGNATURES = {
     "onsas_create_multi": (C.c_int32, [_i32p, C.c_int32, C.POINTER(_vp)]),
     "onsas_device_count": (C.c_int32, [_vp]),
     "onsas_part_create": (C.c_int32, [C.c_int32, C.c_int64, _dp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp,
-                                      C.c_int32, C.POINTER(_vp)]),
+                                      C.c_int32, C.c_int32, C.POINTER(_vp)]),
     "onsas_part_destroy": (C.c_int32, [_vp]),
     "onsas_part_sizes": (C.c_int32, [_vp, C.c_int32, _i64p]),
     "onsas_part_local_to_global": (C.c_int32, [_vp, C.c_int32, _i32p]),

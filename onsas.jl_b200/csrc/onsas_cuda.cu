@@ -198,6 +198,8 @@ struct onsas_ctx {
         size_t smem = 0;
     } st_plan;
     int force_mg = 0;  // diagnostics: run the multi-GPU kernel even with one rank
+    int reorder = 0;   // ONSAS_OPT_REORDER: 1 = the nodes are renumbered along a Z-curve inside onsas_finalize_mesh (invisible to the caller)
+    std::vector<std::pair<int32_t, int64_t>> opt_log;  // options in the order they were set (replayed on the device contexts of a group)
 
     // comm
     ncclComm_t comm = nullptr;
@@ -209,6 +211,7 @@ struct onsas_ctx {
     std::vector<void*> ipc_opened;
     bool p2p_ready = false;
     std::vector<int32_t> h_send_nodes;
+    std::vector<int32_t> h_agg_ptr;        // aggregate-major numbering: owned-node ranges of the preconditioner's aggregates (else empty)
     std::vector<int64_t> remote_halo_off;  // per neighbour: where this rank's values start inside ITS halo (contexts loaded from a partition)
     // device-side load patterns (unit nodal vectors of the load boundary conditions), n_local_dofs each
     DevBuf<double> patterns, factors;
@@ -387,6 +390,7 @@ void grp_set_option(onsas_ctx* g, int32_t key, int64_t value);
 void grp_materials_changed(onsas_ctx* g);
 void grp_free_dofs_changed(onsas_ctx* g);
 void grp_finalize(onsas_ctx* g);
+void grp_wrap_single(onsas_ctx* g);
 void grp_set_vec(onsas_ctx* g, int which, const double* v);
 void grp_get_vec(onsas_ctx* g, int which, double* v);
 void grp_add_face_load(onsas_ctx* g, int64_t n_faces, const int32_t* tri, int32_t kind, const double* values, int32_t* pattern_id);
@@ -719,8 +723,8 @@ void launch_stream(onsas_ctx* c, CgArgs A) {
 }
 
 // ---------------------------------------------------------------- two-level preconditioner: aggregates + coarse inverse
-constexpr int CO_NC_MAX = 1536;     // coarse dofs: the dense inverse (18.9 MB) stays in L2 and fits the Gauss-Jordan kernel's shared memory
-constexpr int CO_TARGET_NODES = 343;  // nodes per aggregate (7^3) when the mesh is large enough
+constexpr int CO_NC_MAX = COARSE_NC_MAX;  // partition.hpp (the partitioner cuts the same aggregates when it numbers aggregate-major)
+constexpr int CO_TARGET_NODES = COARSE_TARGET_NODES;
 
 // k-way recursive coordinate bisection of the owned nodes (deterministic: ties broken by node id)
 void rcb_aggregate(const double* xyz, int dim, std::vector<int32_t>& ids, size_t lo, size_t hi, int parts, int first, std::vector<int32_t>& agg) {
@@ -755,8 +759,15 @@ void build_coarse(onsas_ctx* c) {
     const int cd = (c->dim == 3 && c->coarse_rbm) ? 6 : c->dim;
     int n_agg = (int)std::max<int64_t>(1, std::min<int64_t>(n / CO_TARGET_NODES, CO_NC_MAX / cd));
     std::vector<int32_t> ids((size_t)n), agg((size_t)n, 0);
-    for (int64_t i = 0; i < n; ++i) ids[i] = (int32_t)i;
-    rcb_aggregate(c->h_xyz.data(), c->dim, ids, 0, (size_t)n, n_agg, 0, agg);
+    if (!c->h_agg_ptr.empty() && c->h_agg_ptr.back() == n && (int)(c->h_agg_ptr.size() - 1) * cd <= CO_NC_MAX) {
+        // aggregate-major numbering (ONSAS_OPT_REORDER = 2): the partitioner already cut the aggregates, they are node ranges
+        n_agg = (int)c->h_agg_ptr.size() - 1;
+        for (int a = 0; a < n_agg; ++a)
+            for (int32_t i = c->h_agg_ptr[a]; i < c->h_agg_ptr[a + 1]; ++i) agg[i] = a;
+    } else {
+        for (int64_t i = 0; i < n; ++i) ids[i] = (int32_t)i;
+        rcb_aggregate(c->h_xyz.data(), c->dim, ids, 0, (size_t)n, n_agg, 0, agg);
+    }
     std::vector<int32_t> ptr((size_t)n_agg + 1, 0), nodes((size_t)n);
     for (int64_t i = 0; i < n; ++i) ptr[agg[i] + 1]++;
     for (int a = 0; a < n_agg; ++a) ptr[a + 1] += ptr[a];
@@ -1062,9 +1073,14 @@ int32_t onsas_destroy(onsas_ctx* c) {
 int32_t onsas_set_stream(onsas_ctx* c, void* s) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
-        require(!c->grp, ONSAS_ERR_UNSUPPORTED, "a multi-device context runs on its own streams (one per device)");
+        require(!c->grp || c->grp->sub.size() == 1, ONSAS_ERR_UNSUPPORTED, "a multi-device context runs on its own streams (one per device)");
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         c->stream = s ? (cudaStream_t)s : c->own_stream;
+        if (c->grp) {  // a renumbered single-device context: its device context does the work
+            onsas_ctx* d = c->grp->sub[0];
+            CUDA_CHECK(cudaStreamSynchronize(d->stream));
+            d->stream = s ? (cudaStream_t)s : d->own_stream;
+        }
     });
 }
 
@@ -1084,9 +1100,11 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_HOST_MID_WEIGHT: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "weight must be 1..64"); c->host_mid_weight = (int)value; c->hp.built = false; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
+            case ONSAS_OPT_REORDER: require(value >= 0 && value <= 2, ONSAS_ERR_INVALID_ARG, "reorder must be 0, 1 or 2"); require(!c->finalized, ONSAS_ERR_INVALID_ARG, "ONSAS_OPT_REORDER must be set before onsas_finalize_mesh"); c->reorder = (int)value; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
         }
-        if (c->grp) grp_set_option(c, key, value);
+        c->opt_log.emplace_back(key, value);
+        if (c->grp && key != ONSAS_OPT_REORDER) grp_set_option(c, key, value);
     });
 }
 
@@ -1102,6 +1120,8 @@ int32_t onsas_set_nodes(onsas_ctx* c, int64_t n_nodes, int64_t n_owned, int32_t 
         c->n_nodes = n_nodes;
         c->n_owned = n_owned;
         c->h_xyz.assign(xyz, xyz + n_nodes * dim);
+        c->h_agg_ptr.clear();
+        c->remote_halo_off.clear();
         c->have_nodes = true;
         c->finalized = false;
     });
@@ -1181,6 +1201,7 @@ int32_t onsas_set_free_dofs(onsas_ctx* c, int64_t n_free, const int64_t* free_do
 int32_t onsas_finalize_mesh(onsas_ctx* c) {
     if (!c) return ONSAS_ERR_INVALID_ARG;
     return guard(c, [&] {
+        if (!c->grp && c->reorder && c->n_ranks == 1 && c->n_owned == c->n_nodes) grp_wrap_single(c);
         if (c->grp) return grp_finalize(c);
         require(c->have_nodes, ONSAS_ERR_NOT_READY, "onsas_set_nodes has not been called");
         require(!c->h_mat_kind.empty(), ONSAS_ERR_NOT_READY, "onsas_set_materials has not been called");

@@ -22,6 +22,12 @@
 namespace onsas {
 
 constexpr int PART_MAX_RANKS = 16;
+// size of the coarse space of the two-level preconditioner (shared with the solver): at most COARSE_NC_MAX coarse dofs
+// per device (the dense inverse, 18.9 MB, stays in L2 and fits the Gauss-Jordan kernel's shared memory), aggregates of
+// about COARSE_TARGET_NODES nodes (7^3) when the mesh is large enough
+constexpr int COARSE_NC_MAX = 1536;
+constexpr int COARSE_TARGET_NODES = 343;
+int coarse_aggregate_count(int64_t n_owned_nodes, int dim);
 
 struct Partition {
     int n_ranks = 0, dim = 3;
@@ -36,6 +42,7 @@ struct Partition {
     std::vector<int32_t> tets, tet_mat, trusses, truss_mat;
     bool tet_has_mat = false, truss_has_mat = false;
     std::vector<double> area;
+    std::vector<std::vector<int32_t>> agg_ptr;  // reorder = 2: per rank, the node ranges (relative to the rank's first node) of its aggregates
     std::vector<uint8_t> free_mask;  // [n_nodes*dim] (new numbering) 1 = free dof
     int64_t n_free = 0;
     int owner_of(int64_t new_id) const;
@@ -55,12 +62,17 @@ struct LocalPart {
     std::vector<int64_t> send_ptr, recv_ptr;   // [n_nbr+1]
     std::vector<int32_t> send_nodes;           // local (owned) node ids grouped by neighbour, ascending global id
     std::vector<int64_t> remote_halo_off;      // [n_nbr] where this rank's values start inside neighbour k's halo (in nodes)
+    std::vector<int32_t> agg_ptr;              // reorder = 2: [n_agg+1] owned-node ranges of the preconditioner's aggregates, else empty
 };
 
 // Returns an empty string on success.  conn arrays are element-major, 0-based original node ids; mat ids may be null.
 std::string build_partition(int dim, int64_t n_nodes, const double* xyz, int64_t n_tets, const int32_t* tets,
                             const int32_t* tet_mat, int64_t n_trusses, const int32_t* trusses, const int32_t* truss_mat,
-                            const double* area, int64_t n_free, const int64_t* free_dofs, int n_ranks, Partition& out);
+                            const double* area, int64_t n_free, const int64_t* free_dofs, int n_ranks, int reorder, Partition& out);
+// reorder: 0 = inside a part the caller's node order is kept (meshes numbered for locality: structured grids, banded
+// numberings); 1 = inside a part the nodes follow the Z-curve of their coordinates (any numbering becomes local);
+// 2 = aggregate-major: the part is cut into the aggregates of the two-level preconditioner, numbered one after the other
+// (Z-curve inside each), and LocalPart::agg_ptr hands their ranges to the solver.
 
 void build_local_part(const Partition& P, int rank, LocalPart& out);
 

@@ -314,7 +314,7 @@ class NativePartition:
     `n_ranks` parts, the halo plan of every rank.  Used by the one-process-per-GPU binding (every process builds the same
     partition and loads its own rank); a multi-device DeviceContext runs the same code inside onsas_finalize_mesh."""
 
-    def __init__(self, xyz, n_ranks: int, tets=None, tet_mat=None, trusses=None, truss_mat=None, truss_area=None, free_dofs=None):
+    def __init__(self, xyz, n_ranks: int, tets=None, tet_mat=None, trusses=None, truss_mat=None, truss_area=None, free_dofs=None, reorder: int = 0):
         self._lib = L.lib()
         xyz = _as(xyz, np.float64)
         if xyz.ndim == 1:
@@ -330,7 +330,7 @@ class NativePartition:
         h = C.c_void_p()
         st = self._lib.onsas_part_create(self.dim, self.n_nodes, xyz.ravel(), 0 if tets is None else len(tets), _ptr(tets), _ptr(tm),
                                          0 if trusses is None else len(trusses), _ptr(trusses), _ptr(bm), _ptr(ar), len(fd), _ptr(fd),
-                                         self.n_ranks, C.byref(h))
+                                         self.n_ranks, int(reorder), C.byref(h))
         if st != L.OK:
             raise OnsasError(st, (self._lib.onsas_last_error(None) or b"").decode())
         self._h = h
@@ -377,10 +377,13 @@ class NativePartition:
 
 
 def context_from_flat(xyz, tets=None, trusses=None, truss_area=None, truss_strain=0, mat_kind=(0,), mat_params=((1.0, 1.0),),
-                      tet_mat=None, truss_mat=None, free_dofs=None, device: int = 0, n_owned=None,
-                      n_free_global: int = 0) -> DeviceContext:
-    """Upload a structure-of-arrays model and finalize it."""
+                      tet_mat=None, truss_mat=None, free_dofs=None, device=0, n_owned=None,
+                      n_free_global: int = 0, reorder: int = 0) -> DeviceContext:
+    """Upload a structure-of-arrays model and finalize it.  `reorder = 1`: the library renumbers the nodes along a Z-curve
+    internally (ONSAS_OPT_REORDER; the caller keeps its own numbering everywhere)."""
     ctx = DeviceContext(device)
+    if reorder:
+        ctx.set_option(L.OPT_REORDER, reorder)
     ctx.set_nodes(xyz, n_owned)
     ctx.set_materials(mat_kind, mat_params)
     if tets is not None and len(tets):

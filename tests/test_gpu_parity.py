@@ -458,3 +458,51 @@ def test_assemble_host_is_bitwise_the_three_call_path(ob, oracle, case):
     ctx.assemble()
     np.testing.assert_array_equal(ctx.pcg(b, ob.PRECOND_JACOBI, 1e-12)[0], x1)
     ctx.close()
+
+
+def test_library_side_reordering_is_invisible_to_the_caller(ob, oracle):
+    """ONSAS_OPT_REORDER = 1 on a randomly numbered mesh (nodes AND elements permuted, as a Gmsh mesh arrives,
+    Interfaces/Gmsh.jl:25-83): the library renumbers along a Z-curve internally; every result comes back in the caller's
+    numbering -- K, F_int, stress / strain bitwise equal to the un-reordered context (entries are summed in element order
+    either way), solves equal to the solver tolerance, device-side loads equal."""
+    m, mesh = cases.box_model(9, 6, 5, mat="neo", jitter=0.1)
+    rng = np.random.default_rng(4)
+    perm, eperm = rng.permutation(mesh.n_nodes), rng.permutation(mesh.n_tets)
+    xyz = np.empty_like(m.xyz)
+    xyz[perm] = m.xyz
+    tets = perm[m.tets[eperm]].astype(np.int32)
+    free = np.sort(perm[m.free_dofs // 3] * 3 + m.free_dofs % 3)
+    kw = dict(tets=tets, mat_kind=m.mat_kind, mat_params=m.mat_params, free_dofs=free)
+    plain = ob.context_from_flat(xyz, **kw)
+    reord = ob.context_from_flat(xyz, reorder=1, **kw)
+    gm = oracle.FlatModel(xyz=xyz, tets=tets, mat_kind=m.mat_kind, mat_params=m.mat_params, free_dofs=free)
+    U = cases.random_U(gm, 0.02)
+    for c in (plain, reord):
+        c.set_U(U)
+        c.assemble()
+    np.testing.assert_array_equal(reord.get_Fint(), plain.get_Fint())
+    for a, b in zip(plain.get_csr(), reord.get_csr()):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(plain.get_stress_strain(), reord.get_stress_strain()):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(reord.assemble_host(U), plain.get_Fint())
+    ref = oracle.Assembly(gm).assemble(U)
+    assert cases.rel_err(reord.get_Fint(), ref.F_int) < 1e-12
+    b = rng.standard_normal(gm.n_dofs)
+    x0, it0, _ = plain.pcg(b, ob.PRECOND_JACOBI, 1e-12)
+    for pre in (ob.PRECOND_JACOBI, ob.PRECOND_TWO_LEVEL):
+        x1, it1, _ = reord.pcg(b, pre, 1e-12)
+        assert np.abs(x1 - x0).max() < 1e-9 * np.abs(x0).max()
+    faces = perm[mesh.faces["x1"]].astype(np.int32)
+    for c in (plain, reord):
+        c.add_face_load(faces, 0, [-1.0, 0.0, 0.0])
+        c.apply_loads([0.4])
+        c.set_U(np.zeros(gm.n_dofs))
+    np.testing.assert_array_equal(reord.get_Fext(), plain.get_Fext())
+    for _ in range(6):
+        i0, i1 = plain.newton_step(ob.PRECOND_JACOBI, 1e-13), reord.newton_step(ob.PRECOND_JACOBI, 1e-13)
+    assert cases.rel_err(reord.get_U(), plain.get_U()) < 1e-9 and i1.norm_r < 1e-8 * i1.norm_Fext
+    st0, st1 = plain.table_stats(), reord.table_stats()
+    assert st1["nnz_blocks"] == st0["nnz_blocks"] and st1["padded_block_slots"] <= st0["padded_block_slots"]
+    for c in (plain, reord):
+        c.close()

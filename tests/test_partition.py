@@ -67,3 +67,31 @@ def test_native_partition_trusses_and_errors(ob):
     bad[0, 0] = lat.n_nodes
     with pytest.raises(ob.OnsasError):
         ob.NativePartition(lat.xyz, 2, trusses=bad)
+
+
+def test_z_curve_reordering_is_a_local_permutation(ob):
+    """reorder = 1 (ONSAS_OPT_REORDER): inside every part the nodes follow the Z-curve of their coordinates -- still a
+    permutation with the same owned SETS as reorder = 0, and a randomly numbered mesh gets back the locality of a structured
+    one: the nodes an 8-row slice touches stay a small neighbourhood."""
+    mesh = mg.box_tet_mesh(16, 16, 16, 1.0, 1.0, 1.0)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(mesh.n_nodes)
+    xyz = np.empty_like(mesh.xyz)
+    xyz[perm] = mesh.xyz
+    tets = perm[mesh.tets].astype(np.int32)
+    for n_ranks in (1, 4):
+        P0 = ob.NativePartition(xyz, n_ranks, tets=tets)
+        P1 = ob.NativePartition(xyz, n_ranks, tets=tets, reorder=1)
+        for r in range(n_ranks):
+            s0, s1 = P0.sizes(r), P1.sizes(r)
+            assert s0 == s1
+            a, b = P0.local_to_global(r), P1.local_to_global(r)
+            no = s0["n_owned"]
+            assert np.array_equal(np.sort(a[:no]), np.sort(b[:no])) and np.array_equal(np.sort(a[no:]), np.sort(b[no:]))
+            np.testing.assert_array_equal(P0.local_elements(r), P1.local_elements(r))   # element order is untouched
+            # locality: mean distance between consecutive owned nodes
+            d0 = np.linalg.norm(np.diff(xyz[a[:no]], axis=0), axis=1).mean()
+            d1 = np.linalg.norm(np.diff(xyz[b[:no]], axis=0), axis=1).mean()
+            assert d1 < 0.25 * d0 and d1 < 3.0 / 16                                     # random numbering: ~0.6; Z-curve: ~1.5 cells
+    with pytest.raises(ob.OnsasError):
+        ob.NativePartition(xyz, 2, tets=tets, reorder=7)
