@@ -229,11 +229,40 @@ struct onsas_ctx {
     int64_t n_own_dofs() const { return n_owned * dim; }
 };
 
+// pinned host staging buffer (grown on demand): the copies of a group's local vectors overlap the kernels like the caller's own
+struct HostBuf {
+    double* p = nullptr;
+    size_t n = 0, cap = 0;
+    void resize(size_t count) {
+        if (count > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            if (cudaMallocHost(&p, count * sizeof(double)) != cudaSuccess) {
+                p = nullptr;
+                cap = n = 0;
+                throw std::bad_alloc();
+            }
+            cap = count;
+        }
+        n = count;
+    }
+    double* data() { return p; }
+    size_t size() const { return n; }
+    double& operator[](size_t i) { return p[i]; }
+    HostBuf() = default;
+    HostBuf(const HostBuf&) = delete;
+    HostBuf& operator=(const HostBuf&) = delete;
+    HostBuf(HostBuf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    ~HostBuf() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
 struct Group {
     std::vector<onsas_ctx*> sub;          // one context per device, rank r = sub[r]
     Partition part;                       // the global partition (freed down to what the vector traffic needs after finalize)
     std::vector<LocalPart> lp;            // per rank: l2g, element ids, sizes (connectivity arrays released after upload)
-    std::vector<std::vector<double>> hA, hB;  // per-rank host staging of local vectors
+    std::vector<HostBuf> hA, hB;          // per-rank PINNED host staging of local vectors
     int64_t n_free = 0;
 };
 

@@ -499,7 +499,7 @@ def test_library_side_reordering_is_invisible_to_the_caller(ob, oracle):
         c.apply_loads([0.4])
         c.set_U(np.zeros(gm.n_dofs))
     np.testing.assert_array_equal(reord.get_Fext(), plain.get_Fext())
-    for _ in range(6):
+    for _ in range(8):
         i0, i1 = plain.newton_step(ob.PRECOND_JACOBI, 1e-13), reord.newton_step(ob.PRECOND_JACOBI, 1e-13)
     assert cases.rel_err(reord.get_U(), plain.get_U()) < 1e-9 and i1.norm_r < 1e-8 * i1.norm_Fext
     st0, st1 = plain.table_stats(), reord.table_stats()
