@@ -85,6 +85,10 @@ typedef struct onsas_ctx onsas_ctx;
                                         dof list, face list and result stays in the caller's numbering.  2 = aggregate-major: the nodes of every aggregate of the
                                         two-level preconditioner are numbered consecutively (Z-curve inside an aggregate), so its aggregate-ordered
                                         passes stream through memory.  0 (default) keeps the caller's order */
+#define ONSAS_OPT_CG_SINGLE_REDUCTION 14 /* streamed persistent solver with the Jacobi preconditioner: 1 (default) = single-reduction recurrence
+                                            (Chronopoulos-Gear: one reduction of (r.r, r.u, u.Ku) and two grid barriers per iteration, one cross-GPU
+                                            all-reduce), 0 = the classic recurrence (three barriers, two all-reduces).  Same iterates in exact
+                                            arithmetic; precond = 0 always runs the classic one (IterativeSolvers' cg! step by step) */
 #define ONSAS_OPT_COARSE_FUSED 11    /* two-level preconditioner: 1 = residual update in aggregate order, fused with w = Z^T r (default), 0 = separate pass */
 
 /* ---------------------------------------------------------------- life cycle */

@@ -486,7 +486,9 @@ struct CgArgs {
     CgState* st;
     long long* prof;    // optional [8]: SM-clock cycles block 0 spent per phase of the persistent kernel (diagnostics)
     int* err;           // device error flag (3 = a shared-memory stage never arrived)
-    double* p_pad;      // cg_stream: search direction with one 32-byte sector per node (BS = 3: stride 4), owned + halo nodes
+    double* p_pad;      // cg_stream: the vector the SpMV gathers, one 32-byte sector per node (BS = 3: stride 4), owned + halo nodes:
+                        // the search direction p (classic CG) or the preconditioned residual u (single-reduction CG)
+    double* s;          // single-reduction CG: s = K p (owned dofs)
     CoarseArgs co;      // precond = 2
 };
 
@@ -1213,7 +1215,13 @@ __device__ __forceinline__ void ld_node(const double* pn, double (&v)[BS]) {
 }
 
 // CW = consumer warps the instantiation is compiled for (8: 288 threads, 224 registers; 12: 416 threads, 152 registers)
-template <int BS, int CW>
+// SR = single-reduction CG (Chronopoulos-Gear), for precond 0 / 1: with u = M^-1 r, w = K u, gamma = r.u, delta = u.w
+//     beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old),
+//     p = u + beta p,  s = w + beta s (= K p),  x += alpha p,  r -= alpha s,  u = M^-1 r
+// All vector updates are ONE local phase, and r.r, r.u are known at its end, so an iteration is
+// {vector phase | grid barrier | SpMV w = K u with u.w | one reduction of (r.r, r.u, u.w)}: two grid barriers and ONE
+// cross-GPU all-reduce per iteration instead of three and two.  Same iterates as the classic recurrence in exact arithmetic.
+template <int BS, int CW, bool SR>
 __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamArgs S, P2PArgs P) {
     constexpr int ST_THREADS = (CW + 1) * 32;
     constexpr int VB = CW > 8 ? 5 : 8;  // dofs per thread and batch in the vector phases (register budget: 152 vs 224)
@@ -1475,6 +1483,157 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     double rho_prev = 1.0;
     long long it = 0;
     if (profiling) tprev = clock64();
+    const int lrow = lane & 7, qpart = lane >> 3;
+
+    // ---- Ap = K v from the shared-memory rings (v = the padded vector p_pad), returns the thread's share of v.Ap
+    auto spmv_phase = [&]() -> double {
+        double d = 0.0;
+        if (is_producer) {
+            // stay DEPTH fills ahead: n_my fills per SpMV phase, each as soon as its slot has been released
+            if (n_my > 0)
+                for (int k = 0; k < n_my; ++k, ++f_next) {
+                    mbar_wait(&empty[cw][f_next % D], (uint32_t)((f_next / D - 1) & 1), A.err);
+                    fill(f_next);
+                }
+        } else if (n_my > 0) {
+            const long long tc0 = A.prof != nullptr ? clock64() : 0;
+            for (int k = 0; k < n_my; ++k, ++q_done) {
+                const int slot = (int)(q_done % D);
+                mbar_wait(&full[cw][slot], (uint32_t)((q_done / D) & 1), A.err);
+                const int width = s_width[cw][slot];
+                const unsigned char* stg = dyn + ((size_t)cw * D + slot) * slot_bytes;
+                const double* sv = reinterpret_cast<const double*>(stg) + lrow;
+                const int32_t* sc = reinterpret_cast<const int32_t*>(stg + val_bytes) + lrow;
+                const int64_t row = (first + k * step) * C + lrow;
+                const bool own = qpart == 0 && row < A.n_rows;
+                double po[BS];  // the row's own v (for v.Ap), fetched in the same round trip as the gathers
+#pragma unroll
+                for (int r = 0; r < BS; ++r) po[r] = 0.0;
+                if (own) ld_node<BS>(A.p_pad + row * PS, po);
+                double acc[BS];
+#pragma unroll
+                for (int r = 0; r < BS; ++r) acc[r] = 0.0;
+#pragma unroll 4
+                for (int blk = qpart; blk < width; blk += 4) {
+                    const int64_t cn = sc[blk * C];
+                    double pv[BS];
+                    ld_node<BS>(A.p_pad + cn * PS, pv);
+#pragma unroll
+                    for (int r = 0; r < BS; ++r)
+#pragma unroll
+                        for (int q = 0; q < BS; ++q) acc[r] += sv[(blk * BB + r * BS + q) * C] * pv[q];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[cw][slot]);  // every lane has read its part of the slot: release it
+#pragma unroll
+                for (int r = 0; r < BS; ++r) {
+                    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 8);
+                    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 16);
+                }
+                if (own) {  // rows of fixed dofs are not masked here: v is zero there and the update phase skips them
+#pragma unroll
+                    for (int r = 0; r < BS; ++r) {
+                        A.Ap[row * BS + r] = acc[r];
+                        d += po[r] * acc[r];
+                    }
+                }
+            }
+            if (A.prof != nullptr && lane == 0) A.prof[16 + blockIdx.x * CW + w] += clock64() - tc0;  // per-warp SpMV cycles (diagnostics)
+        }
+        return d;
+    };
+
+    if constexpr (SR) {
+        // ---- single-reduction CG (precond 0 / 1)
+        double* __restrict__ xv = A.x;
+        double* __restrict__ rv = A.r;
+        double* __restrict__ pvec = A.p;
+        double* __restrict__ sv2 = A.s;
+        double* __restrict__ uv = A.p_pad;
+        const double* __restrict__ wv = A.Ap;
+        const double* __restrict__ dv = A.dinv;
+        // u = M^-1 r of the initial residual into the padded vector (owned), pushed to the neighbours; s = 0
+        for (int64_t i = gtid; i < A.n; i += gsz) {
+            const double ui = rv[i] * dv[i];
+            uv[pad_of(i)] = ui;
+            sv2[i] = 0.0;  // (multi-GPU: the prologue above has already pushed u of the interface dofs with this epoch)
+        }
+        if (mg)
+            for (int64_t h = gtid; h < P.n_halo_dofs; h += gsz) {
+                uv[pad_of(A.n + h)] = ll_load(P.zh + 2 * h, hepoch, P.err);
+                pvec[A.n + h] = 0.0;
+            }
+        grid.sync();
+        double dl[1] = {block_sum<ST_THREADS>(spmv_phase(), sh)};  // delta_0 = u.K u
+        grid_reduce(dl);
+        if (mg) p2p_allreduce<1>(P, dl, repoch, sh4);
+        double gamma = rho, alpha = gamma / dl[0], beta = 0.0;
+        if (profiling) tprev = clock64();
+        while (!(it >= A.maxiter || res <= tol || res != res)) {
+            if (*(volatile int*)A.err == 3) break;
+            ++hepoch;
+            double s3[3] = {0.0, 0.0, 0.0};
+            constexpr int VS = 3;  // dofs per thread and batch: seven vectors are live per dof (128 registers per thread)
+            for (int64_t i0 = gtid; i0 < A.n; i0 += VS * gsz) {
+                double u[VS], pp[VS], ww[VS], ss[VS], x[VS], rr[VS], di[VS];
+#pragma unroll
+                for (int k = 0; k < VS; ++k) {  // loads of a batch first (tail lanes re-read the last dof: no branches)
+                    const int64_t i = i0 + k * gsz < A.n ? i0 + k * gsz : A.n - 1;
+                    u[k] = uv[pad_of(i)];
+                    pp[k] = pvec[i];
+                    ww[k] = wv[i];
+                    ss[k] = sv2[i];
+                    x[k] = xv[i];
+                    rr[k] = rv[i];
+                    di[k] = dv[i];
+                }
+#pragma unroll
+                for (int k = 0; k < VS; ++k) {
+                    const int64_t i = i0 + k * gsz;
+                    if (i < A.n) {
+                        const double pn = u[k] + beta * pp[k];
+                        const double sn = ww[k] + beta * ss[k];
+                        pvec[i] = pn;
+                        sv2[i] = sn;
+                        xv[i] = x[k] + alpha * pn;
+                        const double ri = di[k] != 0.0 ? rr[k] - alpha * sn : 0.0;  // fixed dofs: d = 0 (the SpMV does not mask)
+                        rv[i] = ri;
+                        const double un = ri * di[k];
+                        uv[pad_of(i)] = un;
+                        s3[0] += ri * ri;
+                        s3[1] += ri * un;
+                        if (mg && (A.mask[i] & 2)) p2p_push(P, i, un, hepoch);
+                    }
+                }
+            }
+            if (mg)  // halo dofs: the same p and x recurrences as on the owner (bitwise), then the neighbours' new u
+                for (int64_t h = gtid; h < P.n_halo_dofs; h += gsz) {
+                    const int64_t i = A.n + h, j = pad_of(i);
+                    const double pn = uv[j] + beta * pvec[i];
+                    pvec[i] = pn;
+                    xv[i] += alpha * pn;
+                    uv[j] = ll_load(P.zh + 2 * h, hepoch, P.err);
+                }
+            prof(0);
+            grid.sync();
+            prof(1);
+            s3[2] = spmv_phase();
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s3[k] = block_sum<ST_THREADS>(s3[k], sh);
+            prof(2);
+            grid_reduce(s3);
+            prof(3);
+            if (mg) p2p_allreduce<3>(P, s3, repoch, sh4);
+            beta = s3[1] / gamma;
+            alpha = s3[1] / (s3[2] - beta * s3[1] / alpha);
+            rho_prev = gamma;
+            gamma = s3[1];
+            rho = gamma;
+            res = sqrt(s3[0]);
+            ++it;
+            prof(6);
+        }
+    }
 
     // fused residual update (two-level): this warp's chunk of its aggregate, fixed for the whole solve
     const int fw_base_a = (int)blockIdx.x * AG_PER_CTA;
@@ -1497,8 +1656,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
             }
         }
     }
-    const int lrow = lane & 7, qpart = lane >> 3;
-    while (!(it >= A.maxiter || res <= tol || res != res)) {  // a non-finite residual (breakdown) ends the solve: err = 4
+    while (!SR && !(it >= A.maxiter || res <= tol || res != res)) {  // a non-finite residual (breakdown) ends the solve: err = 4
         // ---- p = z + beta p (owned dofs; halo dofs from the neighbours' pushes of epoch hepoch)
         {
             const double beta = rho / rho_prev;
@@ -1601,59 +1759,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         grid.sync();
         prof(1);
         // ---- Ap = K p from the shared-memory rings, partial p.Ap
-        double d = 0.0;
-        if (is_producer) {
-            // stay DEPTH fills ahead: n_my fills per SpMV phase, each as soon as its slot has been released
-            if (n_my > 0)
-                for (int k = 0; k < n_my; ++k, ++f_next) {
-                    mbar_wait(&empty[cw][f_next % D], (uint32_t)((f_next / D - 1) & 1), A.err);
-                    fill(f_next);
-                }
-        } else if (n_my > 0) {
-            const long long tc0 = A.prof != nullptr ? clock64() : 0;
-            for (int k = 0; k < n_my; ++k, ++q_done) {
-                const int slot = (int)(q_done % D);
-                mbar_wait(&full[cw][slot], (uint32_t)((q_done / D) & 1), A.err);
-                const int width = s_width[cw][slot];
-                const unsigned char* stg = dyn + ((size_t)cw * D + slot) * slot_bytes;
-                const double* sv = reinterpret_cast<const double*>(stg) + lrow;
-                const int32_t* sc = reinterpret_cast<const int32_t*>(stg + val_bytes) + lrow;
-                const int64_t row = (first + k * step) * C + lrow;
-                const bool own = qpart == 0 && row < A.n_rows;
-                double po[BS];  // the row's own p (for p.Ap), fetched in the same round trip as the gathers
-#pragma unroll
-                for (int r = 0; r < BS; ++r) po[r] = 0.0;
-                if (own) ld_node<BS>(A.p_pad + row * PS, po);
-                double acc[BS];
-#pragma unroll
-                for (int r = 0; r < BS; ++r) acc[r] = 0.0;
-#pragma unroll 4
-                for (int blk = qpart; blk < width; blk += 4) {
-                    const int64_t cn = sc[blk * C];
-                    double pv[BS];
-                    ld_node<BS>(A.p_pad + cn * PS, pv);
-#pragma unroll
-                    for (int r = 0; r < BS; ++r)
-#pragma unroll
-                        for (int q = 0; q < BS; ++q) acc[r] += sv[(blk * BB + r * BS + q) * C] * pv[q];
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[cw][slot]);  // every lane has read its part of the slot: release it
-#pragma unroll
-                for (int r = 0; r < BS; ++r) {
-                    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 8);
-                    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 16);
-                }
-                if (own) {  // rows of fixed dofs are not masked here: p is zero there and the update phase skips them
-#pragma unroll
-                    for (int r = 0; r < BS; ++r) {
-                        A.Ap[row * BS + r] = acc[r];
-                        d += po[r] * acc[r];
-                    }
-                }
-            }
-            if (A.prof != nullptr && lane == 0) A.prof[16 + blockIdx.x * CW + w] += clock64() - tc0;  // per-warp SpMV cycles (diagnostics)
-        }
+        const double d = spmv_phase();
         double pAp[1] = {block_sum<ST_THREADS>(d, sh)};
         prof(2);
         grid_reduce(pAp);

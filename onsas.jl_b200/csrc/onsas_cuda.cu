@@ -147,7 +147,7 @@ struct onsas_ctx {
     MeshTables tab;
 
     // device
-    DevBuf<double> X, U, Fext, Fint, val, x, r, p, p_pad, Ap, dinv, rhs, partials, red, tet_out, truss_out, area, mat_params;
+    DevBuf<double> X, U, Fext, Fint, val, x, r, p, p_pad, Ap, dinv, rhs, s_vec, partials, red, tet_out, truss_out, area, mat_params;
     DevBuf<int32_t> tets, tet_mat, trusses, truss_mat, mat_kind, col, diag_slot, pair_code[2], snodes[2], send_nodes;
     DevBuf<uint16_t> pair_lnodes[2];
     DevBuf<int64_t> slice_ptr;
@@ -194,9 +194,11 @@ struct onsas_ctx {
     struct StreamPlan {
         bool built = false, ok = false;
         int n_cw = 0, depth = 0, grid = 0, threads = 0;
-        void* kern = nullptr;
+        void* kern = nullptr;     // classic recurrence (every preconditioner)
+        void* kern_sr = nullptr;  // single-reduction recurrence (precond 0 / 1)
         size_t smem = 0;
     } st_plan;
+    int cg_single_reduction = 1;  // ONSAS_OPT_CG_SINGLE_REDUCTION: Jacobi-PCG runs the single-reduction recurrence
     int force_mg = 0;  // diagnostics: run the multi-GPU kernel even with one rank
     int reorder = 0;   // ONSAS_OPT_REORDER: 1 = the nodes are renumbered along a Z-curve inside onsas_finalize_mesh (invisible to the caller)
     std::vector<std::pair<int32_t, int64_t>> opt_log;  // options in the order they were set (replayed on the device contexts of a group)
@@ -648,6 +650,7 @@ CgArgs make_cg_args(onsas_ctx* c, int precond, double reltol, double abstol, int
     A.prof = c->cg_profile ? c->prof.p : nullptr;
     A.err = c->err_flag.p;
     A.p_pad = c->p_pad.p;
+    A.s = c->s_vec.p;
     return A;
 }
 
@@ -710,9 +713,9 @@ bool plan_stream(onsas_ctx* c) {
     const int slots = (int)(budget / slot_bytes);
     if (slots < 2) return false;
     // measured on the 1 M-tet cube (scripts/cg_stream_probe.py): 12 warps x 2 slots 47.8 us / CG iteration, 8 x 3 52.8 us
-    int cw_max = 12, want_depth = 2;
-    if (const char* e = getenv("ONSAS_STREAM_CW")) cw_max = atoi(e) >= 12 ? 12 : 8;  // experiment knobs
-    if (const char* e = getenv("ONSAS_STREAM_DEPTH")) want_depth = std::max(2, std::min(ST_MAX_DEPTH, atoi(e)));
+    const int cw_max = 12;
+    int want_depth = 2;
+    if (const char* e = getenv("ONSAS_STREAM_DEPTH")) want_depth = std::max(2, std::min(ST_MAX_DEPTH, atoi(e)));  // experiment knob
     int depth = std::min(want_depth, slots);
     int n_cw = std::min(cw_max, slots / depth);
     if (n_cw < cw_max && depth > 2) {  // wide rows: rather keep the warps and give each two slots
@@ -720,13 +723,16 @@ bool plan_stream(onsas_ctx* c) {
         n_cw = std::min(cw_max, slots / 2);
     }
     const size_t smem = slot_bytes * (size_t)n_cw * depth;
-    void* kern = cw_max == 12 ? (void*)cg_stream<BS, 12> : (void*)cg_stream<BS, 8>;
+    void* kern = (void*)cg_stream<BS, 12, false>;
+    void* kern_sr = (void*)cg_stream<BS, 12, true>;
     const int threads = (cw_max + 1) * 32;
     ensure_dyn_smem(c->device, kern, smem);
+    ensure_dyn_smem(c->device, kern_sr, smem);
     int occ = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ < 1) return false;
     c->st_plan.kern = kern;
+    c->st_plan.kern_sr = kern_sr;
     c->st_plan.threads = threads;
     c->st_plan.n_cw = n_cw;
     c->st_plan.depth = depth;
@@ -748,7 +754,10 @@ void launch_stream(onsas_ctx* c, CgArgs A) {
     S.n_slices = c->tab.n_slices;
     P2PArgs P = make_p2p_args(c);
     void* args[] = {&A, &S, &P};
-    CUDA_CHECK(cudaLaunchCooperativeKernel(c->st_plan.kern, dim3(c->st_plan.grid), dim3(c->st_plan.threads), args, c->st_plan.smem, c->stream));
+    // Jacobi-PCG (the north-star solver) runs the single-reduction recurrence; precond = 0 keeps the classic one, which
+    // restates IterativeSolvers' cg! step by step, and the two-level preconditioner needs its own phase structure
+    const bool sr = c->cg_single_reduction && A.precond == 1;
+    CUDA_CHECK(cudaLaunchCooperativeKernel(sr ? c->st_plan.kern_sr : c->st_plan.kern, dim3(c->st_plan.grid), dim3(c->st_plan.threads), args, c->st_plan.smem, c->stream));
 }
 
 // ---------------------------------------------------------------- two-level preconditioner: aggregates + coarse inverse
@@ -1129,6 +1138,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_HOST_MID_WEIGHT: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "weight must be 1..64"); c->host_mid_weight = (int)value; c->hp.built = false; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
+            case ONSAS_OPT_CG_SINGLE_REDUCTION: c->cg_single_reduction = value != 0; break;
             case ONSAS_OPT_REORDER: require(value >= 0 && value <= 2, ONSAS_ERR_INVALID_ARG, "reorder must be 0, 1 or 2"); require(!c->finalized, ONSAS_ERR_INVALID_ARG, "ONSAS_OPT_REORDER must be set before onsas_finalize_mesh"); c->reorder = (int)value; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
         }
@@ -1315,6 +1325,7 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->x.alloc(nl); c->x.zero(s);  // owned + halo dofs: the peer-memory CG keeps the solution consistent on the halo
         c->r.alloc(no); c->r.zero(s);
         c->Ap.alloc(no); c->Ap.zero(s);
+        c->s_vec.alloc(no); c->s_vec.zero(s);
         c->dinv.alloc(no); c->dinv.zero(s);
         c->tet_out.alloc((size_t)c->n_tets * 16); c->tet_out.zero(s);
         c->truss_out.alloc((size_t)c->n_trusses * 2); c->truss_out.zero(s);
