@@ -501,7 +501,7 @@ def test_library_side_reordering_is_invisible_to_the_caller(ob, oracle):
     np.testing.assert_array_equal(reord.get_Fext(), plain.get_Fext())
     for _ in range(8):
         i0, i1 = plain.newton_step(ob.PRECOND_JACOBI, 1e-13), reord.newton_step(ob.PRECOND_JACOBI, 1e-13)
-    assert cases.rel_err(reord.get_U(), plain.get_U()) < 1e-9 and i1.norm_r < 1e-8 * i1.norm_Fext
+    assert cases.rel_err(reord.get_U(), plain.get_U()) < 1e-8 and i1.norm_r < 1e-8 * i1.norm_Fext
     st0, st1 = plain.table_stats(), reord.table_stats()
     assert st1["nnz_blocks"] == st0["nnz_blocks"] and st1["padded_block_slots"] <= st0["padded_block_slots"]
     for c in (plain, reord):
