@@ -63,8 +63,26 @@ struct AsmArgs {
 // different bank pairs, so a half-warp of 8-byte reads to distinct nodes of a run is conflict-free)
 __host__ __device__ constexpr int snode_rec(int dim) { return 2 * dim + 1; }
 
+// material of a pair's element, fetched together with the node data (before the staging barrier, not after it)
+struct PairMat {
+    double p0, p1;  // the two material parameters
+    double area;    // trusses
+    int kind;
+};
+template <int FAMILY>
+__device__ __forceinline__ PairMat pair_material(const AsmArgs& A, int32_t code) {
+    const int64_t e = FAMILY == 0 ? code >> 2 : code >> 1;
+    const int m = A.mat_id ? __ldg(A.mat_id + e) : 0;
+    PairMat M;
+    M.p0 = __ldg(A.mat_params + 2 * m);
+    M.p1 = __ldg(A.mat_params + 2 * m + 1);
+    M.kind = __ldg(A.mat_kind + m);
+    M.area = FAMILY == 1 ? __ldg(A.area + e) : 0.0;
+    return M;
+}
+
 template <int KIND>
-__device__ __forceinline__ void tet_pair(const AsmArgs& A, const double* sn, const uint2 ln, int32_t code, double* rec) {
+__device__ __forceinline__ void tet_pair(const AsmArgs& A, const double* sn, const uint2 ln, int32_t code, const PairMat& M, double* rec) {
     const int64_t e = code >> 2;
     const int a = code & 3;
     const unsigned li[4] = {ln.x & 0x7fffu, ln.x >> 16, ln.y & 0xffffu, ln.y >> 16};
@@ -79,10 +97,9 @@ __device__ __forceinline__ void tet_pair(const AsmArgs& A, const double* sn, con
             U[k][c] = np[3 + c];
         }
     }
-    const int m = A.mat_id ? __ldg(A.mat_id + e) : 0;
-    const double p0 = __ldg(A.mat_params + 2 * m), p1 = __ldg(A.mat_params + 2 * m + 1);
+    const double p0 = M.p0, p1 = M.p1;
     int kind = KIND;
-    if (KIND == MAT_MIXED) kind = __ldg(A.mat_kind + m);
+    if (KIND == MAT_MIXED) kind = M.kind;
 
     double vol;
     auto run = [&](auto tag) {
@@ -109,7 +126,7 @@ __device__ __forceinline__ void tet_pair(const AsmArgs& A, const double* sn, con
 }
 
 template <int DIM>
-__device__ __forceinline__ void truss_pair(const AsmArgs& A, const double* sn, const uint32_t ln, int32_t code, double* rec) {
+__device__ __forceinline__ void truss_pair(const AsmArgs& A, const double* sn, const uint32_t ln, int32_t code, const PairMat& M, double* rec) {
     const int64_t e = code >> 1;
     const int a = code & 1;
     const double* n0 = sn + (ln & 0x7fffu) * snode_rec(DIM);
@@ -123,10 +140,9 @@ __device__ __forceinline__ void truss_pair(const AsmArgs& A, const double* sn, c
         U[0][c] = n0[DIM + c];
         U[1][c] = n1[DIM + c];
     }
-    const int m = A.mat_id ? __ldg(A.mat_id + e) : 0;
-    const double Emod = truss_modulus(__ldg(A.mat_kind + m), __ldg(A.mat_params + 2 * m), __ldg(A.mat_params + 2 * m + 1));
+    const double Emod = truss_modulus(M.kind, M.p0, M.p1);
     double blk[2][9], f[3], se[2];
-    truss_row<DIM>(A.strain_model, X, U, Emod, __ldg(A.area + e), a, blk, f, se);
+    truss_row<DIM>(A.strain_model, X, U, Emod, M.area, a, blk, f, se);
 #pragma unroll
     for (int b = 0; b < 2; ++b)
 #pragma unroll
@@ -140,9 +156,10 @@ __device__ __forceinline__ void truss_pair(const AsmArgs& A, const double* sn, c
 }
 
 // shared memory of one assembly CTA:
-// [stage: max_pairs*REC (+ skew) doubles][nodes: max_snodes * (2 dim + 1) doubles][scode: max_pairs*NPE u16][scp: max_width*C+1 u16]
+// [stage: max_pairs*REC (+ skew) doubles][ASM_ZEROS zeros][nodes: max_snodes * (2 dim + 1) doubles][scode: max_pairs*NPE u16][scp: max_width*C+1 u16]
+constexpr int ASM_ZEROS = 4;  // >= DIM doubles, keeps the node records 32-byte aligned
 __host__ __device__ constexpr size_t asm_smem_bytes(int max_pairs, int max_width, int max_snodes, int rec, int npe, int dim) {
-    return ((size_t)max_pairs * rec + ROW_SKEW * SLICE_ROWS + (size_t)max_snodes * snode_rec(dim)) * 8 +
+    return ((size_t)max_pairs * rec + ROW_SKEW * SLICE_ROWS + ASM_ZEROS + (size_t)max_snodes * snode_rec(dim)) * 8 +
            (((size_t)max_pairs * npe * 2 + ((size_t)max_width * SLICE_ROWS + 1) * 2 + 15) / 16) * 16;
 }
 
@@ -165,7 +182,9 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     constexpr int REC = FAMILY == 0 ? TET_REC : truss_rec(DIM);
     constexpr int FOFF = NPE * BB;
     constexpr int NS = snode_rec(DIM);
-    double* const snd = stage + (size_t)A.max_pairs * REC + ROW_SKEW * C;
+    const int zero_off = A.max_pairs * REC + ROW_SKEW * C;  // ASM_ZEROS doubles of zeros: what the batched sums of phase B read past a list's end
+    double* const snd = stage + zero_off + ASM_ZEROS;
+    if (threadIdx.x < ASM_ZEROS) stage[zero_off + threadIdx.x] = 0.0;
     uint16_t* scode = reinterpret_cast<uint16_t*>(snd + (size_t)A.max_snodes * NS);
     uint16_t* scp = scode + (size_t)A.max_pairs * NPE;
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -242,6 +261,8 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
             }
         }
     }
+    PairMat mat = PairMat();
+    if (t < np) mat = pair_material<FAMILY>(A, code);
     if (tid < nscp) scp[tid] = (uint16_t)(cp0 - cbase);
     for (int i = tid + nth; i < nscp; i += nth) scp[i] = (uint16_t)(__ldg(A.cptr + base * C + i) - cbase);
     __syncthreads();
@@ -252,9 +273,9 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     while (t < np_a) {
         reinterpret_cast<CodeVec*>(scode)[t] = chunk;
         if constexpr (FAMILY == 0)
-            tet_pair<KIND>(A, snd, nodes, code, stage + (size_t)t * REC + row_skew(FAMILY, l));
+            tet_pair<KIND>(A, snd, nodes, code, mat, stage + (size_t)t * REC + row_skew(FAMILY, l));
         else
-            truss_pair<DIM>(A, snd, nodes, code, stage + (size_t)t * REC + row_skew(FAMILY, l));
+            truss_pair<DIM>(A, snd, nodes, code, mat, stage + (size_t)t * REC + row_skew(FAMILY, l));
         t += nth;
         if (t < np_a) {  // slices with more pairs than threads (high-valence meshes): header again from L1, not from registers
             const int4* hq = reinterpret_cast<const int4*>(A.hdr + slice);
@@ -262,6 +283,7 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
             nodes = __ldg(reinterpret_cast<const NodeVec*>(A.pair_lnodes) + pq + t);
             code = __ldg(A.pair_code + pq + t);
             chunk = __ldg(reinterpret_cast<const CodeVec*>(A.ccode + (uint32_t)(pq * NPE)) + t);
+            mat = pair_material<FAMILY>(A, code);
             l = row_of_pair(__ldg(hq + 1), __ldg(hq + 2), t);
         }
     }
@@ -285,10 +307,23 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
             double acc[DIM];
 #pragma unroll
             for (int j = 0; j < DIM; ++j) acc[j] = 0.0;
-            for (int q = q0; q < q1; ++q) {
-                const double* src = stage + scode[q] + r * DIM;
+            // contributions in batches of PB: the PB code loads, then the PB * DIM value loads are independent of each other
+            // (two dependent shared-memory round trips per batch instead of per contribution); the ADDS keep the ascending
+            // element order.  Batch slots past the end read the CTA's block of zeros.
+            constexpr int PB = 4;
+            for (int q = q0; q < q1; q += PB) {
+                int cd[PB];
 #pragma unroll
-                for (int j = 0; j < DIM; ++j) acc[j] += src[j];
+                for (int k = 0; k < PB; ++k) cd[k] = q + k < q1 ? (int)scode[q + k] + r * DIM : zero_off;
+                double v[PB][DIM];
+#pragma unroll
+                for (int k = 0; k < PB; ++k)
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j) v[k][j] = stage[cd[k] + j];
+#pragma unroll
+                for (int k = 0; k < PB; ++k)
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j) acc[j] += v[k][j];
             }
             double* dst = vout + ((size_t)s * BB + r * DIM) * C + lane;
 #pragma unroll
@@ -303,7 +338,14 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
             const int64_t row = (int64_t)slice * C + lane;
             if (t1 > t0 || !ACCUM) {
                 double acc = 0.0;
-                for (int tt = t0; tt < t1; ++tt) acc += stage[tt * REC + row_skew(FAMILY, lane) + FOFF + r];
+                constexpr int FB = 8;  // the same batching for the row's force entries (24 pairs per row on the structured mesh)
+                for (int tt = t0; tt < t1; tt += FB) {
+                    double v[FB];
+#pragma unroll
+                    for (int k = 0; k < FB; ++k) v[k] = stage[tt + k < t1 ? (tt + k) * REC + row_skew(FAMILY, lane) + FOFF + r : zero_off];
+#pragma unroll
+                    for (int k = 0; k < FB; ++k) acc += v[k];
+                }
                 if (row < A.n_rows_guard) {
                     if (ACCUM) acc += A.F_int[row * DIM + r];
                     A.F_int[row * DIM + r] = acc;

@@ -165,7 +165,7 @@ struct onsas_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 
     // options
-    int cg_mode = 0, asm_minb = 3, check_every = 16, cg_bps = 6;
+    int cg_mode = 0, asm_minb = 3, truss_minb = 3, check_every = 16, cg_bps = 6;
     int cg_grid = 0, part_stride = 4096;
     // two-level preconditioner (precond = 2): node aggregates, dense coarse inverse, work vectors
     struct Coarse {
@@ -463,15 +463,22 @@ void launch_assemble_range(onsas_ctx* c) {
         const int mp = c->tab.fam[1].max_pairs_per_slice;
         const int threads = round_threads(mp);
         const size_t smem = asm_smem_bytes(A.max_pairs, A.max_width, A.max_snodes, truss_rec(c->dim), 2, c->dim);
-        if (wrote) {
-            if (c->dim == 3) launch_asm_inst<1, 0, 3, true, 256, 2>(c, A, threads, smem);
-            else if (c->dim == 2) launch_asm_inst<1, 0, 2, true, 256, 2>(c, A, threads, smem);
-            else launch_asm_inst<1, 0, 1, true, 256, 2>(c, A, threads, smem);
-        } else {
-            if (c->dim == 3) launch_asm_inst<1, 0, 3, false, 256, 2>(c, A, threads, smem);
-            else if (c->dim == 2) launch_asm_inst<1, 0, 2, false, 256, 2>(c, A, threads, smem);
-            else launch_asm_inst<1, 0, 1, false, 256, 2>(c, A, threads, smem);
-        }
+        // register budget of the truss kernel (its CTAs are small: 128 threads on the braced lattice): 2 -> 120 registers,
+        // 3 -> 80, 4 -> 64 (ONSAS_OPT_TRUSS_MINBLOCKS)
+        auto go = [&](auto dimtag, auto acctag) {
+            constexpr int D = decltype(dimtag)::value;
+            constexpr bool ACC = decltype(acctag)::value != 0;
+            if (c->truss_minb >= 4) launch_asm_inst<1, 0, D, ACC, 256, 4>(c, A, threads, smem);
+            else if (c->truss_minb == 3) launch_asm_inst<1, 0, D, ACC, 256, 3>(c, A, threads, smem);
+            else launch_asm_inst<1, 0, D, ACC, 256, 2>(c, A, threads, smem);
+        };
+        auto go_dim = [&](auto acctag) {
+            if (c->dim == 3) go(IC<3>(), acctag);
+            else if (c->dim == 2) go(IC<2>(), acctag);
+            else go(IC<1>(), acctag);
+        };
+        if (wrote) go_dim(IC<1>());
+        else go_dim(IC<0>());
         wrote = true;
     }
     if (!wrote) {  // structure without elements: K = 0, F_int = 0
@@ -1138,6 +1145,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_HOST_MID_WEIGHT: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "weight must be 1..64"); c->host_mid_weight = (int)value; c->hp.built = false; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
+            case ONSAS_OPT_TRUSS_MINBLOCKS: require(value >= 2 && value <= 4, ONSAS_ERR_INVALID_ARG, "truss min blocks must be 2..4"); c->truss_minb = (int)value; break;
             case ONSAS_OPT_CG_SINGLE_REDUCTION: c->cg_single_reduction = value != 0; break;
             case ONSAS_OPT_REORDER: require(value >= 0 && value <= 2, ONSAS_ERR_INVALID_ARG, "reorder must be 0, 1 or 2"); require(!c->finalized, ONSAS_ERR_INVALID_ARG, "ONSAS_OPT_REORDER must be set before onsas_finalize_mesh"); c->reorder = (int)value; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");

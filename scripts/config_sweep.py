@@ -115,6 +115,7 @@ def c5(n=112):
                                mat_kind=[ob.MAT_SVK], mat_params=[[0.0, E / 2]], free_dofs=free)
     t_fin = time.time() - t0
     ctx.set_stream(stream.cuda_stream)
+    ctx.set_option(L.OPT_TRUSS_MINBLOCKS, int(os.environ.get("ONSAS_TRUSS_MINB", "3")))
     eps = 1e-3
     U = np.zeros((nn, 3))
     U[:, 0] = eps * mesh.xyz[:, 0]                                   # homogeneous stretch: interior nodes stay in equilibrium
