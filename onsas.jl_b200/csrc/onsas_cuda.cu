@@ -165,7 +165,7 @@ struct onsas_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 
     // options
-    int cg_mode = 0, asm_minb = 3, truss_minb = 3, check_every = 16, cg_bps = 6;
+    int cg_mode = 0, asm_minb = 3, truss_minb = 4, check_every = 16, cg_bps = 6;
     int cg_grid = 0, part_stride = 4096;
     // two-level preconditioner (precond = 2): node aggregates, dense coarse inverse, work vectors
     struct Coarse {
