@@ -1275,6 +1275,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     __shared__ int s_width[ST_MAX_CW][ST_MAX_DEPTH];  // blocks per row of the slice sitting in a slot
     constexpr int CDM = BS == 3 ? 6 : BS;             // most coarse dofs per aggregate (translations + rotations in 3D)
     __shared__ double s_wp[ST_MAX_CW + 1][CDM];       // two-level preconditioner: chunk sums of w = Z^T r
+    __shared__ double s_y[(ST_MAX_CW + 1) * CDM];     // single-reduction two-level solver: coarse values of this CTA's aggregates
     constexpr int BB = BS * BS;
     constexpr int PS = BS == 3 ? 4 : BS;  // stride of a node in the padded search direction
     const int tid = threadIdx.x;
@@ -1457,6 +1458,41 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     // y = E^-1 w once w is complete: barrier, then one warp per row of the dense inverse (L2-resident; 16-byte loads,
     // 12 + 12 of them in flight per lane).  z is never stored: r.z = sum r^2 d + w.y, so this leaves y in memory and
     // returns the thread's share of w.y; the p update forms z_i = d_i r_i + (Z y)_i on the fly.
+    // row k of y = E^-1 w by one warp (the dense inverse is L2-resident; 16-byte loads, 12 + 12 of them in flight per lane);
+    // the result is valid in every lane
+    auto einv_row_dot = [&](int k) -> double {
+        const CoarseArgs& G = A.co;
+        double acc = 0.0;
+        if ((G.nc & 1) == 0) {  // rows are 16-byte aligned
+            const double2* row = reinterpret_cast<const double2*>(G.Einv + (size_t)k * G.nc);
+            const double2* wv = reinterpret_cast<const double2*>(G.w);
+            const int n2 = G.nc >> 1;
+            int j = lane;
+            for (; j + 11 * 32 < n2; j += 12 * 32) {
+                double2 e[12], ww[12];
+#pragma unroll
+                for (int u = 0; u < 12; ++u) {
+                    e[u] = __ldg(row + j + 32 * u);
+                    ww[u] = __ldcg(wv + j + 32 * u);
+                }
+#pragma unroll
+                for (int u = 0; u < 12; ++u) acc += e[u].x * ww[u].x + e[u].y * ww[u].y;
+            }
+            for (; j < n2; j += 32) {
+                const double2 e = __ldg(row + j), ww = __ldcg(wv + j);
+                acc += e.x * ww.x + e.y * ww.y;
+            }
+        } else {
+            const double* row = G.Einv + (size_t)k * G.nc;
+            for (int j = lane; j < G.nc; j += 32) acc += __ldg(row + j) * __ldcg(G.w + j);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        return acc;
+    };
+    // y = E^-1 w once w is complete: barrier, then one warp per row of the dense inverse.  z is never stored:
+    // r.z = sum r^2 d + w.y, so this leaves y in memory and returns the thread's share of w.y; the p update forms
+    // z_i = d_i r_i + (Z y)_i on the fly.
     auto coarse_solve = [&]() -> double {
         const CoarseArgs& G = A.co;
         const int gw = (int)(gtid >> 5), nw = (int)(gsz >> 5);
@@ -1465,32 +1501,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         cprof(10);
         double wy = 0.0;
         for (int k = gw; k < G.nc; k += nw) {
-            double acc = 0.0;
-            if ((G.nc & 1) == 0) {  // rows are 16-byte aligned
-                const double2* row = reinterpret_cast<const double2*>(G.Einv + (size_t)k * G.nc);
-                const double2* wv = reinterpret_cast<const double2*>(G.w);
-                const int n2 = G.nc >> 1;
-                int j = lane;
-                for (; j + 11 * 32 < n2; j += 12 * 32) {
-                    double2 e[12], ww[12];
-#pragma unroll
-                    for (int u = 0; u < 12; ++u) {
-                        e[u] = __ldg(row + j + 32 * u);
-                        ww[u] = __ldcg(wv + j + 32 * u);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 12; ++u) acc += e[u].x * ww[u].x + e[u].y * ww[u].y;
-                }
-                for (; j < n2; j += 32) {
-                    const double2 e = __ldg(row + j), ww = __ldcg(wv + j);
-                    acc += e.x * ww.x + e.y * ww.y;
-                }
-            } else {
-                const double* row = G.Einv + (size_t)k * G.nc;
-                for (int j = lane; j < G.nc; j += 32) acc += __ldg(row + j) * __ldcg(G.w + j);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            const double acc = einv_row_dot(k);
             if (lane == 0) {
                 G.y[k] = acc;
                 wy += __ldcg(G.w + k) * acc;
@@ -1585,6 +1596,27 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         return d;
     };
 
+    // fused residual update (two-level): this warp's chunk of its aggregate, fixed for the whole solve
+    const int fw_base_a = (int)blockIdx.x * AG_PER_CTA;
+    const bool fw_cta = two_level && fw_base_a < A.co.n_agg;  // AG_PER_CTA = ceil(n_agg / grid): a single pass covers all aggregates
+    bool fw_active = false;
+    int fw_b0 = 0, fw_b1 = 0;
+    int fw_nid[4] = {-1, -1, -1, -1};
+    if (fw_cta && (A.co.fused != 0 || SR)) {
+        const int m = w / SPLIT, ch = w % SPLIT, a = fw_base_a + m;
+        fw_active = m < AG_PER_CTA && a < A.co.n_agg;
+        if (fw_active) {
+            const int q0 = A.co.agg_ptr[a], q1 = A.co.agg_ptr[a + 1];
+            const int len = (q1 - q0 + SPLIT - 1) / SPLIT;
+            fw_b0 = q0 + ch * len;
+            fw_b1 = fw_b0 + len < q1 ? fw_b0 + len : q1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = fw_b0 + lane + 32 * u;
+                fw_nid[u] = q < fw_b1 ? A.co.agg_nodes[q] : -1;
+            }
+        }
+    }
     if constexpr (SR) {
         // ---- single-reduction CG (precond 0 / 1)
         double* __restrict__ xv = A.x;
@@ -1594,7 +1626,37 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         double* __restrict__ uv = A.p_pad;
         const double* __restrict__ wv = A.Ap;
         const double* __restrict__ dv = A.dinv;
+        // (Z y)_c of a node of an aggregate whose coarse values are ya[0 .. CD): translation + omega x rho
+        auto zy_node = [&](const double* ya, int64_t nd, double (&zc)[BS]) {
+#pragma unroll
+            for (int c = 0; c < BS; ++c) zc[c] = ya[c];
+            if constexpr (BS == 3) {
+                if (rbm) {
+                    const double* rp = A.co.rho + nd * 3;
+                    const double r0 = rp[0], r1 = rp[1], r2 = rp[2];
+                    zc[0] += ya[4] * r2 - ya[5] * r1;
+                    zc[1] += ya[5] * r0 - ya[3] * r2;
+                    zc[2] += ya[3] * r1 - ya[4] * r0;
+                }
+            }
+        };
         // u = M^-1 r of the initial residual into the padded vector (owned), pushed to the neighbours; s = 0
+        if (two_level) {  // y = E^-1 Z^T r0 is in memory (prologue above); one thread per node
+            for (int64_t nd = gtid; nd < A.n_rows; nd += gsz) {
+                double ya[CDM], zc[BS];
+                const double* yp = A.co.y + (size_t)A.co.agg[nd] * CD;
+                for (int c = 0; c < CD; ++c) ya[c] = __ldcg(yp + c);
+                zy_node(ya, nd, zc);
+#pragma unroll
+                for (int c = 0; c < BS; ++c) {
+                    const int64_t i = nd * BS + c;
+                    const double ui = dv[i] != 0.0 ? rv[i] * dv[i] + zc[c] : 0.0;
+                    uv[pad_of(i)] = ui;
+                    sv2[i] = 0.0;
+                    if (mg && (A.mask[i] & 2)) p2p_push(P, i, ui, hepoch);
+                }
+            }
+        } else
         for (int64_t i = gtid; i < A.n; i += gsz) {
             const double ui = rv[i] * dv[i];
             uv[pad_of(i)] = ui;
@@ -1615,6 +1677,100 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
             if (*(volatile int*)A.err == 3) break;
             ++hepoch;
             double s3[3] = {0.0, 0.0, 0.0};
+            if (two_level) {
+                // ---- two-level: the same recurrences in AGGREGATE order (this warp's chunk of its aggregate, as in the
+                //      classic solver's fused update), so that w = Z^T r of the new residual is accumulated on the way;
+                //      then, once w is complete, every CTA solves for the coarse values of ITS aggregates only
+                //      (y = rows of E^-1 times w) and forms u = D^-1 r + Z y for their nodes.  Three grid barriers and one
+                //      cross-GPU all-reduce per iteration (classic two-level: four and two).
+                double acc[CDM];
+#pragma unroll
+                for (int c = 0; c < CDM; ++c) acc[c] = 0.0;
+                auto v1_node = [&](int64_t nd) {
+                    double u[BS], pp[BS], ww[BS], ss[BS], x[BS], rr[BS], di[BS], rn[BS];
+                    ld_node<BS>(uv + nd * PS, u);
+#pragma unroll
+                    for (int c = 0; c < BS; ++c) {
+                        const int64_t i = nd * BS + c;
+                        pp[c] = pvec[i];
+                        ww[c] = wv[i];
+                        ss[c] = sv2[i];
+                        x[c] = xv[i];
+                        rr[c] = rv[i];
+                        di[c] = dv[i];
+                    }
+#pragma unroll
+                    for (int c = 0; c < BS; ++c) {
+                        const int64_t i = nd * BS + c;
+                        const double pn = u[c] + beta * pp[c];
+                        const double sn = ww[c] + beta * ss[c];
+                        pvec[i] = pn;
+                        sv2[i] = sn;
+                        xv[i] = x[c] + alpha * pn;
+                        const double ri = di[c] != 0.0 ? rr[c] - alpha * sn : 0.0;
+                        rv[i] = ri;
+                        rn[c] = ri;
+                        s3[0] += ri * ri;
+                        s3[1] += ri * (ri * di[c]);
+                    }
+                    w_accumulate(acc, nd, rn);
+                };
+                if (fw_cta) {
+                    if (fw_active) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (fw_nid[k] >= 0) v1_node(fw_nid[k]);
+                        for (int q = fw_b0 + 128 + lane; q < fw_b1; q += 32) v1_node(A.co.agg_nodes[q]);  // chunks longer than 128 nodes
+                    }
+                    w_combine(acc, fw_active, fw_base_a);
+                }
+                if (mg)  // halo dofs: the owner's p and x recurrences (their old u is still in the padded vector)
+                    for (int64_t h = gtid; h < P.n_halo_dofs; h += gsz) {
+                        const int64_t i = A.n + h;
+                        const double pn = uv[pad_of(i)] + beta * pvec[i];
+                        pvec[i] = pn;
+                        xv[i] += alpha * pn;
+                    }
+                prof(4);
+                grid.sync();  // w = Z^T r complete
+                prof(5);
+                if (fw_cta) {
+                    for (int k = w; k < AG_PER_CTA * CD; k += CW + 1) {  // one warp per coarse row of this CTA's aggregates
+                        const int a = fw_base_a + k / CD;
+                        if (a < A.co.n_agg) {
+                            const int gk = a * CD + k % CD;
+                            const double yk = einv_row_dot(gk);
+                            if (lane == 0) {
+                                s_y[k] = yk;
+                                s3[1] += __ldcg(A.co.w + gk) * yk;  // r.u = sum r^2 d + w.y
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (fw_active) {
+                        double ya[CDM];
+                        for (int c = 0; c < CD; ++c) ya[c] = s_y[(w / SPLIT) * CD + c];
+                        auto v2_node = [&](int64_t nd) {
+                            double zc[BS];
+                            zy_node(ya, nd, zc);
+#pragma unroll
+                            for (int c = 0; c < BS; ++c) {
+                                const int64_t i = nd * BS + c;
+                                const double d = dv[i];
+                                const double un = d != 0.0 ? rv[i] * d + zc[c] : 0.0;
+                                uv[nd * PS + c] = un;
+                                if (mg && (A.mask[i] & 2)) p2p_push(P, i, un, hepoch);
+                            }
+                        };
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (fw_nid[k] >= 0) v2_node(fw_nid[k]);
+                        for (int q = fw_b0 + 128 + lane; q < fw_b1; q += 32) v2_node(A.co.agg_nodes[q]);
+                    }
+                }
+                if (mg)
+                    for (int64_t h = gtid; h < P.n_halo_dofs; h += gsz) uv[pad_of(A.n + h)] = ll_load(P.zh + 2 * h, hepoch, P.err);
+            } else {
             constexpr int VS = 3;  // dofs per thread and batch: seven vectors are live per dof (128 registers per thread)
             for (int64_t i0 = gtid; i0 < A.n; i0 += VS * gsz) {
                 double u[VS], pp[VS], ww[VS], ss[VS], x[VS], rr[VS], di[VS];
@@ -1656,6 +1812,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                     xv[i] += alpha * pn;
                     uv[j] = ll_load(P.zh + 2 * h, hepoch, P.err);
                 }
+            }
             prof(0);
             grid.sync();
             prof(1);
@@ -1677,27 +1834,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         }
     }
 
-    // fused residual update (two-level): this warp's chunk of its aggregate, fixed for the whole solve
-    const int fw_base_a = (int)blockIdx.x * AG_PER_CTA;
-    const bool fw_cta = two_level && fw_base_a < A.co.n_agg;  // AG_PER_CTA = ceil(n_agg / grid): a single pass covers all aggregates
-    bool fw_active = false;
-    int fw_b0 = 0, fw_b1 = 0;
-    int fw_nid[4] = {-1, -1, -1, -1};
-    if (fw_cta && A.co.fused != 0) {
-        const int m = w / SPLIT, ch = w % SPLIT, a = fw_base_a + m;
-        fw_active = m < AG_PER_CTA && a < A.co.n_agg;
-        if (fw_active) {
-            const int q0 = A.co.agg_ptr[a], q1 = A.co.agg_ptr[a + 1];
-            const int len = (q1 - q0 + SPLIT - 1) / SPLIT;
-            fw_b0 = q0 + ch * len;
-            fw_b1 = fw_b0 + len < q1 ? fw_b0 + len : q1;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int q = fw_b0 + lane + 32 * u;
-                fw_nid[u] = q < fw_b1 ? A.co.agg_nodes[q] : -1;
-            }
-        }
-    }
     while (!SR && !(it >= A.maxiter || res <= tol || res != res)) {  // a non-finite residual (breakdown) ends the solve: err = 4
         // ---- p = z + beta p (owned dofs; halo dofs from the neighbours' pushes of epoch hepoch)
         {

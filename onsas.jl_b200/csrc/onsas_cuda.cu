@@ -198,7 +198,7 @@ struct onsas_ctx {
         void* kern_sr = nullptr;  // single-reduction recurrence (precond 0 / 1)
         size_t smem = 0;
     } st_plan;
-    int cg_single_reduction = 1;  // ONSAS_OPT_CG_SINGLE_REDUCTION: Jacobi-PCG runs the single-reduction recurrence
+    int cg_single_reduction = 3;  // ONSAS_OPT_CG_SINGLE_REDUCTION: bit 0 = Jacobi-PCG, bit 1 = two-level PCG run the single-reduction recurrence
     int force_mg = 0;  // diagnostics: run the multi-GPU kernel even with one rank
     int reorder = 0;   // ONSAS_OPT_REORDER: 1 = the nodes are renumbered along a Z-curve inside onsas_finalize_mesh (invisible to the caller)
     std::vector<std::pair<int32_t, int64_t>> opt_log;  // options in the order they were set (replayed on the device contexts of a group)
@@ -763,7 +763,7 @@ void launch_stream(onsas_ctx* c, CgArgs A) {
     void* args[] = {&A, &S, &P};
     // Jacobi-PCG (the north-star solver) runs the single-reduction recurrence; precond = 0 keeps the classic one, which
     // restates IterativeSolvers' cg! step by step, and the two-level preconditioner needs its own phase structure
-    const bool sr = c->cg_single_reduction && A.precond == 1;
+    const bool sr = (A.precond == 1 && (c->cg_single_reduction & 1)) || (A.precond == 2 && (c->cg_single_reduction & 2));
     CUDA_CHECK(cudaLaunchCooperativeKernel(sr ? c->st_plan.kern_sr : c->st_plan.kern, dim3(c->st_plan.grid), dim3(c->st_plan.threads), args, c->st_plan.smem, c->stream));
 }
 
@@ -1146,7 +1146,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
             case ONSAS_OPT_TRUSS_MINBLOCKS: require(value >= 2 && value <= 4, ONSAS_ERR_INVALID_ARG, "truss min blocks must be 2..4"); c->truss_minb = (int)value; break;
-            case ONSAS_OPT_CG_SINGLE_REDUCTION: c->cg_single_reduction = value != 0; break;
+            case ONSAS_OPT_CG_SINGLE_REDUCTION: require(value >= 0 && value <= 3, ONSAS_ERR_INVALID_ARG, "single-reduction mask must be 0..3"); c->cg_single_reduction = (int)value; break;
             case ONSAS_OPT_REORDER: require(value >= 0 && value <= 2, ONSAS_ERR_INVALID_ARG, "reorder must be 0, 1 or 2"); require(!c->finalized, ONSAS_ERR_INVALID_ARG, "ONSAS_OPT_REORDER must be set before onsas_finalize_mesh"); c->reorder = (int)value; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
         }

@@ -506,3 +506,53 @@ def test_library_side_reordering_is_invisible_to_the_caller(ob, oracle):
     assert st1["nnz_blocks"] == st0["nnz_blocks"] and st1["padded_block_slots"] <= st0["padded_block_slots"]
     for c in (plain, reord):
         c.close()
+
+
+def test_non_finite_residual_stops_the_solve_at_once(ob):
+    """A NaN in F_ext (or K, U) makes the CG residual non-finite: `res <= tol` is never true, so without a guard the solve would
+    run to maxiter = n_free iterations.  The solvers stop at once and report ONSAS_ERR_BREAKDOWN; the context stays usable."""
+    import time
+    m, mesh = cases.box_model(8, 4, 4, mat="svk")
+    for mode in (0, 1, 2):
+        ctx = ob.context_from_flat(m.xyz, tets=m.tets, mat_kind=m.mat_kind, mat_params=m.mat_params, free_dofs=m.free_dofs)
+        ctx.set_option(ob._lib.OPT_CG_MODE, mode)
+        F = mg.global_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["x1"], (0.1, 0.0, 0.0))
+        bad = F.copy()
+        bad[m.free_dofs[5]] = np.nan
+        ctx.set_Fext(bad)
+        t0 = time.perf_counter()
+        with pytest.raises(ob.OnsasError) as ei:
+            ctx.newton_step(ob.PRECOND_JACOBI)
+        assert ei.value.status == ob._lib.ERR_BREAKDOWN and time.perf_counter() - t0 < 5.0
+        ctx.set_U(np.zeros(mesh.n_nodes * 3))
+        ctx.set_Fext(F)
+        info = ctx.newton_step(ob.PRECOND_JACOBI)                 # the same context solves again
+        assert info.cg_residual <= info.cg_tol and np.isfinite(ctx.get_U()).all()
+        ctx.close()
+
+
+def test_two_contexts_with_different_meshes_interleave(ob):
+    """The dynamic shared-memory limit of a kernel is a per-device property shared by all contexts: a second context with a
+    narrower mesh (a 1-D truss chain plans a few KB for the streamed CG, a tet mesh ~200 KB) must not lower it under the
+    first one (round-1 advisor finding)."""
+    m, mesh = cases.box_model(8, 4, 4, mat="svk")
+    big = ob.context_from_flat(m.xyz, tets=m.tets, mat_kind=m.mat_kind, mat_params=m.mat_params, free_dofs=m.free_dofs)
+    F = mg.global_face_load(mesh.n_nodes, mesh.xyz, mesh.faces["x1"], (0.1, 0.0, 0.0))
+    big.set_Fext(F)
+    i0 = big.newton_step(ob.PRECOND_JACOBI)
+    mt, fext, p = cases.clamped_truss(50)
+    small = ob.context_from_flat(mt.xyz, trusses=mt.trusses, truss_area=mt.truss_area, truss_strain=ob.STRAIN_GREEN,
+                                 mat_kind=mt.mat_kind, mat_params=mt.mat_params, free_dofs=mt.free_dofs)
+    small.set_Fext(fext(0.1))
+    small.newton_step(ob.PRECOND_JACOBI, 1e-12)
+    big.set_U(np.zeros(mesh.n_nodes * 3))
+    i1 = big.newton_step(ob.PRECOND_JACOBI)                       # would fail with "invalid argument" if the limit had been lowered
+    assert i1.cg_iters == i0.cg_iters and i1.norm_r == i0.norm_r
+    for pre in (ob.PRECOND_TWO_LEVEL,):
+        big.set_U(np.zeros(mesh.n_nodes * 3))
+        small.set_U(np.zeros(len(mt.xyz)))
+        big.newton_step(pre)
+        small.newton_step(pre, 1e-12)
+        big.newton_step(pre)
+    big.close()
+    small.close()
