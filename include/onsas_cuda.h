@@ -85,10 +85,12 @@ typedef struct onsas_ctx onsas_ctx;
                                         dof list, face list and result stays in the caller's numbering.  2 = aggregate-major: the nodes of every aggregate of the
                                         two-level preconditioner are numbered consecutively (Z-curve inside an aggregate), so its aggregate-ordered
                                         passes stream through memory.  0 (default) keeps the caller's order */
-#define ONSAS_OPT_CG_SINGLE_REDUCTION 14 /* streamed persistent solver with the Jacobi preconditioner: 1 (default) = single-reduction recurrence
+#define ONSAS_OPT_CG_SINGLE_REDUCTION 14 /* streamed persistent solver, bit mask: bit 0 (default on) = Jacobi-PCG runs the single-reduction recurrence
                                             (Chronopoulos-Gear: one reduction of (r.r, r.u, u.Ku) and two grid barriers per iteration, one cross-GPU
-                                            all-reduce), 0 = the classic recurrence (three barriers, two all-reduces).  Same iterates in exact
-                                            arithmetic; precond = 0 always runs the classic one (IterativeSolvers' cg! step by step) */
+                                            all-reduce; the classic recurrence has three barriers and two all-reduces); bit 1 (default off) = the
+                                            two-level PCG too (three barriers instead of four, but more vector traffic: measured slower per iteration,
+                                            profiles/r48/sr_ab.log).  Same iterates in exact arithmetic; precond = 0 always runs the classic
+                                            recurrence (IterativeSolvers' cg! step by step) */
 #define ONSAS_OPT_TRUSS_MINBLOCKS 15  /* register budget of the truss assembly kernel: 2 = 120, 3 = 80, 4 = 64 registers (default: 8.2 G bars/s on the 10 M-bar lattice against 6.5 at 120) */
 #define ONSAS_OPT_COARSE_FUSED 11    /* two-level preconditioner: 1 = residual update in aggregate order, fused with w = Z^T r (default), 0 = separate pass */
 

@@ -198,7 +198,7 @@ struct onsas_ctx {
         void* kern_sr = nullptr;  // single-reduction recurrence (precond 0 / 1)
         size_t smem = 0;
     } st_plan;
-    int cg_single_reduction = 3;  // ONSAS_OPT_CG_SINGLE_REDUCTION: bit 0 = Jacobi-PCG, bit 1 = two-level PCG run the single-reduction recurrence
+    int cg_single_reduction = 1;  // ONSAS_OPT_CG_SINGLE_REDUCTION: bit 0 = Jacobi-PCG (default), bit 1 = two-level PCG run the single-reduction recurrence
     int force_mg = 0;  // diagnostics: run the multi-GPU kernel even with one rank
     int reorder = 0;   // ONSAS_OPT_REORDER: 1 = the nodes are renumbered along a Z-curve inside onsas_finalize_mesh (invisible to the caller)
     std::vector<std::pair<int32_t, int64_t>> opt_log;  // options in the order they were set (replayed on the device contexts of a group)

@@ -6,6 +6,7 @@ import math
 import numpy as np
 import pytest
 
+from onsas_jl_b200 import meshgen as mg
 from tests import cases
 from tests.golden import reference_vectors as G
 
