@@ -271,6 +271,34 @@ def run_strong_c4(args, ob, N, rank, dist, local_rank, barrier, max_over_ranks):
         else:
             out["newton_step_" + name] = None
     out["analytic"] = {"alpha_beta_start": [a_prev, b_prev], "alpha_beta_after_one_newton_step": [a_nw, b_nw], "alpha_beta_equilibrium": [a_eq, b_eq]}
+    # ---- the complete solve of the target sentence at this size: 8 load steps from U = 0 with the reference's control flow
+    #      (NonLinearStaticAnalyses.jl:70-104: load-step loop x Newton loop, isconverged! on the norms every rank receives --
+    #      they are all-reduced inside the solver, so every rank takes the same decisions).  From 4 GPUs on by default
+    #      (one GPU needs ~2 minutes for it).
+    if N >= args.c4_full_solve_min_gpus:
+        import math
+        tols = ob.ConvergenceSettings(1e-8, 1e-8, 30)
+        ctx.set_U(loc(np.zeros(mesh.n_nodes * 3)))
+        iters, cgs = [], []
+        barrier()
+        t0 = time.perf_counter()
+        for lam in np.linspace(1.0 / 8, 1.0, 8):
+            ctx.set_Fext(loc(Fext * lam))
+            it = ob.ResidualsIterationStep()
+            cg = 0
+            while isinstance(ob.isconverged(it, tols), ob.NotConvergedYet):
+                info = ctx.newton_step(ob.PRECOND_TWO_LEVEL, 1e-10)
+                it.update(info.norm_dU, info.norm_dU / info.norm_U if info.norm_U > 0 else math.inf,
+                          info.norm_r, info.norm_r / info.norm_Fext if info.norm_Fext > 0 else math.inf)
+                cg += int(info.cg_iters)
+            iters.append(it.iter)
+            cgs.append(cg)
+        barrier()
+        wall = max_over_ranks(time.perf_counter() - t0)
+        out["full_solve"] = {"workload": "examples/uniaxial_extension on this mesh: 8 load steps from U = 0, tolerances 1e-8, two-level PCG at reltol 1e-10",
+                             "wall_s": wall, "newton_iterations": iters, "reference_newton_iterations": [6, 5, 5, 4, 4, 4, 5, 5],
+                             "cg_iterations_per_load_step": cgs,
+                             "rel_error_vs_analytic_alpha2_beta_sqrt0.1": state_error(ctx, mesh, l2g, n_own, field(a_eq, b_eq), dist)}
     ctx.close()
     return out
 
@@ -589,6 +617,7 @@ def main():
     ap.add_argument("--no-c4", action="store_true", help="skip the configs[3] strong-scaling leg (39.9 M tets)")
     ap.add_argument("--c4-cells", type=int, default=188, help="cells per edge of the configs[3] cube (188 -> 39 868 032 tets)")
     ap.add_argument("--no-full-solve", action="store_true", help="skip the full 8-load-step solve leg")
+    ap.add_argument("--c4-full-solve-min-gpus", type=int, default=4, help="run the complete 8-load-step solve on the configs[3] mesh from this many GPUs on")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -310,7 +310,7 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
             // contributions in batches of PB: the PB code loads, then the PB * DIM value loads are independent of each other
             // (two dependent shared-memory round trips per batch instead of per contribution); the ADDS keep the ascending
             // element order.  Batch slots past the end read the CTA's block of zeros.
-            constexpr int PB = 4;
+            constexpr int PB = FAMILY == 0 ? 4 : 2;  // tets: 6.4 contributions per slot on the structured mesh; trusses: 1.5
             for (int q = q0; q < q1; q += PB) {
                 int cd[PB];
 #pragma unroll
