@@ -30,8 +30,9 @@ def nvlink_bytes():
     """sum over links of (tx, rx) KiB of GPU 0 (nvidia-smi nvlink -gt d), or None"""
     try:
         out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", "0"], capture_output=True, text=True, timeout=20).stdout
-        tx = sum(int(v) for v in re.findall(r"Data Tx: (\d+) KiB", out))
-        rx = sum(int(v) for v in re.findall(r"Data Rx: (\d+) KiB", out))
+        tx = sum(int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+        rx = sum(int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+        nvlink_bytes.raw = out[:600]
         return tx, rx
     except Exception:
         return None
@@ -74,6 +75,7 @@ for name, pre, sr in (("jacobi single-reduction", ob.PRECOND_JACOBI, 1), ("jacob
         if nv0 and nv1:
             rec["nvlink_gpu0_KiB_during_the_profiled_step"] = {"tx": nv1[0] - nv0[0], "rx": nv1[1] - nv0[1]}
             rec["nvlink_gpu0_bytes_per_iteration"] = {"tx": 1024.0 * (nv1[0] - nv0[0]) / max(int(info.cg_iters), 1), "rx": 1024.0 * (nv1[1] - nv0[1]) / max(int(info.cg_iters), 1)}
+        rec["nvidia_smi_nvlink_raw_head"] = getattr(nvlink_bytes, "raw", "")[:300]
         print(json.dumps(rec), flush=True)
 ctx.close()
 if dist is not None:
