@@ -190,7 +190,15 @@ struct onsas_ctx {
         cudaStream_t s_in = nullptr, s_out = nullptr, s_k2 = nullptr;
         cudaEvent_t ev_start = nullptr;
         std::vector<cudaEvent_t> ev_in, ev_k;
+        cudaEvent_t ev_join[2] = {nullptr, nullptr};
+        cudaGraphExec_t gexec = nullptr;        // the captured pipeline for the buffers (gU, gF)
+        const double* gU = nullptr;
+        double* gF = nullptr;
+        const double* seenU = nullptr;          // buffers of the previous call (a pair seen twice in a row is captured)
+        double* seenF = nullptr;
+        bool graph_failed = false;
     } hp;
+    int host_graph = 1;  // ONSAS_OPT_HOST_GRAPH
     struct StreamPlan {
         bool built = false, ok = false;
         int n_cw = 0, depth = 0, grid = 0, threads = 0;
@@ -415,6 +423,7 @@ void download(onsas_ctx* c, double* h, const double* d, size_t n);
 void check_deferred(onsas_ctx* c);
 void p2p_wire(onsas_ctx* c, const std::vector<unsigned char*>& win, const int64_t* remote_halo_off);
 void derive_element_kinds(onsas_ctx* c);
+void drop_host_graph(onsas_ctx* c);
 // group.inc: the same entry points on a multi-device context (global vectors in the caller's numbering)
 void grp_destroy(onsas_ctx* g);
 void grp_set_option(onsas_ctx* g, int32_t key, int64_t value);
@@ -512,12 +521,15 @@ void build_host_plan(onsas_ctx* c) {
     const int64_t ns = c->tab.n_slices;
     const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, c->host_chunks), ns));
     if (H.built && (int)H.node_hi.size() == nch) return;
+    drop_host_graph(c);
     host_range_plan(c->tab, c->host_chunks, c->host_mid_weight, H.slice0, H.node_hi);  // tables.cpp (CPU-tested)
     if (!H.s_in) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&H.s_in, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&H.s_out, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&H.s_k2, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&H.ev_start, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&H.ev_join[0], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&H.ev_join[1], cudaEventDisableTiming));
     }
     while ((int)H.ev_in.size() < nch) {
         cudaEvent_t a, b;
@@ -529,20 +541,16 @@ void build_host_plan(onsas_ctx* c) {
     H.built = true;
 }
 
-void assemble_host(onsas_ctx* c, const double* U, double* F) {
-    require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
-    const size_t nl = (size_t)c->n_local_dofs(), no = (size_t)c->n_own_dofs();
-    if (c->host_chunks <= 1 || c->tab.n_slices == 0 || (c->n_tets == 0 && c->n_trusses == 0)) {
-        // pipelining switched off: copy in, assemble, copy out.  (Multi-GPU pipelines too: U arrives with its halo part.)
-        CUDA_CHECK(cudaMemcpyAsync(c->U.p, U, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        launch_assemble(c);
-        if (nl > no) std::fill(F + no, F + nl, 0.0);
-        CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        download(c, F, c->Fint.p, no);
-        check_deferred(c);
-        return;
-    }
-    build_host_plan(c);
+void drop_host_graph(onsas_ctx* c) {
+    auto& H = c->hp;
+    if (H.gexec) cudaGraphExecDestroy(H.gexec);
+    H.gexec = nullptr;
+    H.gU = H.gF = nullptr;
+}
+
+// enqueues the pipelined assembly (no host synchronisation): U in as growing prefixes on the copy-in stream, the slice ranges
+// alternating on two compute streams, the rows of F_int out on the copy-out stream, the deferred-error flag last
+void enqueue_host_pipeline(onsas_ctx* c, const double* U, double* F) {
     auto& H = c->hp;
     struct Restore {  // the range / stream of "the next assembly launch" never outlives this call, whatever throws
         onsas_ctx* c;
@@ -554,9 +562,9 @@ void assemble_host(onsas_ctx* c, const double* U, double* F) {
     } restore{c};
     const int nch = (int)H.node_hi.size();
     const int bs = c->dim;
-    c->co.fresh = false;
     CUDA_CHECK(cudaEventRecord(H.ev_start, c->stream));  // earlier work on the compute stream may still read U / F_int
     CUDA_CHECK(cudaStreamWaitEvent(H.s_in, H.ev_start, 0));
+    CUDA_CHECK(cudaStreamWaitEvent(H.s_out, H.ev_start, 0));
     // consecutive ranges alternate between two compute streams: the first CTAs of range k + 1 fill the SMs that the
     // last wave of range k leaves idle (the ranges write disjoint rows of K, F_int and disjoint element records)
     const bool two = c->host_streams >= 2 && nch > 1;
@@ -585,11 +593,82 @@ void assemble_host(onsas_ctx* c, const double* U, double* F) {
         if (r1 > r0)
             CUDA_CHECK(cudaMemcpyAsync(F + r0 * bs, c->Fint.p + r0 * bs, (size_t)(r1 - r0) * bs * sizeof(double), cudaMemcpyDeviceToHost, H.s_out));
     }
-    c->asm_first = 0;
-    c->asm_count = -1;
-    if (nl > no) std::fill(F + no, F + nl, 0.0);  // halo part of F_int: not assembled on this rank
     CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, H.s_out));
-    CUDA_CHECK(cudaStreamSynchronize(H.s_out));  // the last kernel has finished too: the compute stream is idle
+}
+
+void assemble_host(onsas_ctx* c, const double* U, double* F) {
+    require(c->finalized, ONSAS_ERR_NOT_READY, "onsas_finalize_mesh has not been called");
+    const size_t nl = (size_t)c->n_local_dofs(), no = (size_t)c->n_own_dofs();
+    if (c->host_chunks <= 1 || c->tab.n_slices == 0 || (c->n_tets == 0 && c->n_trusses == 0)) {
+        // pipelining switched off: copy in, assemble, copy out.  (Multi-GPU pipelines too: U arrives with its halo part.)
+        CUDA_CHECK(cudaMemcpyAsync(c->U.p, U, nl * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        launch_assemble(c);
+        if (nl > no) std::fill(F + no, F + nl, 0.0);
+        CUDA_CHECK(cudaMemcpyAsync(c->h_flag, c->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        download(c, F, c->Fint.p, no);
+        check_deferred(c);
+        return;
+    }
+    build_host_plan(c);
+    auto& H = c->hp;
+    c->co.fresh = false;
+    if (nl > no) std::fill(F + no, F + nl, 0.0);  // halo part of F_int: not assembled on this rank
+    // The pipeline is ~80 stream operations (copies, kernels, events on four streams): enqueueing them costs the host about as
+    // much time as the device needs to run them.  When the caller keeps its state in the same pinned buffers from call to call
+    // (the reference's state vectors are persistent arrays), the whole pipeline is captured ONCE into a CUDA graph and every
+    // later call is a single graph launch.  Same operations, same order on every stream: bitwise the same results.
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeHost;
+    };
+    bool done = false;
+    if (c->host_graph && !H.graph_failed) {
+        if (H.gexec && H.gU == U && H.gF == F) {
+            CUDA_CHECK(cudaGraphLaunch(H.gexec, c->stream));
+            done = true;
+        } else if (H.seenU == U && H.seenF == F && is_pinned(U) && is_pinned(F)) {
+            drop_host_graph(c);
+            cudaGraph_t g = nullptr;
+            bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok) {
+                try {
+                    enqueue_host_pipeline(c, U, F);
+                    // join the forked streams back into the capturing one
+                    CUDA_CHECK(cudaEventRecord(H.ev_join[0], H.s_in));
+                    CUDA_CHECK(cudaStreamWaitEvent(c->stream, H.ev_join[0], 0));
+                    CUDA_CHECK(cudaEventRecord(H.ev_join[1], H.s_out));
+                    CUDA_CHECK(cudaStreamWaitEvent(c->stream, H.ev_join[1], 0));
+                } catch (...) {
+                    ok = false;
+                }
+                if (cudaStreamEndCapture(c->stream, &g) != cudaSuccess || g == nullptr) ok = false;
+            }
+            if (ok && cudaGraphInstantiate(&H.gexec, g, 0) != cudaSuccess) ok = false;
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            if (ok) {
+                H.gU = U;
+                H.gF = F;
+                CUDA_CHECK(cudaGraphLaunch(H.gexec, c->stream));
+                done = true;
+            } else {
+                H.gexec = nullptr;
+                H.graph_failed = true;  // this driver / pipeline shape cannot be captured: stay with the eager path
+            }
+        }
+    }
+    H.seenU = U;
+    H.seenF = F;
+    if (done) {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    } else {
+        enqueue_host_pipeline(c, U, F);
+        CUDA_CHECK(cudaStreamSynchronize(H.s_out));  // the last kernel has finished too: the compute stream is idle
+    }
     check_deferred(c);
 }
 
@@ -1104,6 +1183,9 @@ int32_t onsas_destroy(onsas_ctx* c) {
         if (ev) cudaEventDestroy(ev);
     if (c->h_st) cudaFreeHost(c->h_st);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    drop_host_graph(c);
+    if (c->hp.ev_join[0]) cudaEventDestroy(c->hp.ev_join[0]);
+    if (c->hp.ev_join[1]) cudaEventDestroy(c->hp.ev_join[1]);
     if (c->hp.s_in) cudaStreamDestroy(c->hp.s_in);
     if (c->hp.s_out) cudaStreamDestroy(c->hp.s_out);
     if (c->hp.s_k2) cudaStreamDestroy(c->hp.s_k2);
@@ -1120,6 +1202,7 @@ int32_t onsas_set_stream(onsas_ctx* c, void* s) {
     return guard(c, [&] {
         require(!c->grp || c->grp->sub.size() == 1, ONSAS_ERR_UNSUPPORTED, "a multi-device context runs on its own streams (one per device)");
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        drop_host_graph(c);
         c->stream = s ? (cudaStream_t)s : c->own_stream;
         if (c->grp) {  // a renumbered single-device context: its device context does the work
             onsas_ctx* d = c->grp->sub[0];
@@ -1145,12 +1228,14 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_HOST_MID_WEIGHT: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "weight must be 1..64"); c->host_mid_weight = (int)value; c->hp.built = false; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
+            case ONSAS_OPT_HOST_GRAPH: c->host_graph = value != 0; c->hp.graph_failed = false; break;
             case ONSAS_OPT_TRUSS_MINBLOCKS: require(value >= 2 && value <= 4, ONSAS_ERR_INVALID_ARG, "truss min blocks must be 2..4"); c->truss_minb = (int)value; break;
             case ONSAS_OPT_CG_SINGLE_REDUCTION: require(value >= 0 && value <= 3, ONSAS_ERR_INVALID_ARG, "single-reduction mask must be 0..3"); c->cg_single_reduction = (int)value; break;
             case ONSAS_OPT_REORDER: require(value >= 0 && value <= 2, ONSAS_ERR_INVALID_ARG, "reorder must be 0, 1 or 2"); require(!c->finalized, ONSAS_ERR_INVALID_ARG, "ONSAS_OPT_REORDER must be set before onsas_finalize_mesh"); c->reorder = (int)value; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
         }
         c->opt_log.emplace_back(key, value);
+        drop_host_graph(c);  // a captured pipeline bakes the launch configuration in
         if (c->grp && key != ONSAS_OPT_REORDER) grp_set_option(c, key, value);
     });
 }
@@ -1185,6 +1270,7 @@ int32_t onsas_set_materials(onsas_ctx* c, int32_t n, const int32_t* kind, const 
             // are re-derived in place -- the tables, U, F_ext and the load patterns of the mesh stay as they are
             if (c->grp) return grp_materials_changed(c);
             derive_element_kinds(c);
+            drop_host_graph(c);  // the element kind selects the kernel instantiation
             c->mat_kind.upload(c->h_mat_kind, c->stream);
             c->mat_params.upload(c->h_mat_params, c->stream);
             CUDA_CHECK(cudaStreamSynchronize(c->stream));
