@@ -92,8 +92,9 @@ typedef struct onsas_ctx onsas_ctx;
                                             profiles/r48/sr_ab.log).  Same iterates in exact arithmetic; precond = 0 always runs the classic
                                             recurrence (IterativeSolvers' cg! step by step) */
 #define ONSAS_OPT_TRUSS_MINBLOCKS 15  /* register budget of the truss assembly kernel: 2 = 120, 3 = 80, 4 = 64 registers (default: 8.2 G bars/s on the 10 M-bar lattice against 6.5 at 120) */
-#define ONSAS_OPT_HOST_GRAPH 16      /* onsas_assemble_host: 1 (default) = when the same pinned buffers are passed twice in a row, the pipeline of copies and
-                                        kernels is captured once into a CUDA graph and every later call is one graph launch; 0 = always enqueue it */
+#define ONSAS_OPT_HOST_GRAPH 16      /* onsas_assemble_host: 1 = when the same pinned buffers are passed twice in a row, the pipeline of copies and kernels is
+                                        captured once into a CUDA graph and every later call is one graph launch; 0 (default) = always enqueue it
+                                        (measured on B200: the replayed 80-node, 4-stream graph takes 0.409 ms per pass, the eager enqueue 0.383) */
 #define ONSAS_OPT_COARSE_FUSED 11    /* two-level preconditioner: 1 = residual update in aggregate order, fused with w = Z^T r (default), 0 = separate pass */
 
 /* ---------------------------------------------------------------- life cycle */

@@ -17,8 +17,9 @@ hU, hF = bench.pinned(ctx.n_dofs), bench.pinned(ctx.n_dofs)
 hU[:] = U_half
 lib, h = ctx._lib, ctx._h
 K = 50
-for chunks, weight, streams in ((4, 4, 1), (12, 3, 2), (10, 3, 2), (12, 2, 2), (16, 3, 2), (16, 2, 2), (20, 3, 2), (24, 3, 2), (24, 2, 2), (32, 2, 2),
-                                (12, 3, 1), (4, 4, 1), (12, 3, 2), (16, 3, 2), (20, 3, 2), (24, 2, 2)):
+for chunks, weight, streams, graph in ((4, 4, 1, 0), (12, 3, 2, 0), (8, 3, 2, 0), (6, 2, 2, 0), (10, 3, 2, 0), (12, 2, 2, 0), (16, 3, 2, 0), (20, 3, 2, 0), (24, 2, 2, 0),
+                                       (12, 3, 1, 0), (12, 3, 2, 1), (6, 2, 2, 1), (4, 4, 1, 1), (4, 2, 2, 1), (12, 3, 2, 0), (8, 3, 2, 0), (16, 3, 2, 0)):
+    ctx.set_option(ob._lib.OPT_HOST_GRAPH, graph)
     ctx.set_option(ob._lib.OPT_HOST_STREAMS, streams)
     ctx.set_option(ob._lib.OPT_HOST_CHUNKS, chunks)
     ctx.set_option(ob._lib.OPT_HOST_MID_WEIGHT, weight)
@@ -28,7 +29,7 @@ for chunks, weight, streams in ((4, 4, 1), (12, 3, 2), (10, 3, 2), (12, 2, 2), (
     for _ in range(K):
         assert lib.onsas_assemble_host(h, hU, hF) == 0
     ms = (time.perf_counter() - t0) * 1e3 / K
-    print(f"chunks={chunks:3d} mid_weight={weight:2d} streams={streams}  {ms:.4f} ms per call  {mesh.n_tets / ms / 1e6:.3f} G tets/s", flush=True)
+    print(f"chunks={chunks:3d} mid_weight={weight:2d} streams={streams} graph={graph}  {ms:.4f} ms per call  {mesh.n_tets / ms / 1e6:.3f} G tets/s", flush=True)
 t0 = time.perf_counter()
 for _ in range(K):
     assert lib.onsas_set_U(h, hU) == 0
@@ -38,6 +39,7 @@ ms = (time.perf_counter() - t0) * 1e3 / K
 print(f"three calls  {ms:.4f} ms per step  {mesh.n_tets / ms / 1e6:.3f} G tets/s")
 # pageable host buffers (no overlap possible): still correct, and how much slower
 pU, pF = np.array(hU), np.empty_like(np.asarray(hF))
+ctx.set_option(ob._lib.OPT_HOST_GRAPH, 0)
 ctx.set_option(ob._lib.OPT_HOST_CHUNKS, 4)
 ctx.set_option(ob._lib.OPT_HOST_MID_WEIGHT, 4)
 t0 = time.perf_counter()

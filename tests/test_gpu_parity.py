@@ -571,6 +571,7 @@ def test_assemble_host_graph_replay_is_bitwise_the_eager_pipeline(ob):
     hU = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
     hF = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
     rng = np.random.default_rng(8)
+    ctx.set_option(ob._lib.OPT_HOST_GRAPH, 1)
 
     def three_calls(U):
         ctx.set_U(U)
