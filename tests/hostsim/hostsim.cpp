@@ -145,6 +145,38 @@ int64_t hs_stat(HsModel* m, int which) {
     }
 }
 
+// invariants of the slice node lists the assembly kernel stages in shared memory (tables.cpp): out = {violations, lists that are
+// not strictly ascending, pairs whose local indices do not map back to their element's nodes, elements whose record is written
+// by no pair or by more than one (among the elements that touch an owned node), largest list, total list entries}
+void hs_check_slice_nodes(HsModel* m, int family, const int32_t* conn, int64_t n_elem, int64_t* out /*[6]*/) {
+    const MeshTables& t = m->tab;
+    const FamilyTables& F = t.fam[family];
+    for (int k = 0; k < 6; ++k) out[k] = 0;
+    if (F.n_elem == 0) return;
+    std::vector<int> writers((size_t)n_elem, 0), touched((size_t)n_elem, 0);
+    for (int64_t sl = 0; sl < t.n_slices; ++sl) {
+        const SliceHdr& H = F.hdr[sl];
+        const int32_t* sn = F.snodes.data() + H.snode_base;
+        out[4] = std::max<int64_t>(out[4], H.n_snodes);
+        out[5] += H.n_snodes;
+        for (int k = 1; k < H.n_snodes; ++k)
+            if (sn[k] <= sn[k - 1]) out[1]++;
+        for (int tt = 0; tt < H.n_pairs; ++tt) {
+            const int64_t p = H.pair_base + tt;
+            const int64_t e = F.pair_code[p] / F.npe;
+            touched[e] = 1;
+            for (int b = 0; b < F.npe; ++b) {
+                const uint16_t li = F.pair_lnodes[(size_t)p * F.npe + b] & 0x7fffu;
+                if (li >= H.n_snodes || sn[li] != conn[e * F.npe + b]) out[2]++;
+            }
+            if (F.pair_lnodes[(size_t)p * F.npe] & 0x8000u) writers[e]++;
+        }
+    }
+    for (int64_t e = 0; e < n_elem; ++e)
+        if (touched[e] && writers[e] != 1) out[3]++;
+    out[0] = out[1] + out[2] + out[3];
+}
+
 // slice ranges of the pipelined host-buffer assembly (tables.cpp::host_range_plan); returns the number of ranges
 int hs_host_plan(HsModel* m, int chunks, int mid_weight, int64_t* slice0 /*[chunks+1]*/, int64_t* node_hi /*[chunks]*/) {
     std::vector<int64_t> s0, hi;

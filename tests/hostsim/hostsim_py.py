@@ -22,6 +22,8 @@ hs.hs_nnz.argtypes = [_vp]
 hs.hs_stat.restype = C.c_int64
 hs.hs_stat.argtypes = [_vp, C.c_int]
 hs.hs_host_plan.restype = C.c_int
+hs.hs_check_slice_nodes.restype = None
+hs.hs_check_slice_nodes.argtypes = [_vp, C.c_int, _vp, C.c_int64, _lp]
 hs.hs_host_plan.argtypes = [_vp, C.c_int, C.c_int, _lp, _lp]
 hs.hs_assemble.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _ip, _dp, _dp, _dp, C.c_int]
 hs.hs_get.argtypes = [_vp, _lp, _ip, _dp, _dp, _dp, _dp]
@@ -54,6 +56,12 @@ class HostSim:
 
     def stats(self):
         return [hs.hs_stat(self.h, i) for i in range(5)]
+
+    def check_slice_nodes(self, family, conn):
+        out = np.zeros(6, np.int64)
+        conn = np.ascontiguousarray(conn, np.int32)
+        hs.hs_check_slice_nodes(self.h, family, conn.ctypes.data_as(_vp), len(conn), out)
+        return dict(zip(("violations", "unsorted", "bad_index", "bad_writer", "max_list", "entries"), (int(v) for v in out)))
 
     def host_plan(self, chunks, mid_weight):
         """(slice0 [n+1], node_hi [n]) of onsas_assemble_host's slice ranges."""

@@ -146,3 +146,26 @@ def test_host_range_plan_of_the_pipelined_assembly(hostsim, oracle):
                     assert hi[0] < 0.35 * n          # the first kernel starts after a small prefix of U
                 else:
                     assert hi[0] > 0.9 * n           # random numbering: (almost) everything first
+
+
+def test_slice_node_lists_the_assembly_kernel_stages(hostsim, oracle):
+    """The per-slice node lists (tables.cpp, round 2): every list is strictly ascending, every pair's 16-bit indices map back to
+    its element's nodes, exactly one pair of every element carries the "writes the element record" bit -- also when only part of
+    the nodes are owned (multi-GPU: the pair of the element's first OWNED node), and on a structured mesh a slice lists a small
+    neighbourhood (the point of staging it in shared memory) while a random numbering lists almost every node a pair touches."""
+    m, mesh = cases.box_model(10, 6, 5, mat="svk")
+    sim = hostsim.HostSim(m)
+    chk = sim.check_slice_nodes(0, m.tets)
+    assert chk["violations"] == 0 and chk["max_list"] <= 100          # 8 consecutive x-nodes +- 1 in every direction: <= 10 x 3 x 3
+    rng = np.random.default_rng(2)
+    perm = rng.permutation(m.xyz.shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    shuffled = oracle.FlatModel(xyz=m.xyz[inv], tets=perm[m.tets].astype(np.int32), mat_kind=m.mat_kind, mat_params=m.mat_params,
+                                free_dofs=np.arange(len(perm) * 3))
+    chk2 = hostsim.HostSim(shuffled).check_slice_nodes(0, shuffled.tets)
+    assert chk2["violations"] == 0 and chk2["entries"] > 1.5 * chk["entries"]
+    part = hostsim.HostSim(m, n_rows=200).check_slice_nodes(0, m.tets)       # only the first 200 nodes are rows: elements whose
+    assert part["violations"] == 0 and 0 < part["entries"] < chk["entries"]   # first node is a halo node still have one writer
+    mt, _, _ = cases.von_mises_truss(0)
+    assert hostsim.HostSim(mt).check_slice_nodes(1, mt.trusses)["violations"] == 0
