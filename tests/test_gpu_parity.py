@@ -594,3 +594,35 @@ def test_assemble_host_graph_replay_is_bitwise_the_eager_pipeline(ob):
     np.testing.assert_array_equal(hF, ref)
     np.testing.assert_array_equal(ctx.assemble_host(np.array(hU)), ref)   # pageable buffers: eager
     ctx.close()
+
+
+def test_material_swap_on_a_finalized_mesh_keeps_the_state(ob):
+    """onsas_set_materials after onsas_finalize_mesh (replace!(s, material), Structures.jl) re-derives the element kinds in
+    place: U, F_ext and the load patterns survive, and the next assembly equals a fresh context of the new material bit for bit
+    (round-1 advisor finding: the swap used to invalidate the mesh and silently drop the solver state)."""
+    m, mesh = cases.box_model(8, 4, 4, mat="svk")
+    K, mu = 1.0 / (3 * 0.4), 1.0 / 2.6
+    ctx = ob.context_from_flat(m.xyz, tets=m.tets, mat_kind=m.mat_kind, mat_params=m.mat_params, free_dofs=m.free_dofs)
+    ctx.add_face_load(mesh.faces["x1"], 0, [1.0, 0.0, 0.0])
+    ctx.apply_loads([0.3])
+    U = cases.random_U(m, 0.02)
+    ctx.set_U(U)
+    F0 = ctx.get_Fext()
+    ctx.set_materials([ob.MAT_NEOHOOKEAN], [[K, mu]])
+    np.testing.assert_array_equal(ctx.get_U(), U)
+    np.testing.assert_array_equal(ctx.get_Fext(), F0)
+    ctx.apply_loads([0.6])                                         # the pattern is still registered
+    np.testing.assert_allclose(ctx.get_Fext(), 2 * F0, rtol=1e-15)
+    ctx.assemble()
+    fresh = ob.context_from_flat(m.xyz, tets=m.tets, mat_kind=[ob.MAT_NEOHOOKEAN], mat_params=[[K, mu]], free_dofs=m.free_dofs)
+    fresh.set_U(U)
+    fresh.assemble()
+    np.testing.assert_array_equal(ctx.get_Fint(), fresh.get_Fint())
+    for a, b in zip(ctx.get_csr(), fresh.get_csr()):
+        np.testing.assert_array_equal(a, b)
+    info = ctx.newton_step(ob.PRECOND_TWO_LEVEL)                   # and the coarse operator follows the new K
+    assert info.cg_residual <= info.cg_tol
+    with pytest.raises(ob.OnsasError):
+        ctx.set_materials([7], [[1.0, 1.0]])                       # unknown kind
+    ctx.close()
+    fresh.close()
