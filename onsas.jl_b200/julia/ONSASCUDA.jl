@@ -180,9 +180,11 @@ is not a face load (the host `apply!` + `onsas_set_Fext` path is used then).  `n
 """
 function register_loads!(ctx::CudaContext, s::AbstractStructure, node_index::AbstractDict)
     factors = Function[]
-    lbcs = load_bcs(boundary_conditions(s))
-    all(ents -> all(e -> e isa TriangularFace, ents), values(lbcs)) || return nothing   # decide before anything is registered
-    for (bc, ents) in pairs(lbcs)
+    bcs = boundary_conditions(s)
+    lbcs = load_bcs(bcs)                             # Vector of load BCs (StructuralBoundaryConditions.jl:188-192); bcs[bc] = its entities
+    all(bc -> all(e -> e isa TriangularFace, bcs[bc]), lbcs) || return nothing   # decide before anything is registered
+    for bc in lbcs
+        ents = bcs[bc]
         tri = Int32[node_index[n] for e in ents for n in nodes(e)]              # 3 x n_faces, already 0-based
         pid = Ref{Int32}(-1)
         if bc isa Pressure
