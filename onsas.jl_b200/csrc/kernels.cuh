@@ -985,6 +985,11 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double
             __syncthreads();
             if (tid < CD * CD) {  // thread (r, c): nodes in ascending order, blocks in storage order -> a fixed summation order
                 const int r = tid / CD, c = tid % CD;
+                // consecutive blocks mostly belong to the same target aggregate (a node's neighbours are its own aggregate's
+                // nodes, except at the aggregate's surface): their contributions are summed in a register and meet the row in
+                // shared memory once per run -- no read-modify-write chain through shared memory per block
+                int run_b = -1;
+                double run = 0.0;
                 for (int w = 0; w < CO_NW; ++w) {
                     const int nbw = s_nb[w];
                     if (nbw == 0) continue;
@@ -1004,9 +1009,15 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double
                             for (int qq = 0; qq < BS; ++qq) t += Kb[p * BS + qq] * zj[qq];
                             acc += zi[p] * t;
                         }
-                        erow[(size_t)r * nc + b * CD + c] += acc;
+                        if (b != run_b) {
+                            if (run_b >= 0) erow[(size_t)r * nc + run_b * CD + c] += run;
+                            run_b = b;
+                            run = 0.0;
+                        }
+                        run += acc;
                     }
                 }
+                if (run_b >= 0) erow[(size_t)r * nc + run_b * CD + c] += run;
             }
             if (!__syncthreads_or(left > CO_WB)) break;  // barrier (staging buffers are free again) + "another round?"
         }
