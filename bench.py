@@ -162,6 +162,13 @@ def build_problem(cells: int, n_ranks: int):
     return mesh, free, U_half, U_prev, Fext
 
 
+def workload_config(cells, n_gpus, n_tets, n_dofs):
+    """`config` of the JSON line: the workload only (identical in both arms at N = 1), nothing about the implementation."""
+    return {"workload": f"examples/uniaxial_compression NeoHookean tet cube (configs[1]), structured {cells}^3 cells per GPU, "
+                        "state = analytic homogeneous field at load factor 0.5",
+            "n_tets": int(n_tets), "n_dofs": int(n_dofs), "l2": "inputs larger than L2 (~0.4 GB touched per pass)"}
+
+
 def pinned(n):
     import torch
     return torch.empty(n, dtype=torch.float64).pin_memory().numpy()
@@ -503,12 +510,11 @@ def run_ours(args):
         "metric": "tet_fint_Kt_assembled_elements_per_s", "value": value, "unit": "tets/s", "n_gpus": N, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"examples/uniaxial_compression NeoHookean tet cube, structured {args.cells}^3 cells per GPU "
-                               f"({n_tets_total} tets total), state = analytic homogeneous field at load factor 0.5",
-                   "n_tets": n_tets_total, "n_dofs": mesh.n_nodes * 3, "l2": "inputs larger than L2 (~0.4 GB touched per pass)", "extra_warmup_steps": extra_warmup,
-                   "partition": "single GPU" if N == 1 else f"RCB slabs, {N} ranks (library partitioner), no exchange inside the assembly (U carries its halo part); CG: " +
-                                ("one launch per phase, NCCL between them" if args.no_p2p else
-                                 "persistent TMA-streamed kernel, halo + all-reduce pushed over NVLink peer memory")},
+        "config": workload_config(args.cells, N, n_tets_total, mesh.n_nodes * 3),
+        "implementation": {"extra_warmup_steps": extra_warmup,
+                           "partition": "single GPU" if N == 1 else f"RCB slabs, {N} ranks (library partitioner), no exchange inside the assembly (U carries its halo part); CG: " +
+                                        ("one launch per phase, NCCL between them" if args.no_p2p else
+                                         "persistent TMA-streamed kernel, halo + all-reduce pushed over NVLink peer memory")},
         "newton_step_ms": nw[0], "newton_step": {"ms_assemble": nw[1], "ms_solve": nw[2], "cg_iters": nw[3], "precond": "jacobi",
                                                   "cg_reltol": float(np.sqrt(np.finfo(np.float64).eps)), "rel_residual_in": nw[4],
                                                   "rel_dU": nw[5]},
@@ -596,9 +602,9 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "tet_fint_Kt_assembled_elements_per_s", "value": val, "unit": "tets/s",
            "n_gpus": args.gpus, "steps": Kb, "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"examples/uniaxial_compression NeoHookean tet cube, structured {cells}^3 cells ({mesh.n_tets} tets), "
-                                  "reference algorithm restated in C (ONSAS.jl is Julia; no Julia toolchain in this image)",
-                      "note": "the CPU arm always runs the 1-GPU mesh (rates are compared: tets/s); at --gpus N > 1 our arm's mesh is N times larger"},
+           "config": workload_config(cells, 1, mesh.n_tets, mesh.n_nodes * 3),   # the same keys and strings as our arm's line at N = 1
+           "implementation": {"what": "the reference's algorithm restated in C (ONSAS.jl is Julia; no Julia toolchain in this image), OpenMP on all host cores",
+                              "note": "the CPU arm always runs the 1-GPU mesh (rates are compared: tets/s); at --gpus N > 1 our arm's mesh is N times larger"},
            "cpu_baseline": {"value": val, "unit": "tets/s", "cores": cores, "kind": "port",
                             "sample": f"{Kb} full assembly passes, OpenMP over elements + row-parallel gather"},
            "e2e": {"value": val, "unit": "tets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
