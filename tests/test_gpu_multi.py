@@ -138,3 +138,34 @@ def test_reference_api_on_two_devices(ob):
     Ua = mg.homogeneous_field(mesh.xyz, 2.0, math.sqrt(0.1))
     assert np.abs(sol.U[-1] - Ua).max() < 1e-8 * np.abs(Ua).max()
     assert np.abs(sol.tet_stress[-1][:, 0] - 3.0).max() < 1e-7
+
+
+def test_truss_lattice_on_two_devices_and_reordered(ob):
+    """Trusses through the multi-device context (and through the library-side renumbering on one device): a clamped, pulled and
+    sheared braced lattice, large-displacement Newton -- same iterates as the plain single-device context."""
+    _need_two_gpus()
+    lat = mg.truss_lattice(10, 4, 4, 2.0)
+    E, A = 210e9, 2.5e-3
+    fixed = {c: lat.node_sets["x0"] for c in range(3)}
+    free = mg.free_dofs_from_fixed(lat.n_nodes, 3, fixed)
+    F = np.zeros((lat.n_nodes, 3))
+    F[lat.node_sets["x1"], 0] = 0.02 * E * A
+    F[lat.node_sets["x1"], 2] = 0.002 * E * A
+    kw = dict(trusses=lat.bars, truss_area=np.full(lat.n_bars, A), truss_strain=ob.STRAIN_GREEN, mat_kind=[ob.MAT_SVK],
+              mat_params=[[0.0, E / 2]], free_dofs=free)
+    ctxs = [ob.context_from_flat(lat.xyz, device=0, **kw), ob.context_from_flat(lat.xyz, device=[0, 1], **kw),
+            ob.context_from_flat(lat.xyz, device=0, reorder=1, **kw), ob.context_from_flat(lat.xyz, device=[1, 0], reorder=2, **kw)]
+    for c in ctxs:
+        c.set_Fext(F.ravel())
+    for it in range(7):
+        infos = [c.newton_step(ob.PRECOND_JACOBI, 1e-13) for c in ctxs]
+        for i in infos[1:]:
+            assert i.norm_r == pytest.approx(infos[0].norm_r, rel=1e-6, abs=1e-9 * infos[0].norm_Fext)
+    U0 = ctxs[0].get_U()
+    assert infos[0].norm_r < 1e-8 * infos[0].norm_Fext and np.abs(U0).max() > 0.01
+    for c in ctxs[1:]:
+        assert cases.rel_err(c.get_U(), U0) < 1e-9
+        for a, b in zip(c.get_stress_strain(ob.FAMILY_TRUSS), ctxs[0].get_stress_strain(ob.FAMILY_TRUSS)):
+            np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-6 * E * 1e-3)
+    for c in ctxs:
+        c.close()
