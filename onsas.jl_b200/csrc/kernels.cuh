@@ -500,6 +500,23 @@ struct CoarseArgs {
     const double* Einv;        // [nc][nc]
     double* w;                 // [nc]  Z^T r
     double* y;                 // [nc]  E^-1 w
+    int n_cols;                // nodes that carry aggregate data: n_rows (rank-local level) or all local nodes (global level)
+    int agg_row0;              // global id of the first aggregate of this rank (0 for the rank-local level)
+    // ---- global coarse level across ranks (ONSAS_OPT_COARSE_GLOBAL, n_ranks > 1): with level-2 aggregates that are unions of
+    //      this rank's aggregates (Z2 = Z T), M^-1 = D^-1 + Z [blockdiag_rank(E^-1) + T E2^-1 T^T] Z^T, E2 = Z2^T K Z2 assembled by
+    //      all ranks and inverted on each.  Per application: y = E^-1 w + G w2 with G = T (E2^-1)[own rows, :] precomputed and
+    //      w2 = all ranks' T^T w, all-gathered over the peer window in the LL format.
+    int glob;                  // 1 = on
+    int nc2, n2_own, agg2_first;   // global coarse dofs; this rank's level-2 aggregates and the global id of its first
+    const double* G;               // [nc][nc2]
+    const int32_t* child_ptr;      // [n2_own+1] the (consecutive) level-1 aggregates of each own level-2 aggregate
+    const double* dvec;            // [n_agg][3] centroid of a level-1 aggregate minus its parent's
+    unsigned long long* w2_ll;     // local LL receive buffer: [2][nc2] pairs of words
+    unsigned long long* const* peer_w2;  // [n_ranks] the same buffer on every rank
+    double* w2_plain;              // [nc2] the gathered vector as plain doubles (written by one CTA, read by all)
+    unsigned int* w2_flag;         // epoch of the content of w2_plain
+    unsigned long long* w2_epoch;  // the epoch counter, persists across launches
+    int n_ranks;
 };
 
 struct CgArgs {
@@ -967,7 +984,7 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double
                 const int64_t j = A.col[(base + s0 + lane) * C + lrow];
                 int b = -1;
                 unsigned mj = 0;
-                if (j < A.n_rows) {
+                if (j < G.n_cols) {
                     b = G.agg[j];
                     for (int c = 0; c < BS; ++c) mj |= (unsigned)(A.mask[j * BS + c] & 1) << c;
                     if (rbm)
@@ -1025,12 +1042,61 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double
     // coarse dofs without any free fine dof: unit diagonal keeps E invertible (their w is always 0).  With rotations a
     // degenerate aggregate (collinear nodes) has a rotation that moves nothing: E + 1e-9 diag(E) stays positive definite.
     if (tid < CD) {
-        double& d = erow[(size_t)tid * nc + a * CD + tid];
+        double& d = erow[(size_t)tid * nc + (a + G.agg_row0) * CD + tid];
         if (d == 0.0) d = 1.0;
         else if (rbm) d *= 1.0 + 1e-9;
     }
     __syncthreads();
     for (int k = tid; k < CD * nc; k += CO_THREADS) E[(size_t)(a * CD) * nc + k] = erow[k];
+}
+
+// ---- global coarse level: exchange of the rows of E2 over the peer window, and the folded operator G
+// copies this rank's rows of E2 into every peer's E2 (plain peer stores; the flags follow in a later kernel of the same stream)
+__global__ void k_push_rows(const double* __restrict__ src, size_t n, double* const* peers, int n_ranks, int rank, size_t dst_off) {
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == rank) continue;
+        double* dst = peers[r] + dst_off;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+}
+// "my rows of refresh `epoch` have landed": one flag per source rank in every peer's window
+__global__ void k_set_flags(unsigned long long* const* peer_flags, int n_ranks, int rank, unsigned long long epoch) {
+    const int r = threadIdx.x;
+    if (r < n_ranks && r != rank) {
+        __threadfence_system();
+        *(volatile unsigned long long*)(peer_flags[r] + rank) = epoch;
+    }
+}
+// waits until every other rank's rows of refresh `epoch` have landed here (watchdog: err = 2)
+__global__ void k_wait_flags(const unsigned long long* flags, int n_ranks, int rank, unsigned long long epoch, int* err) {
+    const int r = threadIdx.x;
+    if (r < n_ranks && r != rank) {
+        const long long t0 = clock64();
+        while (*(volatile const unsigned long long*)(flags + r) < epoch) {
+            if (clock64() - t0 > 8000000000LL) {
+                *err = 2;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+// G = T (E2^-1)[own rows, :]: row (a, i) of G is the row of E2^-1 of a's parent for the same coarse dof, plus, for the
+// translations, the parent's rotation rows times the offset d = c(a) - c(parent)  (t_child = t_parent + omega_parent x d)
+__global__ void k_build_G(const double* __restrict__ E2inv, int nc2, int nc, const int32_t* __restrict__ parent_of, int agg2_first,
+                          const double* __restrict__ dvec, double* __restrict__ G) {
+    const int k = blockIdx.x;
+    if (k >= nc) return;
+    const int a = k / 6, i = k % 6;
+    const size_t gp = (size_t)(agg2_first + parent_of[a]) * 6;
+    const double d0 = dvec[a * 3], d1 = dvec[a * 3 + 1], d2 = dvec[a * 3 + 2];
+    for (int j = threadIdx.x; j < nc2; j += blockDim.x) {
+        double v = E2inv[(gp + i) * nc2 + j];
+        if (i == 0) v += d2 * E2inv[(gp + 4) * nc2 + j] - d1 * E2inv[(gp + 5) * nc2 + j];
+        else if (i == 1) v += d0 * E2inv[(gp + 5) * nc2 + j] - d2 * E2inv[(gp + 3) * nc2 + j];
+        else if (i == 2) v += d1 * E2inv[(gp + 3) * nc2 + j] - d0 * E2inv[(gp + 4) * nc2 + j];
+        G[(size_t)k * nc2 + j] = v;
+    }
 }
 
 // In-place Gauss-Jordan inversion of the SPD coarse matrix (no pivoting) in ONE cooperative launch.  The matrix is
@@ -1469,6 +1535,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     // y = E^-1 w once w is complete: barrier, then one warp per row of the dense inverse (L2-resident; 16-byte loads,
     // 12 + 12 of them in flight per lane).  z is never stored: r.z = sum r^2 d + w.y, so this leaves y in memory and
     // returns the thread's share of w.y; the p update forms z_i = d_i r_i + (Z y)_i on the fly.
+    unsigned int co_apps = 0;  // applications of the global coarse level in this launch (its epochs continue across launches)
     // row k of y = E^-1 w by one warp (the dense inverse is L2-resident; 16-byte loads, 12 + 12 of them in flight per lane);
     // the result is valid in every lane
     auto einv_row_dot = [&](int k) -> double {
@@ -1510,14 +1577,64 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
         if (profiling) tca = clock64();
         grid.sync();
         cprof(10);
+        unsigned int e2 = 0;
+        if (G.glob) {
+            // w2 = T^T w of this rank's level-2 aggregates -> every rank (LL words); one CTA turns the gathered vector into
+            // plain doubles for the row dots below
+            e2 = (unsigned int)(*G.w2_epoch) + co_apps + 1u;
+            const int par = (int)(e2 & 1u);
+            if (blockIdx.x == 0) {
+                for (int t = tid; t < G.n2_own * 6; t += ST_THREADS) {
+                    const int P2 = t / 6, q = t % 6;
+                    double v = 0.0;
+                    for (int a = G.child_ptr[P2]; a < G.child_ptr[P2 + 1]; ++a) {
+                        const double* wa = G.w + (size_t)a * 6;
+                        v += __ldcg(wa + q);
+                        if (q >= 3) {  // m2 = m1 + d x f1
+                            const double* d = G.dvec + (size_t)a * 3;
+                            const double f0 = __ldcg(wa), f1 = __ldcg(wa + 1), f2 = __ldcg(wa + 2);
+                            v += q == 3 ? d[1] * f2 - d[2] * f1 : q == 4 ? d[2] * f0 - d[0] * f2 : d[0] * f1 - d[1] * f0;
+                        }
+                    }
+                    const size_t slot = (size_t)par * G.nc2 + (size_t)(G.agg2_first + P2) * 6 + q;
+                    for (int r = 0; r < G.n_ranks; ++r) ll_store(G.peer_w2[r] + 2 * slot, v, e2);
+                }
+            }
+            if (blockIdx.x == gridDim.x - 1) {
+                for (int t = tid; t < G.nc2; t += ST_THREADS) G.w2_plain[t] = ll_load(G.w2_ll + 2 * ((size_t)par * G.nc2 + t), e2, A.err);
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) *(volatile unsigned int*)G.w2_flag = e2;
+            }
+        }
         double wy = 0.0;
+        bool have_w2 = false;
         for (int k = gw; k < G.nc; k += nw) {
-            const double acc = einv_row_dot(k);
+            double acc = einv_row_dot(k);
+            if (G.glob) {
+                if (!have_w2) {  // the gathered w2 is ready once the flag carries this application's epoch
+                    const long long t0 = clock64();
+                    while (*(volatile unsigned int*)G.w2_flag != e2) {
+                        if (clock64() - t0 > 4000000000LL) {
+                            *A.err = 2;
+                            break;
+                        }
+                    }
+                    have_w2 = true;
+                }
+                const double* grow = G.G + (size_t)k * G.nc2;
+                double g = 0.0;
+                for (int j = lane; j < G.nc2; j += 32) g += __ldg(grow + j) * __ldcg(G.w2_plain + j);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+                acc += g;
+            }
             if (lane == 0) {
                 G.y[k] = acc;
                 wy += __ldcg(G.w + k) * acc;
             }
         }
+        if (G.glob) ++co_apps;
         cprof(11);
         return wy;
     };
@@ -2102,6 +2219,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
             P.epochs[0] = repoch;
             P.epochs[1] = hepoch;
         }
+        if (two_level && A.co.glob) *A.co.w2_epoch += co_apps;
     }
 }
 

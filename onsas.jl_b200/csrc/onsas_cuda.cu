@@ -172,11 +172,23 @@ struct onsas_ctx {
         bool built = false;   // aggregates exist for the current mesh
         bool fresh = false;   // Einv matches the K currently assembled
         int n_agg = 0, nc = 0, cd = 0;
+        bool glob = false;    // the global level is part of the operator
+        int nc2 = 0, n2_own = 0, agg2_first = 0;
     } co;
     bool coarse_fused = true;  // residual update in aggregate order, fused with w = Z^T r (same-box sweep: profiles/r18)
     bool coarse_rbm = true;  // 3D: rigid-body rotations of every aggregate join the coarse space (6 coarse dofs per aggregate)
     DevBuf<int32_t> co_agg, co_agg_ptr, co_agg_nodes;
     DevBuf<double> co_E, co_w, co_y, co_rowbuf, co_rho;
+    // global coarse level across ranks (ONSAS_OPT_COARSE_GLOBAL): level-2 aggregates from the partitioner
+    std::vector<int32_t> h_agg2;   // [n_local] global level-2 aggregate of every local node (owned + halo)
+    std::vector<double> h_cen2;    // [n_agg2_total * dim]
+    int n_agg2_per_rank = 0;
+    int coarse_global = 1;         // use it when the context has what it needs (several ranks, 3-D, rotations, peer window)
+    unsigned long long co2_epoch = 0;
+    DevBuf<int32_t> co2_agg, co2_ptr, co2_nodes, co_parent, co_child_ptr;
+    DevBuf<double> co2_rho, co_dvec, co_G, co_w2plain, co_rowbuf2;
+    DevBuf<double*> d_peer_E2;
+    DevBuf<unsigned long long*> d_peer_rowflags, d_peer_w2;
     // onsas_assemble_host: slice ranges launched one after the other while the copies of U (in) and F_int (out) overlap them
     int64_t asm_first = 0, asm_count = -1;  // slice range of the next assembly launches (-1: all slices)
     cudaStream_t asm_stream = nullptr;      // stream of the next assembly launches (null: the context's stream)
@@ -704,7 +716,16 @@ constexpr size_t P2P_HDR_BYTES = 4096;
 static_assert(P2P_SLOTS_BYTES + 16 <= P2P_HDR_BYTES, "window header too small");
 inline unsigned long long* win_slots(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w); }
 inline unsigned long long* win_epochs(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_SLOTS_BYTES); }
-inline unsigned long long* win_zh(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_HDR_BYTES); }
+// global coarse level (same offsets on every rank): [E2: NC2^2 doubles][w2 LL: 2 x NC2 pairs][row flags: 16 words][w2 epoch, flag]
+constexpr size_t P2P_E2_BYTES = (size_t)COARSE_NC_MAX * COARSE_NC_MAX * 8;
+constexpr size_t P2P_W2_BYTES = (size_t)2 * COARSE_NC_MAX * 16;
+constexpr size_t P2P_COARSE_BYTES = P2P_E2_BYTES + P2P_W2_BYTES + 256;
+inline double* win_E2(unsigned char* w) { return reinterpret_cast<double*>(w + P2P_HDR_BYTES); }
+inline unsigned long long* win_w2(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_HDR_BYTES + P2P_E2_BYTES); }
+inline unsigned long long* win_rowflags(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_HDR_BYTES + P2P_E2_BYTES + P2P_W2_BYTES); }
+inline unsigned long long* win_w2epoch(unsigned char* w) { return win_rowflags(w) + 16; }
+inline unsigned int* win_w2flag(unsigned char* w) { return reinterpret_cast<unsigned int*>(win_rowflags(w) + 17); }
+inline unsigned long long* win_zh(unsigned char* w) { return reinterpret_cast<unsigned long long*>(w + P2P_HDR_BYTES + P2P_COARSE_BYTES); }
 
 // ---------------------------------------------------------------- CG drivers
 CgArgs make_cg_args(onsas_ctx* c, int precond, double reltol, double abstol, int64_t maxiter, bool use_rhs, int update_U) {
@@ -842,7 +863,7 @@ void launch_stream(onsas_ctx* c, CgArgs A) {
     void* args[] = {&A, &S, &P};
     // Jacobi-PCG (the north-star solver) runs the single-reduction recurrence; precond = 0 keeps the classic one, which
     // restates IterativeSolvers' cg! step by step, and the two-level preconditioner needs its own phase structure
-    const bool sr = (A.precond == 1 && (c->cg_single_reduction & 1)) || (A.precond == 2 && (c->cg_single_reduction & 2));
+    const bool sr = (A.precond == 1 && (c->cg_single_reduction & 1)) || (A.precond == 2 && (c->cg_single_reduction & 2) && !c->co.glob);
     CUDA_CHECK(cudaLaunchCooperativeKernel(sr ? c->st_plan.kern_sr : c->st_plan.kern, dim3(c->st_plan.grid), dim3(c->st_plan.threads), args, c->st_plan.smem, c->stream));
 }
 
@@ -883,7 +904,35 @@ void build_coarse(onsas_ctx* c) {
     const int cd = (c->dim == 3 && c->coarse_rbm) ? 6 : c->dim;
     int n_agg = (int)std::max<int64_t>(1, std::min<int64_t>(n / CO_TARGET_NODES, CO_NC_MAX / cd));
     std::vector<int32_t> ids((size_t)n), agg((size_t)n, 0);
-    if (!c->h_agg_ptr.empty() && c->h_agg_ptr.back() == n && (int)(c->h_agg_ptr.size() - 1) * cd <= CO_NC_MAX) {
+    const bool glob = c->coarse_global && c->n_ranks > 1 && c->p2p_ready && cd == 6 && c->n_agg2_per_rank > 0 &&
+                      (int64_t)c->h_agg2.size() == c->n_nodes && c->cg_mode == 0;
+    c->co.glob = glob;
+    std::vector<int32_t> child_ptr, parent_of;
+    if (glob) {
+        // the rank's aggregates are cut INSIDE its level-2 aggregates (Z2 = Z T: the global level folds into the rank's operator)
+        const int n2 = c->n_agg2_per_rank, first2 = c->rank * n2;
+        const int per = std::max(1, n_agg / n2);
+        std::vector<std::vector<int32_t>> lists((size_t)n2);
+        for (int64_t i = 0; i < n; ++i) {
+            const int P2 = c->h_agg2[(size_t)i] - first2;
+            require(P2 >= 0 && P2 < n2, ONSAS_ERR_INVALID_ARG, "level-2 aggregate of an owned node belongs to another rank");
+            lists[(size_t)P2].push_back((int32_t)i);
+        }
+        child_ptr.assign(1, 0);
+        int next = 0;
+        for (int P2 = 0; P2 < n2; ++P2) {
+            std::vector<int32_t>& L = lists[(size_t)P2];
+            const int k = (int)std::max<size_t>(1, std::min<size_t>((size_t)per, L.size()));
+            if (!L.empty()) rcb_aggregate(c->h_xyz.data(), c->dim, L, 0, L.size(), k, next, agg);
+            for (int j = 0; j < k; ++j) parent_of.push_back(P2);
+            next += k;
+            child_ptr.push_back(next);
+        }
+        n_agg = next;
+        c->co.n2_own = n2;
+        c->co.agg2_first = first2;
+        c->co.nc2 = (int)(c->h_cen2.size() / 3) * 6;
+    } else if (!c->h_agg_ptr.empty() && c->h_agg_ptr.back() == n && (int)(c->h_agg_ptr.size() - 1) * cd <= CO_NC_MAX) {
         // aggregate-major numbering (ONSAS_OPT_REORDER = 2): the partitioner already cut the aggregates, they are node ranges
         n_agg = (int)c->h_agg_ptr.size() - 1;
         for (int a = 0; a < n_agg; ++a)
@@ -911,6 +960,38 @@ void build_coarse(onsas_ctx* c) {
     }
     const int nc = n_agg * cd;
     cudaStream_t s = c->stream;
+    if (glob) {
+        // tables of the global level: level-2 aggregate and position relative to ITS centroid for every local node (halo
+        // nodes too: the rows of E2 couple to the neighbours' aggregates), the node lists of the own level-2 aggregates,
+        // parent and centroid offset of every own aggregate
+        const int n2 = c->co.n2_own, first2 = c->co.agg2_first;
+        std::vector<double> rho2((size_t)c->n_nodes * 3), dvec((size_t)n_agg * 3), cen1((size_t)n_agg * 3, 0.0);
+        for (int64_t i = 0; i < c->n_nodes; ++i)
+            for (int d = 0; d < 3; ++d) rho2[(size_t)i * 3 + d] = c->h_xyz[(size_t)i * 3 + d] - c->h_cen2[(size_t)c->h_agg2[(size_t)i] * 3 + d];
+        for (int a = 0; a < n_agg; ++a) {
+            for (int32_t q = ptr[a]; q < ptr[a + 1]; ++q)
+                for (int d = 0; d < 3; ++d) cen1[(size_t)a * 3 + d] += c->h_xyz[(size_t)nodes[q] * 3 + d];
+            for (int d = 0; d < 3; ++d) {
+                cen1[(size_t)a * 3 + d] /= std::max<int32_t>(1, ptr[a + 1] - ptr[a]);
+                dvec[(size_t)a * 3 + d] = cen1[(size_t)a * 3 + d] - c->h_cen2[(size_t)(first2 + parent_of[(size_t)a]) * 3 + d];
+            }
+        }
+        std::vector<int32_t> ptr2((size_t)n2 + 1, 0), nodes2((size_t)n);
+        for (int64_t i = 0; i < n; ++i) ptr2[(size_t)(c->h_agg2[(size_t)i] - first2) + 1]++;
+        for (int a = 0; a < n2; ++a) ptr2[(size_t)a + 1] += ptr2[(size_t)a];
+        std::vector<int32_t> fill2(ptr2.begin(), ptr2.end() - 1);
+        for (int64_t i = 0; i < n; ++i) nodes2[(size_t)fill2[(size_t)(c->h_agg2[(size_t)i] - first2)]++] = (int32_t)i;
+        c->co2_agg.upload(c->h_agg2, s);
+        c->co2_rho.upload(rho2, s);
+        c->co2_ptr.upload(ptr2, s);
+        c->co2_nodes.upload(nodes2, s);
+        c->co_parent.upload(parent_of, s);
+        c->co_child_ptr.upload(child_ptr, s);
+        c->co_dvec.upload(dvec, s);
+        c->co_G.alloc((size_t)nc * c->co.nc2);
+        c->co_w2plain.alloc((size_t)c->co.nc2);
+        c->co_rowbuf2.alloc((size_t)2 * GJ_B * c->co.nc2);
+    }
     c->co_agg.upload(agg, s);
     c->co_agg_ptr.upload(ptr, s);
     c->co_agg_nodes.upload(nodes, s);
@@ -939,6 +1020,23 @@ void fill_coarse_args(onsas_ctx* c, CgArgs& A) {
     A.co.Einv = c->co_E.p;
     A.co.w = c->co_w.p;
     A.co.y = c->co_y.p;
+    A.co.n_cols = (int)c->n_owned;
+    A.co.agg_row0 = 0;
+    A.co.glob = c->co.glob ? 1 : 0;
+    A.co.n_ranks = c->n_ranks;
+    if (c->co.glob) {
+        A.co.nc2 = c->co.nc2;
+        A.co.n2_own = c->co.n2_own;
+        A.co.agg2_first = c->co.agg2_first;
+        A.co.G = c->co_G.p;
+        A.co.child_ptr = c->co_child_ptr.p;
+        A.co.dvec = c->co_dvec.p;
+        A.co.w2_ll = win_w2(c->window.p);
+        A.co.peer_w2 = c->d_peer_w2.p;
+        A.co.w2_plain = c->co_w2plain.p;
+        A.co.w2_flag = win_w2flag(c->window.p);
+        A.co.w2_epoch = win_w2epoch(c->window.p);
+    }
 }
 
 // E = Z^T (M K M) Z for the K currently in memory, then its explicit inverse (both deterministic)
@@ -974,6 +1072,50 @@ void refresh_coarse(onsas_ctx* c, CgArgs& A) {
         double* rb = c->co_rowbuf.p;
         void* args[] = {&M, &ncv, &rowsv, &rb};
         CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gj_invert, dim3(grid), dim3(GJ_THREADS), args, smem, c->stream));
+    }
+    if constexpr (BS == 3) {
+        if (c->co.glob) {
+            // ---- global level: this rank's rows of E2 = Z2^T (M K M) Z2 (halo columns included), pushed into every rank's copy
+            //      of E2 over the peer window; once everybody's rows have landed each rank inverts E2 and folds it into
+            //      G = T (E2^-1)[own rows, :].  Refreshes of different ranks cannot overlap: a globally synchronised solve
+            //      separates them.
+            const int nc2 = c->co.nc2, n2 = c->co.n2_own, first2 = c->co.agg2_first;
+            require((nc2 + GJ_B - 1) / GJ_B <= c->n_sm && nc2 <= COARSE_NC_MAX, ONSAS_ERR_UNSUPPORTED, "global coarse space too large");
+            CgArgs A2 = A;
+            A2.co.n_agg = n2;
+            A2.co.nc = nc2;
+            A2.co.cd = 6;
+            A2.co.rho = c->co2_rho.p;
+            A2.co.agg = c->co2_agg.p;
+            A2.co.agg_ptr = c->co2_ptr.p;
+            A2.co.agg_nodes = c->co2_nodes.p;
+            A2.co.n_cols = (int)c->n_nodes;
+            A2.co.agg_row0 = first2;
+            double* E2 = win_E2(c->window.p);
+            double* rows = E2 + (size_t)first2 * 6 * nc2;
+            const size_t smem2 = (size_t)6 * nc2 * sizeof(double);
+            ensure_dyn_smem(c->device, (const void*)k_coarse_assemble<BS>, smem2);
+            k_coarse_assemble<BS><<<n2, CO_THREADS, smem2, c->stream>>>(A2, rows);
+            CUDA_CHECK(cudaGetLastError());
+            const size_t nrow = (size_t)n2 * 6 * nc2;
+            k_push_rows<<<64, 256, 0, c->stream>>>(rows, nrow, c->d_peer_E2.p, c->n_ranks, c->rank, (size_t)first2 * 6 * nc2);
+            ++c->co2_epoch;
+            k_set_flags<<<1, 32, 0, c->stream>>>(c->d_peer_rowflags.p, c->n_ranks, c->rank, c->co2_epoch);
+            k_wait_flags<<<1, 32, 0, c->stream>>>(win_rowflags(c->window.p), c->n_ranks, c->rank, c->co2_epoch, c->err_flag.p);
+            CUDA_CHECK(cudaGetLastError());
+            {
+                const int grid = (nc2 + GJ_B - 1) / GJ_B;
+                const size_t smem = ((size_t)GJ_B * nc2 + 2 * GJ_B * GJ_B) * sizeof(double);
+                ensure_dyn_smem(c->device, (const void*)k_gj_invert_blocked, smem);
+                double* M = E2;
+                int ncv = nc2;
+                double* rb = c->co_rowbuf2.p;
+                void* args[] = {&M, &ncv, &rb};
+                CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gj_invert_blocked, dim3(grid), dim3(GJ_THREADS), args, smem, c->stream));
+            }
+            k_build_G<<<nc, 256, 0, c->stream>>>(E2, nc2, nc, c->co_parent.p, first2, c->co_dvec.p, c->co_G.p);
+            CUDA_CHECK(cudaGetLastError());
+        }
     }
     c->co.fresh = true;
 }
@@ -1072,6 +1214,18 @@ void p2p_wire(onsas_ctx* c, const std::vector<unsigned char*>& win, const int64_
     c->d_push_ptr.upload(pptr, s);
     c->d_push_dst.upload(pdst, s);
     c->d_peer_slots.upload(slots, s);
+    {
+        std::vector<double*> pe(c->n_ranks);
+        std::vector<unsigned long long*> pf(c->n_ranks), pw(c->n_ranks);
+        for (int r = 0; r < c->n_ranks; ++r) {
+            pe[r] = win_E2(win[r]);
+            pf[r] = win_rowflags(win[r]);
+            pw[r] = win_w2(win[r]);
+        }
+        c->d_peer_E2.upload(pe, s);
+        c->d_peer_rowflags.upload(pf, s);
+        c->d_peer_w2.upload(pw, s);
+    }
     CUDA_CHECK(cudaStreamSynchronize(s));
     // mark the interface dofs (mask bit 1): only they look the push map up inside the solver
     c->h_iface.assign((size_t)nd, 0);
@@ -1228,6 +1382,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_HOST_MID_WEIGHT: require(value >= 1 && value <= 64, ONSAS_ERR_INVALID_ARG, "weight must be 1..64"); c->host_mid_weight = (int)value; c->hp.built = false; break;
             case ONSAS_OPT_CG_PROFILE: c->cg_profile = value != 0; c->cg_grid = 0; break;
             case ONSAS_OPT_CG_BLOCKS_PER_SM: require(value >= 0 && value <= 32, ONSAS_ERR_INVALID_ARG, "blocks per SM out of range"); c->cg_bps = (int)value; c->cg_grid = 0; break;
+            case ONSAS_OPT_COARSE_GLOBAL: c->coarse_global = value != 0; c->co.built = false; c->co.fresh = false; break;
             case ONSAS_OPT_HOST_GRAPH: c->host_graph = value != 0; c->hp.graph_failed = false; break;
             case ONSAS_OPT_TRUSS_MINBLOCKS: require(value >= 2 && value <= 4, ONSAS_ERR_INVALID_ARG, "truss min blocks must be 2..4"); c->truss_minb = (int)value; break;
             case ONSAS_OPT_CG_SINGLE_REDUCTION: require(value >= 0 && value <= 3, ONSAS_ERR_INVALID_ARG, "single-reduction mask must be 0..3"); c->cg_single_reduction = (int)value; break;
@@ -1253,6 +1408,9 @@ int32_t onsas_set_nodes(onsas_ctx* c, int64_t n_nodes, int64_t n_owned, int32_t 
         c->n_owned = n_owned;
         c->h_xyz.assign(xyz, xyz + n_nodes * dim);
         c->h_agg_ptr.clear();
+        c->h_agg2.clear();
+        c->h_cen2.clear();
+        c->n_agg2_per_rank = 0;
         c->remote_halo_off.clear();
         c->have_nodes = true;
         c->finalized = false;
@@ -1411,7 +1569,7 @@ int32_t onsas_finalize_mesh(onsas_ctx* c) {
         c->p_pad.zero(s);
         if (c->n_ranks > 1 || c->force_mg) {
             // P2P window: fixed-size header (scalar slots, epochs) then the LL receive buffer of the halo dofs
-            c->window.alloc(P2P_HDR_BYTES + std::max<size_t>(nl - no, 1) * 16);
+            c->window.alloc(P2P_HDR_BYTES + P2P_COARSE_BYTES + std::max<size_t>(nl - no, 1) * 16);
             c->window.zero(s);
             c->p2p_ready = false;
         }

@@ -130,6 +130,32 @@ std::string build_partition(int dim, int64_t n_nodes, const double* xyz, int64_t
     P.inv.resize((size_t)n_nodes);
 #pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < n_nodes; ++k) P.inv[P.order[k]] = (int32_t)k;
+    if (n_ranks > 1 && reorder != 2) {
+        // level-2 aggregates: bisect a COPY of every part's node list (the numbering stays as it is)
+        const int cd = dim == 3 ? 6 : dim;
+        int64_t smallest = n_nodes;
+        for (int p = 0; p < n_ranks; ++p) smallest = std::min(smallest, P.ranges[p + 1] - P.ranges[p]);
+        const int n2 = (int)std::max<int64_t>(1, std::min<int64_t>((COARSE_NC_MAX / cd) / n_ranks, smallest / 64));
+        P.n_agg2_per_rank = n2;
+        P.agg2.assign((size_t)n_nodes, 0);
+        P.cen2.assign((size_t)n2 * n_ranks * dim, 0.0);
+        for (int p = 0; p < n_ranks; ++p) {
+            const int64_t lo = P.ranges[p], hi = P.ranges[p + 1];
+            std::vector<int32_t> ids(P.order.begin() + lo, P.order.begin() + hi);  // original ids of the part's nodes
+            std::vector<int64_t> sz;
+            rcb(xyz, dim, ids, 0, ids.size(), n2, sz);
+            size_t o = 0;
+            for (int a = 0; a < n2; ++a) {
+                const int g = p * n2 + a;
+                for (int64_t k = 0; k < sz[(size_t)a]; ++k, ++o) {
+                    const int32_t orig = ids[o];
+                    P.agg2[(size_t)P.inv[orig]] = g;
+                    for (int d = 0; d < dim; ++d) P.cen2[(size_t)g * dim + d] += xyz[(size_t)orig * dim + d];
+                }
+                for (int d = 0; d < dim; ++d) P.cen2[(size_t)g * dim + d] /= (double)std::max<int64_t>(1, sz[(size_t)a]);
+            }
+        }
+    }
     P.xyz.resize((size_t)n_nodes * dim);
 #pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < n_nodes; ++k)
@@ -288,6 +314,13 @@ void build_local_part(const Partition& P, int rank, LocalPart& L) {
             if (P.free_mask[(size_t)halo[h] * dim + d]) L.free_dofs.push_back((L.n_owned + (int64_t)h) * dim + d);
     L.n_free_global = P.n_free;
     if ((size_t)rank < P.agg_ptr.size()) L.agg_ptr = P.agg_ptr[(size_t)rank];
+    if (!P.agg2.empty()) {
+        L.n_agg2_per_rank = P.n_agg2_per_rank;
+        L.cen2 = P.cen2;
+        L.agg2.resize((size_t)L.n_local);
+        for (int64_t k = lo; k < hi; ++k) L.agg2[(size_t)(k - lo)] = P.agg2[(size_t)k];
+        for (size_t h = 0; h < halo.size(); ++h) L.agg2[(size_t)L.n_owned + h] = P.agg2[(size_t)halo[h]];
+    }
 }
 
 }  // namespace onsas

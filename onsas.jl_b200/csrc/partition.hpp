@@ -43,6 +43,12 @@ struct Partition {
     bool tet_has_mat = false, truss_has_mat = false;
     std::vector<double> area;
     std::vector<std::vector<int32_t>> agg_ptr;  // reorder = 2: per rank, the node ranges (relative to the rank's first node) of its aggregates
+    // global coarse level of the two-level preconditioner (n_ranks > 1): every rank's nodes are cut into n_agg2_per_rank
+    // "level-2" aggregates (recursive coordinate bisection, numbering untouched); their union over the ranks is ONE coarse
+    // space of at most COARSE_NC_MAX dofs that couples the ranks
+    std::vector<int32_t> agg2;     // [n_nodes] (new ids) global level-2 aggregate of every node; empty when n_ranks == 1
+    std::vector<double> cen2;      // [n_agg2 * dim] centroids
+    int n_agg2_per_rank = 0;
     std::vector<uint8_t> free_mask;  // [n_nodes*dim] (new numbering) 1 = free dof
     int64_t n_free = 0;
     int owner_of(int64_t new_id) const;
@@ -63,6 +69,9 @@ struct LocalPart {
     std::vector<int32_t> send_nodes;           // local (owned) node ids grouped by neighbour, ascending global id
     std::vector<int64_t> remote_halo_off;      // [n_nbr] where this rank's values start inside neighbour k's halo (in nodes)
     std::vector<int32_t> agg_ptr;              // reorder = 2: [n_agg+1] owned-node ranges of the preconditioner's aggregates, else empty
+    std::vector<int32_t> agg2;                 // [n_local] global level-2 aggregate of every local node (owned + halo), or empty
+    std::vector<double> cen2;                  // [n_agg2_total * dim] centroids of all level-2 aggregates
+    int n_agg2_per_rank = 0;                   // this rank owns level-2 aggregates rank * n_agg2_per_rank .. + n_agg2_per_rank
 };
 
 // Returns an empty string on success.  conn arrays are element-major, 0-based original node ids; mat ids may be null.

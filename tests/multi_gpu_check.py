@@ -130,7 +130,27 @@ def main():
             dr_rel = info.norm_r / info.norm_Fext
             it += 1
         iters_n.append(it)
+    # the two-level preconditioner with the GLOBAL coarse level (level-2 aggregates across ranks) and without it: both solve
+    # the same system to the oracle's answer; the global level must not need more iterations
+    rng2 = np.random.default_rng(9)
+    b2 = rng2.standard_normal(mesh2.n_nodes * 3)
+    ctx.set_U((0.02 * rng2.standard_normal((mesh2.n_nodes, 3)))[l2g].ravel())
+    ctx.assemble()
+    its_g = {}
+    xg = {}
+    for glob in (1, 0, 1):
+        ctx.set_option(ob._lib.OPT_COARSE_GLOBAL, glob)
+        xs, its_, _ = ctx.pcg(b2.reshape(-1, 3)[l2g].ravel(), ob.PRECOND_TWO_LEVEL, 1e-12)
+        its_g[glob] = its_
+        xg[glob] = xs
+    xj, its_j, _ = ctx.pcg(b2.reshape(-1, 3)[l2g].ravel(), ob.PRECOND_JACOBI, 1e-12)
     n_own = P.sizes(rank)["n_owned"]
+    sc = max(np.abs(xj).max(), 1e-300)
+    e_glob = max(np.abs(xg[1][:3 * n_own] - xj[:3 * n_own]).max(), np.abs(xg[0][:3 * n_own] - xj[:3 * n_own]).max()) / sc
+    glob_ok = e_glob < 1e-8 and its_g[1] <= its_g[0]
+    if rank == 0:
+        print(f"multi-gpu check world={world}: two-level with the global coarse level {its_g[1]} iterations, without {its_g[0]}, jacobi {its_j}; x vs jacobi solve {e_glob:.2e}", flush=True)
+    ctx.set_U(np.zeros(len(l2g) * 3))
     Un = torch.zeros((mesh2.n_nodes, 3), dtype=torch.float64, device="cuda")
     Un[torch.as_tensor(l2g[:n_own].astype(np.int64), device="cuda")] = torch.as_tensor(ctx.get_U().reshape(-1, 3)[:n_own], device="cuda")
     dist.all_reduce(Un)
@@ -138,18 +158,19 @@ def main():
     native_ok = np.array_equal(Un[order].ravel(), Ug) and iters_n == iters
     if rank == 0 and os.environ.get("ONSAS_MULTI_DUMP"):
         np.save(os.environ["ONSAS_MULTI_DUMP"], Un)      # caller numbering: compared with the one-process multi-device context
-    errs = torch.tensor([e_f, e_k, e_y, e_x, e_u, e_x2, 0.0 if halo_ok else 1.0, 0.0 if native_ok else 1.0], dtype=torch.float64, device="cuda")
+    errs = torch.tensor([e_f, e_k, e_y, e_x, e_u, e_x2, 0.0 if halo_ok else 1.0, 0.0 if native_ok else 1.0, 0.0 if glob_ok else 1.0], dtype=torch.float64, device="cuda")
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     ok = True
     if rank == 0:
-        e_f, e_k, e_y, e_x, e_u, e_x2, bad_halo, bad_native = errs.tolist()
-        halo_ok, native_ok = bad_halo == 0.0, bad_native == 0.0
+        e_f, e_k, e_y, e_x, e_u, e_x2, bad_halo, bad_native, bad_glob = errs.tolist()
+        halo_ok, native_ok, glob_ok = bad_halo == 0.0, bad_native == 0.0, bad_glob == 0.0
         print(f"multi-gpu check world={world}: two-level pcg x {e_x2:.2e} (its {its2} vs jacobi {its[0]})", flush=True)
         print(f"multi-gpu check world={world}: F_int {e_f:.2e}  K {e_k:.2e}  spmv {e_y:.2e}  pcg x {e_x:.2e} (its {its} vs {ito})  "
               f"newton U {e_u:.2e} iters {iters} vs {refn.iterations}", flush=True)
         print(f"multi-gpu check world={world}: halo part of U bitwise current after the solves: {halo_ok}; native partitioner bitwise equal: {native_ok}", flush=True)
         ok = e_f < 1e-12 and e_k < 1e-12 and e_y < 1e-12 and e_x < 1e-8 and e_u < 1e-8 and iters == refn.iterations and e_x2 < 1e-8
-        ok = ok and halo_ok and native_ok
+        ok = ok and halo_ok and native_ok and glob_ok
+        print(f"multi-gpu check world={world}: global coarse level ok: {glob_ok}", flush=True)
         print("MULTI_GPU_CHECK_OK" if ok else "MULTI_GPU_CHECK_FAILED", flush=True)
     dist.barrier()          # never leave the other ranks waiting on a failed assertion
     dist.destroy_process_group()
