@@ -130,6 +130,12 @@ def main():
             dr_rel = info.norm_r / info.norm_Fext
             it += 1
         iters_n.append(it)
+    n_own = P.sizes(rank)["n_owned"]
+    Un = torch.zeros((mesh2.n_nodes, 3), dtype=torch.float64, device="cuda")
+    Un[torch.as_tensor(l2g[:n_own].astype(np.int64), device="cuda")] = torch.as_tensor(ctx.get_U().reshape(-1, 3)[:n_own], device="cuda")
+    dist.all_reduce(Un)
+    Un = Un.cpu().numpy()
+    native_ok = np.array_equal(Un[order].ravel(), Ug) and iters_n == iters
     # the two-level preconditioner with the GLOBAL coarse level (level-2 aggregates across ranks) and without it: both solve
     # the same system to the oracle's answer; the global level must not need more iterations
     rng2 = np.random.default_rng(9)
@@ -150,12 +156,6 @@ def main():
     glob_ok = e_glob < 1e-8 and its_g[1] <= its_g[0]
     if rank == 0:
         print(f"multi-gpu check world={world}: two-level with the global coarse level {its_g[1]} iterations, without {its_g[0]}, jacobi {its_j}; x vs jacobi solve {e_glob:.2e}", flush=True)
-    ctx.set_U(np.zeros(len(l2g) * 3))
-    Un = torch.zeros((mesh2.n_nodes, 3), dtype=torch.float64, device="cuda")
-    Un[torch.as_tensor(l2g[:n_own].astype(np.int64), device="cuda")] = torch.as_tensor(ctx.get_U().reshape(-1, 3)[:n_own], device="cuda")
-    dist.all_reduce(Un)
-    Un = Un.cpu().numpy()
-    native_ok = np.array_equal(Un[order].ravel(), Ug) and iters_n == iters
     if rank == 0 and os.environ.get("ONSAS_MULTI_DUMP"):
         np.save(os.environ["ONSAS_MULTI_DUMP"], Un)      # caller numbering: compared with the one-process multi-device context
     errs = torch.tensor([e_f, e_k, e_y, e_x, e_u, e_x2, 0.0 if halo_ok else 1.0, 0.0 if native_ok else 1.0, 0.0 if glob_ok else 1.0], dtype=torch.float64, device="cuda")
