@@ -95,10 +95,11 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_HOST_GRAPH 16      /* onsas_assemble_host: 1 = when the same pinned buffers are passed twice in a row, the pipeline of copies and kernels is
                                         captured once into a CUDA graph and every later call is one graph launch; 0 (default) = always enqueue it
                                         (measured on B200: the replayed 80-node, 4-stream graph takes 0.409 ms per pass, the eager enqueue 0.383) */
-#define ONSAS_OPT_COARSE_GLOBAL 17   /* two-level preconditioner on several GPUs (3-D, native partition, peer-memory solver): 1 (default) = a global coarse
-                                        level couples the ranks (level-2 aggregates = unions of each rank's aggregates, E2 assembled by all ranks over the
-                                        peer window, folded into each rank's dense operator: one more L2-resident dense apply and one all-gather of <= 1536
-                                        doubles per iteration), 0 = every rank's coarse space stands alone (block-diagonal E) */
+#define ONSAS_OPT_COARSE_GLOBAL 17   /* two-level preconditioner on several GPUs (3-D, native partition, peer-memory solver): 1 = a global coarse level
+                                        couples the ranks (level-2 aggregates = unions of each rank's aggregates, E2 assembled by all ranks over the peer
+                                        window, folded into each rank's dense operator: one more L2-resident dense apply and one all-gather of <= 1536
+                                        doubles per iteration); 0 (default) = every rank's coarse space stands alone (block-diagonal E).  Measured
+                                        (profiles/r61, r62): correct, but the extra latency per iteration outweighs the iterations it saves */
 #define ONSAS_OPT_COARSE_FUSED 11    /* two-level preconditioner: 1 = residual update in aggregate order, fused with w = Z^T r (default), 0 = separate pass */
 
 /* ---------------------------------------------------------------- life cycle */

@@ -183,7 +183,7 @@ struct onsas_ctx {
     std::vector<int32_t> h_agg2;   // [n_local] global level-2 aggregate of every local node (owned + halo)
     std::vector<double> h_cen2;    // [n_agg2_total * dim]
     int n_agg2_per_rank = 0;
-    int coarse_global = 1;         // use it when the context has what it needs (several ranks, 3-D, rotations, peer window)
+    int coarse_global = 0;         // ONSAS_OPT_COARSE_GLOBAL (off by default: measured, per iteration it costs more than its iterations save)
     unsigned long long co2_epoch = 0;
     DevBuf<int32_t> co2_agg, co2_ptr, co2_nodes, co_parent, co_child_ptr;
     DevBuf<double> co2_rho, co_dvec, co_G, co_w2plain, co_rowbuf2;
