@@ -169,3 +169,15 @@ def test_truss_lattice_on_two_devices_and_reordered(ob):
             np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-6 * E * 1e-3)
     for c in ctxs:
         c.close()
+    # a 1-D chain (block size 1) on two devices: examples/clamped_truss, Green strain
+    mt, fext, p = cases.clamped_truss(100)
+    kw1 = dict(trusses=mt.trusses, truss_area=mt.truss_area, truss_strain=ob.STRAIN_GREEN, mat_kind=mt.mat_kind, mat_params=mt.mat_params,
+               free_dofs=mt.free_dofs)
+    a, b = ob.context_from_flat(mt.xyz, device=0, **kw1), ob.context_from_flat(mt.xyz, device=[0, 1], **kw1)
+    for c in (a, b):
+        c.set_Fext(fext(0.3))
+        for _ in range(6):
+            info = c.newton_step(ob.PRECOND_JACOBI, 1e-13, cg_maxiter=5000)
+    assert cases.rel_err(b.get_U(), a.get_U()) < 1e-9 and info.norm_r < 1e-8 * info.norm_Fext
+    a.close()
+    b.close()
