@@ -100,6 +100,10 @@ typedef struct onsas_ctx onsas_ctx;
                                         window, folded into each rank's dense operator: one more L2-resident dense apply and one all-gather of <= 1536
                                         doubles per iteration); 0 (default) = every rank's coarse space stands alone (block-diagonal E).  Measured
                                         (profiles/r61, r62): correct, but the extra latency per iteration outweighs the iterations it saves */
+#define ONSAS_OPT_CG_L2_PREFETCH 18  /* streamed persistent solver: slices per consumer warp the producer warp pulls into L2 (cp.async.bulk.prefetch.L2)
+                                        behind the shared-memory ring as soon as an SpMV phase has issued its last copy -- HBM idles during the vector
+                                        phases and grid barriers of an iteration, so the first part of the next SpMV phase is served from L2.
+                                        0 = off; default: see DESIGN.md section 3.3 */
 #define ONSAS_OPT_COARSE_FUSED 11    /* two-level preconditioner: 1 = residual update in aggregate order, fused with w = Z^T r (default), 0 = separate pass */
 
 /* ---------------------------------------------------------------- life cycle */

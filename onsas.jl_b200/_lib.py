@@ -22,7 +22,7 @@ FAMILY_TET, FAMILY_TRUSS = 0, 1
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_TWO_LEVEL = 0, 1, 2
 OPT_CG_MODE, OPT_ASM_MINBLOCKS, OPT_CG_CHECK_EVERY, OPT_CG_BLOCKS_PER_SM, OPT_CG_PROFILE, OPT_FORCE_MG = 1, 2, 3, 4, 5, 6
 OPT_HOST_CHUNKS, OPT_GJ_BLOCKED, OPT_HOST_MID_WEIGHT, OPT_COARSE_RBM, OPT_COARSE_FUSED, OPT_HOST_STREAMS = 7, 8, 9, 10, 11, 12
-OPT_REORDER, OPT_CG_SINGLE_REDUCTION, OPT_TRUSS_MINBLOCKS, OPT_HOST_GRAPH, OPT_COARSE_GLOBAL = 13, 14, 15, 16, 17
+OPT_REORDER, OPT_CG_SINGLE_REDUCTION, OPT_TRUSS_MINBLOCKS, OPT_HOST_GRAPH, OPT_COARSE_GLOBAL, OPT_CG_L2_PREFETCH = 13, 14, 15, 16, 17, 18
 
 
 class StepInfo(C.Structure):

@@ -1269,6 +1269,7 @@ struct StreamArgs {
     int depth;        // ring slots per consumer warp (2..4)
     int slot_blocks;  // capacity of a slot in blocks (widest slice)
     long long n_slices;
+    int l2_prefetch;  // slices per consumer warp the producer pulls into L2 behind the ring while HBM idles (vector phases, barriers)
 };
 
 constexpr int ST_MAX_CW = 12;
@@ -1313,6 +1314,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
+}
+// HBM idles while the vector phases and the grid barriers of an iteration run out of L2: the producer uses that window to
+// pull the slices that FOLLOW the ring's content into L2, so the first part of the next SpMV phase streams at L2 speed
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(policy) : "memory");
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
@@ -1537,7 +1543,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
     // returns the thread's share of w.y; the p update forms z_i = d_i r_i + (Z y)_i on the fly.
     unsigned int co_apps = 0;  // applications of the global coarse level in this launch (its epochs continue across launches)
     // row k of y = E^-1 w by one warp (the dense inverse is L2-resident; 16-byte loads, 12 + 12 of them in flight per lane);
-    // the result is valid in every lane
+    // the result is valid in every lane.  w (and y in the p update) are ordinary loads: the grid barrier in front of them makes
+    // the other CTAs' stores visible, and the 12 KB vector then comes from L1 for all but the first warp of an SM (as L2-only
+    // loads every row's warp fetched its own copy: as many L2 bytes again as the dense inverse itself)
     auto einv_row_dot = [&](int k) -> double {
         const CoarseArgs& G = A.co;
         double acc = 0.0;
@@ -1551,18 +1559,18 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
 #pragma unroll
                 for (int u = 0; u < 12; ++u) {
                     e[u] = __ldg(row + j + 32 * u);
-                    ww[u] = __ldcg(wv + j + 32 * u);
+                    ww[u] = wv[j + 32 * u];
                 }
 #pragma unroll
                 for (int u = 0; u < 12; ++u) acc += e[u].x * ww[u].x + e[u].y * ww[u].y;
             }
             for (; j < n2; j += 32) {
-                const double2 e = __ldg(row + j), ww = __ldcg(wv + j);
+                const double2 e = __ldg(row + j), ww = wv[j];
                 acc += e.x * ww.x + e.y * ww.y;
             }
         } else {
             const double* row = G.Einv + (size_t)k * G.nc;
-            for (int j = lane; j < G.nc; j += 32) acc += __ldg(row + j) * __ldcg(G.w + j);
+            for (int j = lane; j < G.nc; j += 32) acc += __ldg(row + j) * G.w[j];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -1676,6 +1684,25 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                     mbar_wait(&empty[cw][f_next % D], (uint32_t)((f_next / D - 1) & 1), A.err);
                     fill(f_next);
                 }
+            // the ring now holds (or is receiving) the first D slices of the NEXT phase; the PF slices behind them go to L2
+            const int pf = min(S.l2_prefetch, n_my - D);
+            for (int j0 = 0; j0 < pf; j0 += 4) {
+                int64_t b0[4], b1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long sl = first + ((f_next + j0 + (j0 + u < pf ? u : 0)) % n_my) * step;
+                    b0[u] = A.slice_ptr[sl];
+                    b1[u] = A.slice_ptr[sl + 1];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j0 + u < pf && b1[u] > b0[u]) {
+                        const uint32_t nblk = (uint32_t)(b1[u] - b0[u]);
+                        // same L2 class as the stream itself (evict_first)
+                        bulk_prefetch_l2(A.val + b0[u] * BB * C, nblk * (uint32_t)(BB * C * sizeof(double)), pol_stream);
+                        bulk_prefetch_l2(A.col + b0[u] * C, nblk * (uint32_t)(C * sizeof(int32_t)), pol_stream);
+                    }
+            }
         } else if (n_my > 0) {
             const long long tc0 = A.prof != nullptr ? clock64() : 0;
             for (int k = 0; k < n_my; ++k, ++q_done) {
@@ -1745,6 +1772,22 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
             }
         }
     }
+    // classic two-level solver in 3D: the fused update runs one lane per DOF of the chunk's node list (dof t = 32 j + lane of the
+    // chunk <-> node t / 3, component t % 3 = (lane + 2 j) % 3): the list is ascending, so consecutive lanes touch consecutive
+    // doubles inside every run of consecutive nodes -- one lane per node (24-byte stride, three instructions per vector over the
+    // same lines) needed about three times the L1 wavefronts.  Nodes of the lane's dofs in the chunk's first 128 nodes:
+    int fw_dn[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) fw_dn[j] = -1;
+    if constexpr (BS == 3 && !SR) {
+        if (fw_active) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const int q = fw_b0 + (32 * j + lane) / 3;
+                fw_dn[j] = q < fw_b1 ? A.co.agg_nodes[q] : -1;
+            }
+        }
+    }
     if constexpr (SR) {
         // ---- single-reduction CG (precond 0 / 1)
         double* __restrict__ xv = A.x;
@@ -1773,7 +1816,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
             for (int64_t nd = gtid; nd < A.n_rows; nd += gsz) {
                 double ya[CDM], zc[BS];
                 const double* yp = A.co.y + (size_t)A.co.agg[nd] * CD;
-                for (int c = 0; c < CD; ++c) ya[c] = __ldcg(yp + c);
+                for (int c = 0; c < CD; ++c) ya[c] = yp[c];
                 zy_node(ya, nd, zc);
 #pragma unroll
                 for (int c = 0; c < BS; ++c) {
@@ -1998,8 +2041,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                             const double* ya = A.co.y + (size_t)ag[u] * CD;
 #pragma unroll
                             for (int cc = 0; cc < 3; ++cc) {
-                                ty[u][cc] = __ldcg(ya + cc);
-                                om[u][cc] = rbm ? __ldcg(ya + 3 + cc) : 0.0;
+                                ty[u][cc] = ya[cc];
+                                om[u][cc] = rbm ? ya[3 + cc] : 0.0;
                             }
                         }
 #pragma unroll
@@ -2034,12 +2077,12 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                         const int64_t nd = i / BS;
                         const int cc = (int)(i % BS);
                         const double* ya = A.co.y + (size_t)A.co.agg[nd] * CD;
-                        yc[u] = __ldcg(ya + cc);
+                        yc[u] = ya[cc];
                         if constexpr (BS == 3) {
                             if (rbm) {  // (omega x rho)_c = omega_{c+1} rho_{c+2} - omega_{c+2} rho_{c+1}
                                 const int c1 = cc == 2 ? 0 : cc + 1, c2 = cc == 0 ? 2 : cc - 1;
                                 const double* rp = A.co.rho + nd * 3;
-                                yc[u] += __ldcg(ya + 3 + c1) * rp[c2] - __ldcg(ya + 3 + c2) * rp[c1];
+                                yc[u] += ya[3 + c1] * rp[c2] - ya[3 + c2] * rp[c1];
                             }
                         }
                     }
@@ -2087,8 +2130,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                 double acc[CDM];
 #pragma unroll
                 for (int c = 0; c < CDM; ++c) acc[c] = 0.0;
+                // (the nodes' rho travels in the same round trip as the five vectors: fetched inside the accumulation, after the
+                // stores of x and r, it cost a dependent L2 round trip per node)
                 auto update_pair = [&](const int64_t (&nd)[2]) {
-                    double x[2][BS], pp[2][BS], rr[2][BS], ap[2][BS], di[2][BS];
+                    double x[2][BS], pp[2][BS], rr[2][BS], ap[2][BS], di[2][BS], rh[2][BS];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int64_t n0 = nd[u] >= 0 ? nd[u] : 0;
@@ -2100,6 +2145,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                             rr[u][c] = A.r[i];
                             ap[u][c] = A.Ap[i];
                             di[u][c] = A.dinv[i];
+                            rh[u][c] = rbm ? G.rho[i] : 0.0;
                         }
                     }
 #pragma unroll
@@ -2116,10 +2162,81 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_stream(CgArgs A, StreamAr
                             s2[0] += ri * ri;
                             s2[1] += ri * (ri * di[u][c]);
                         }
-                        w_accumulate(acc, nd[u], rn);
+#pragma unroll
+                        for (int c = 0; c < BS; ++c) acc[c] += rn[c];
+                        if constexpr (BS == 3) {
+                            if (rbm) {  // the same expressions as w_accumulate
+                                acc[3] += rh[u][1] * rn[2] - rh[u][2] * rn[1];
+                                acc[4] += rh[u][2] * rn[0] - rh[u][0] * rn[2];
+                                acc[5] += rh[u][0] * rn[1] - rh[u][1] * rn[0];
+                            }
+                        }
                     }
                 };
-                if (fw_active) {
+                // three trips = 96 consecutive dofs of the chunk's list; the lane's component in trip u is (c0 + SL[u]) % 3 with
+                // c0 = lane % 3, so "slot" k of the accumulators stands for component (c0 + k) % 3 until the end of the pass.
+                // r_c enters (rho x r) twice: + rho_{c+2} r_c in component c + 1 and - rho_{c+1} r_c in component c + 2.
+                const int c0 = lane % 3;
+                double accT[3] = {0.0, 0.0, 0.0}, accR[3] = {0.0, 0.0, 0.0};
+                auto update_group = [&](const int (&nd)[3]) {
+                    constexpr int SL[3] = {0, 2, 1};
+                    double x[3], pp[3], rr[3], ap[3], di[3], ra[3], rb[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int cu = c0 + SL[u] >= 3 ? c0 + SL[u] - 3 : c0 + SL[u];
+                        const int c1 = cu == 2 ? 0 : cu + 1, c2 = cu == 0 ? 2 : cu - 1;
+                        const int64_t n0 = nd[u] >= 0 ? nd[u] : 0;
+                        const int64_t i = n0 * 3 + cu;
+                        x[u] = A.x[i];
+                        rr[u] = A.r[i];
+                        ap[u] = A.Ap[i];
+                        di[u] = A.dinv[i];
+                        pp[u] = A.p_pad[n0 * PS + cu];
+                        ra[u] = rbm ? G.rho[n0 * 3 + c2] : 0.0;
+                        rb[u] = rbm ? G.rho[n0 * 3 + c1] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        if (nd[u] < 0) continue;
+                        const int cu = c0 + SL[u] >= 3 ? c0 + SL[u] - 3 : c0 + SL[u];
+                        const int64_t i = (int64_t)nd[u] * 3 + cu;
+                        A.x[i] = x[u] + alpha * pp[u];
+                        const double ri = di[u] != 0.0 ? rr[u] - alpha * ap[u] : 0.0;
+                        A.r[i] = ri;
+                        s2[0] += ri * ri;
+                        s2[1] += ri * (ri * di[u]);
+                        accT[SL[u]] += ri;
+                        accR[(SL[u] + 1) % 3] += ra[u] * ri;
+                        accR[(SL[u] + 2) % 3] -= rb[u] * ri;
+                    }
+                };
+                if (BS == 3 && fw_active) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (fw_dn[3 * g] >= 0) {  // (the first dof of a group is the lowest: nothing follows an empty group)
+                            const int nd[3] = {fw_dn[3 * g], fw_dn[3 * g + 1], fw_dn[3 * g + 2]};
+                            update_group(nd);
+                        }
+                    }
+                    for (int t0 = 384; t0 < 3 * (fw_b1 - fw_b0); t0 += 96) {  // chunks longer than 128 nodes: ids from memory
+                        int nd[3];
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            const int q = fw_b0 + (t0 + 32 * u + lane) / 3;
+                            nd[u] = q < fw_b1 ? G.agg_nodes[q] : -1;
+                        }
+                        update_group(nd);
+                    }
+                    // slots back to components
+                    acc[0] = c0 == 0 ? accT[0] : c0 == 1 ? accT[2] : accT[1];
+                    acc[1] = c0 == 0 ? accT[1] : c0 == 1 ? accT[0] : accT[2];
+                    acc[2] = c0 == 0 ? accT[2] : c0 == 1 ? accT[1] : accT[0];
+                    if constexpr (CDM == 6) {
+                        acc[3] = c0 == 0 ? accR[0] : c0 == 1 ? accR[2] : accR[1];
+                        acc[4] = c0 == 0 ? accR[1] : c0 == 1 ? accR[0] : accR[2];
+                        acc[5] = c0 == 0 ? accR[2] : c0 == 1 ? accR[1] : accR[0];
+                    }
+                } else if (fw_active) {
                     {
                         const int64_t nd[2] = {fw_nid[0], fw_nid[1]};
                         update_pair(nd);

@@ -220,6 +220,7 @@ struct onsas_ctx {
     } st_plan;
     int cg_single_reduction = 1;  // ONSAS_OPT_CG_SINGLE_REDUCTION: bit 0 = Jacobi-PCG (default), bit 1 = two-level PCG run the single-reduction recurrence
     int force_mg = 0;  // diagnostics: run the multi-GPU kernel even with one rank
+    int cg_l2_prefetch = 0;  // ONSAS_OPT_CG_L2_PREFETCH: slices per consumer warp pulled into L2 behind the ring between SpMV phases
     int reorder = 0;   // ONSAS_OPT_REORDER: 1 = the nodes are renumbered along a Z-curve inside onsas_finalize_mesh (invisible to the caller)
     std::vector<std::pair<int32_t, int64_t>> opt_log;  // options in the order they were set (replayed on the device contexts of a group)
 
@@ -859,6 +860,8 @@ void launch_stream(onsas_ctx* c, CgArgs A) {
     S.depth = c->st_plan.depth;
     S.slot_blocks = c->tab.max_width;
     S.n_slices = c->tab.n_slices;
+    S.l2_prefetch = c->cg_l2_prefetch;
+    if (const char* e = getenv("ONSAS_STREAM_L2_PREFETCH")) S.l2_prefetch = std::max(0, std::min(64, atoi(e)));  // experiment knob
     P2PArgs P = make_p2p_args(c);
     void* args[] = {&A, &S, &P};
     // Jacobi-PCG (the north-star solver) runs the single-reduction recurrence; precond = 0 keeps the classic one, which
@@ -1386,6 +1389,7 @@ int32_t onsas_set_option(onsas_ctx* c, int32_t key, int64_t value) {
             case ONSAS_OPT_HOST_GRAPH: c->host_graph = value != 0; c->hp.graph_failed = false; break;
             case ONSAS_OPT_TRUSS_MINBLOCKS: require(value >= 2 && value <= 4, ONSAS_ERR_INVALID_ARG, "truss min blocks must be 2..4"); c->truss_minb = (int)value; break;
             case ONSAS_OPT_CG_SINGLE_REDUCTION: require(value >= 0 && value <= 3, ONSAS_ERR_INVALID_ARG, "single-reduction mask must be 0..3"); c->cg_single_reduction = (int)value; break;
+            case ONSAS_OPT_CG_L2_PREFETCH: require(value >= 0 && value <= 64, ONSAS_ERR_INVALID_ARG, "L2 prefetch distance must be 0..64 slices"); c->cg_l2_prefetch = (int)value; break;
             case ONSAS_OPT_REORDER: require(value >= 0 && value <= 2, ONSAS_ERR_INVALID_ARG, "reorder must be 0, 1 or 2"); require(!c->finalized, ONSAS_ERR_INVALID_ARG, "ONSAS_OPT_REORDER must be set before onsas_finalize_mesh"); c->reorder = (int)value; break;
             default: throw OnsasError(ONSAS_ERR_INVALID_ARG, "unknown option key");
         }
