@@ -943,8 +943,10 @@ __device__ __forceinline__ void z_column(int cdof, const double* rho, unsigned m
         z[p] = ((mask >> p) & 1u) ? v : 0.0;
     }
 }
+// The first form of the coarse assembly (every contribution applied by the same CD*CD threads, one after the other): kept as the
+// cross-check of k_coarse_assemble (ONSAS_COARSE_CHECK) and as ONSAS_COARSE_SERIAL = 1.
 template <int BS>
-__global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double* E) {
+__global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble_serial(CgArgs A, double* E) {
     extern __shared__ double erow[];  // [CD][nc]
     constexpr int BB = BS * BS;
     const CoarseArgs& G = A.co;
@@ -1043,6 +1045,182 @@ __global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double
     // degenerate aggregate (collinear nodes) has a rotation that moves nothing: E + 1e-9 diag(E) stays positive definite.
     if (tid < CD) {
         double& d = erow[(size_t)tid * nc + (a + G.agg_row0) * CD + tid];
+        if (d == 0.0) d = 1.0;
+        else if (rbm) d *= 1.0 + 1e-9;
+    }
+    __syncthreads();
+    for (int k = tid; k < CD * nc; k += CO_THREADS) E[(size_t)(a * CD) * nc + k] = erow[k];
+}
+
+// E[a-rows, :] = sum over the nodes i of aggregate a and the blocks (i, j) of their rows of Z_i^T (M K_ij M) Z_j.
+// One CTA per aggregate; eight of its nodes are fetched at a time, one per warp (the four dependent load levels node id ->
+// slice -> column ids -> aggregate ids overlap across the warps).  Most blocks of an aggregate's rows have their column in the
+// SAME aggregate (all but the surface nodes' outward neighbours), so the serial form above spent its time in one dependent
+// chain of ~10^4 contributions to E[a, a] by 36 threads, the other 220 waiting at the barrier (ncu: 15.8 barrier stalls per
+// issued instruction, 3.06 ms for 256 aggregates).  Here
+//  * E[a, a] is accumulated by ALL warps: each warp sums the own-aggregate blocks of the nodes it staged in registers (one
+//    lane per entry of the upper triangle -- the sum over all (i, j) pairs inside an aggregate is symmetric because K is),
+//    and the eight partial sums meet once, in warp order, at the end;
+//  * the blocks that target OTHER aggregates (compacted into a list at staging time) are dealt by target over
+//    CO_THREADS / (CD*CD) thread groups (target % groups), each applying its targets in (node, block) order as before.
+// Every entry of E still has one fixed summation order.
+template <int BS>
+__global__ void __launch_bounds__(CO_THREADS) k_coarse_assemble(CgArgs A, double* E) {
+    extern __shared__ double erow[];  // [CD][nc]
+    constexpr int BB = BS * BS;
+    constexpr int CDX = BS == 3 ? 6 : BS;  // largest CD
+    const CoarseArgs& G = A.co;
+    const int a = blockIdx.x, tid = threadIdx.x, nc = G.nc, CD = G.cd, warp = tid >> 5, lane = tid & 31;
+    const bool rbm = CD > BS;
+    const int b_own = a + G.agg_row0;
+    __shared__ double sval[CO_NW * CO_WB * BB];
+    __shared__ int s_b[CO_NW][CO_WB];            // aggregate of the block's column (-1: halo column)
+    __shared__ unsigned char s_m[CO_NW][CO_WB];  // mask bits of the column node's dofs
+    __shared__ double s_rj[CO_NW][CO_WB][3];     // rho of the column node
+    __shared__ double s_ri[CO_NW][3];            // rho of the row node
+    __shared__ int s_nb[CO_NW];                  // blocks the warp staged this round
+    __shared__ unsigned s_mi[CO_NW];             // mask bits of the row node's dofs
+    __shared__ unsigned char s_list[CO_NW][CO_WB];  // staged blocks of the warp whose column lies in ANOTHER aggregate
+    __shared__ unsigned char s_grp[CO_NW][CO_WB];   // ... and the thread group that owns that aggregate's columns of E
+    __shared__ int s_cnt[CO_NW];
+    __shared__ double s_own[CO_NW][CDX * (CDX + 1) / 2];
+    for (int k = tid; k < CD * nc; k += CO_THREADS) erow[k] = 0.0;
+    // lane -> entry (pr, pc), pr <= pc, of the upper triangle of E[a, a]
+    const int NU = CD * (CD + 1) / 2;
+    int pr = 0, pc = lane;
+    while (pr < CD && pc >= CD - pr) {
+        pc -= CD - pr;
+        ++pr;
+    }
+    pc += pr;
+    const bool p_act = lane < NU;
+    double own = 0.0;
+    // thread -> (group, entry) for the other aggregates' blocks
+    const int NG = CO_THREADS / (CD * CD);
+    const int grp = tid / (CD * CD), er = (tid % (CD * CD)) / CD, ec = tid % CD;
+    __syncthreads();
+    const int q0 = G.agg_ptr[a], q1 = G.agg_ptr[a + 1];
+    for (int qb = q0; qb < q1; qb += CO_NW) {
+        const int q = qb + warp;
+        int64_t base = 0, inode = 0;
+        int width = 0, lrow = 0;
+        unsigned mi = 0;
+        if (q < q1) {
+            inode = G.agg_nodes[q];
+            base = A.slice_ptr[inode / C];
+            width = (int)(A.slice_ptr[inode / C + 1] - base);
+            lrow = (int)(inode % C);
+            for (int r = 0; r < BS; ++r) mi |= (unsigned)(A.mask[inode * BS + r] & 1) << r;
+        }
+        for (int s0 = 0;; s0 += CO_WB) {
+            const int left = width - s0;
+            const int nb = left <= 0 ? 0 : (left < CO_WB ? left : CO_WB);
+            int b = -1;
+            if (lane < nb) {
+                const int64_t j = A.col[(base + s0 + lane) * C + lrow];
+                unsigned mj = 0;
+                if (j < G.n_cols) {
+                    b = G.agg[j];
+                    for (int c = 0; c < BS; ++c) mj |= (unsigned)(A.mask[j * BS + c] & 1) << c;
+                    if (rbm)
+                        for (int c = 0; c < 3; ++c) s_rj[warp][lane][c] = G.rho[j * 3 + c];
+                }
+                s_b[warp][lane] = b;
+                s_m[warp][lane] = (unsigned char)mj;
+            }
+            const bool other = b >= 0 && b != b_own;
+            const unsigned om = __ballot_sync(0xffffffffu, other);
+            if (other) {
+                const int pos = __popc(om & ((1u << lane) - 1u));
+                s_list[warp][pos] = (unsigned char)lane;
+                s_grp[warp][pos] = (unsigned char)(b % NG);
+            }
+            for (int t = lane; t < nb * BB; t += 32) sval[(size_t)warp * CO_WB * BB + t] = A.val[((base + s0 + t / BB) * BB + t % BB) * C + lrow];
+            if (lane == 0) {
+                s_nb[warp] = nb;
+                s_mi[warp] = mi;
+                s_cnt[warp] = __popc(om);
+            }
+            if (rbm && lane < 3 && nb > 0) s_ri[warp][lane] = G.rho[inode * 3 + lane];
+            __syncthreads();
+            // ---- E[a, a]: this warp's node, blocks in storage order
+            if (p_act && nb > 0) {
+                double zi[BS];
+                z_column<BS>(pr, s_ri[warp], mi, zi);
+                // (branch-free and unrolled: the blocks' loads and products overlap, only the additions into `own` are a chain;
+                // a block of another aggregate contributes an exact zero through its cleared mask)
+#pragma unroll 4
+                for (int s = 0; s < nb; ++s) {
+                    const unsigned mj = s_b[warp][s] == b_own ? (unsigned)s_m[warp][s] : 0u;
+                    double zj[BS];
+                    z_column<BS>(pc, s_rj[warp][s], mj, zj);
+                    const double* Kb = sval + ((size_t)warp * CO_WB + s) * BB;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int p = 0; p < BS; ++p) {
+                        double t = 0.0;
+#pragma unroll
+                        for (int qq = 0; qq < BS; ++qq) t += Kb[p * BS + qq] * zj[qq];
+                        acc += zi[p] * t;
+                    }
+                    own += acc;
+                }
+            }
+            // ---- the other aggregates: group grp owns the targets b with b % NG == grp; nodes in ascending order, blocks in
+            //      storage order; consecutive contributions to the same target are summed in a register first
+            if (grp < NG) {
+                int run_b = -1;
+                double run = 0.0;
+                for (int w = 0; w < CO_NW; ++w) {
+                    const int cnt = s_cnt[w];
+                    bool have_zi = false;
+                    double zi[BS];
+                    for (int k = 0; k < cnt; ++k) {
+                        if (s_grp[w][k] != grp) continue;
+                        const int s = s_list[w][k];
+                        const int bt = s_b[w][s];
+                        if (!have_zi) {
+                            z_column<BS>(er, s_ri[w], s_mi[w], zi);
+                            have_zi = true;
+                        }
+                        double zj[BS];
+                        z_column<BS>(ec, s_rj[w][s], s_m[w][s], zj);
+                        const double* Kb = sval + ((size_t)w * CO_WB + s) * BB;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int p = 0; p < BS; ++p) {
+                            double t = 0.0;
+#pragma unroll
+                            for (int qq = 0; qq < BS; ++qq) t += Kb[p * BS + qq] * zj[qq];
+                            acc += zi[p] * t;
+                        }
+                        if (bt != run_b) {
+                            if (run_b >= 0) erow[(size_t)er * nc + run_b * CD + ec] += run;
+                            run_b = bt;
+                            run = 0.0;
+                        }
+                        run += acc;
+                    }
+                }
+                if (run_b >= 0) erow[(size_t)er * nc + run_b * CD + ec] += run;
+            }
+            if (!__syncthreads_or(left > CO_WB)) break;  // barrier (staging buffers are free again) + "another round?"
+        }
+    }
+    // the warps' partial sums of E[a, a], in warp order; both triangles get the same value
+    if (p_act) s_own[warp][lane] = own;
+    __syncthreads();
+    if (tid < NU) {
+        double v = 0.0;
+        for (int w = 0; w < CO_NW; ++w) v += s_own[w][tid];
+        erow[(size_t)pr * nc + b_own * CD + pc] = v;
+        erow[(size_t)pc * nc + b_own * CD + pr] = v;
+    }
+    __syncthreads();
+    // coarse dofs without any free fine dof: unit diagonal keeps E invertible (their w is always 0).  With rotations a
+    // degenerate aggregate (collinear nodes) has a rotation that moves nothing: E + 1e-9 diag(E) stays positive definite.
+    if (tid < CD) {
+        double& d = erow[(size_t)tid * nc + b_own * CD + tid];
         if (d == 0.0) d = 1.0;
         else if (rbm) d *= 1.0 + 1e-9;
     }

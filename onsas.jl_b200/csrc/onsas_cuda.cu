@@ -1051,9 +1051,31 @@ void refresh_coarse(onsas_ctx* c, CgArgs& A) {
     const int nc = c->co.nc;
     {
         const size_t smem = (size_t)c->co.cd * nc * sizeof(double);
+        static const bool serial = getenv("ONSAS_COARSE_SERIAL") != nullptr;  // experiment knob: the first form of the kernel
         ensure_dyn_smem(c->device, (const void*)k_coarse_assemble<BS>, smem);
-        k_coarse_assemble<BS><<<c->co.n_agg, CO_THREADS, smem, c->stream>>>(A, c->co_E.p);
+        ensure_dyn_smem(c->device, (const void*)k_coarse_assemble_serial<BS>, smem);
+        if (serial) k_coarse_assemble_serial<BS><<<c->co.n_agg, CO_THREADS, smem, c->stream>>>(A, c->co_E.p);
+        else k_coarse_assemble<BS><<<c->co.n_agg, CO_THREADS, smem, c->stream>>>(A, c->co_E.p);
         CUDA_CHECK(cudaGetLastError());
+        if (getenv("ONSAS_COARSE_CHECK")) {  // diagnostics: both forms of the kernel on the same K, largest difference of E
+            DevBuf<double> E2;
+            E2.alloc((size_t)nc * nc);
+            if (serial) k_coarse_assemble<BS><<<c->co.n_agg, CO_THREADS, smem, c->stream>>>(A, E2.p);
+            else k_coarse_assemble_serial<BS><<<c->co.n_agg, CO_THREADS, smem, c->stream>>>(A, E2.p);
+            CUDA_CHECK(cudaGetLastError());
+            std::vector<double> h1((size_t)nc * nc), h2((size_t)nc * nc);
+            CUDA_CHECK(cudaMemcpyAsync(h1.data(), c->co_E.p, h1.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaMemcpyAsync(h2.data(), E2.p, h2.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            double dmax = 0.0, emax = 0.0, asym = 0.0;
+            for (size_t k = 0; k < h1.size(); ++k) {
+                dmax = std::max(dmax, std::fabs(h1[k] - h2[k]));
+                emax = std::max(emax, std::fabs(h2[k]));
+            }
+            for (int i = 0; i < nc; ++i)
+                for (int j = 0; j < i; ++j) asym = std::max(asym, std::fabs(h1[(size_t)i * nc + j] - h1[(size_t)j * nc + i]));
+            fprintf(stderr, "[onsas] coarse operator check: nc = %d, max |E - E_other_form| = %.3e, max |E| = %.3e, max |E - E^T| = %.3e\n", nc, dmax, emax, asym);
+        }
     }
     if (c->gj_blocked && (nc + GJ_B - 1) / GJ_B <= c->n_sm) {  // panels of 12 rows: nc / 12 grid barriers
         const int grid = (nc + GJ_B - 1) / GJ_B;

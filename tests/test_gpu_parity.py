@@ -406,6 +406,57 @@ def test_two_level_blocked_and_unblocked_coarse_inverse_agree(ob, oracle):
         assert cases.rel_err(x1, x0) < 1e-9, grid
 
 
+def test_coarse_operator_both_kernel_forms_agree():
+    """E = Z^T (M K M) Z by k_coarse_assemble (own-aggregate blocks summed by all warps, the other targets dealt over thread
+    groups) against the first, serial form of the kernel on the same K (ONSAS_COARSE_CHECK runs both and reports the largest
+    difference): equal to rounding, E symmetric; with and without the rotations, jittered mesh, several aggregates."""
+    import os
+    import re
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, onsas_jl_b200 as ob\n"
+        "from tests import cases\n"
+        "from tests.test_gpu_parity import _ctx\n"
+        "m, _ = cases.box_model(24, 12, 12, mat='neo', jitter=0.1)\n"
+        "b = np.random.default_rng(8).standard_normal(m.n_dofs)\n"
+        "for rbm in (1, 0):\n"
+        "    ctx = _ctx(ob, m)\n"
+        "    ctx.set_option(ob._lib.OPT_COARSE_RBM, rbm)\n"
+        "    ctx.set_U(cases.random_U(m, 0.002))\n"
+        "    ctx.assemble()\n"
+        "    x, its, _ = ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-10)\n"
+        "    print('its', its)\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root,
+                         env=dict(os.environ, ONSAS_COARSE_CHECK="1"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = re.findall(r"max \|E - E_other_form\| = (\S+), max \|E\| = (\S+), max \|E - E\^T\| = (\S+)", out.stderr)
+    assert len(lines) == 2, out.stderr[-2000:]
+    for d, e, a in lines:
+        assert float(d) < 1e-12 * float(e) and float(a) < 1e-12 * float(e), lines
+
+
+def test_l2_prefetch_option_does_not_change_a_bit(ob):
+    """ONSAS_OPT_CG_L2_PREFETCH (the producer warp asks for the slices behind its ring with cp.async.bulk.prefetch.L2): a pure
+    cache hint -- same iterations, same bits, for the Jacobi and the two-level solver."""
+    m, _ = cases.box_model(24, 12, 12, mat="neo", jitter=0.1)
+    ctx = _ctx(ob, m)
+    ctx.set_U(cases.random_U(m, 0.002))
+    ctx.assemble()
+    b = np.random.default_rng(3).standard_normal(m.n_dofs)
+    for pre in (ob.PRECOND_JACOBI, ob.PRECOND_TWO_LEVEL):
+        ctx.set_option(ob._lib.OPT_CG_L2_PREFETCH, 0)
+        x0, it0, _ = ctx.pcg(b, pre, 1e-10)
+        for pf in (1, 3, 64):
+            ctx.set_option(ob._lib.OPT_CG_L2_PREFETCH, pf)
+            x1, it1, _ = ctx.pcg(b, pre, 1e-10)
+            assert it1 == it0
+            np.testing.assert_array_equal(x1, x0)
+    ctx.set_option(ob._lib.OPT_CG_L2_PREFETCH, 0)
+
+
 @pytest.mark.parametrize("case", ["box", "random_numbering", "mixed"])
 def test_assemble_host_is_bitwise_the_three_call_path(ob, oracle, case):
     """onsas_assemble_host (U in, F_int out, copies pipelined over slice ranges) against onsas_set_U + onsas_assemble +
