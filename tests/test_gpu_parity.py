@@ -438,6 +438,46 @@ def test_coarse_operator_both_kernel_forms_agree():
         assert float(d) < 1e-12 * float(e) and float(a) < 1e-12 * float(e), lines
 
 
+@pytest.mark.parametrize("dim", [1, 2])
+def test_two_level_preconditioner_in_one_and_two_dimensions(ob, oracle, dim):
+    """The coarse space in 1-D and 2-D (translations only: one or two coarse dofs per aggregate, 256 or 64 thread groups in
+    k_coarse_assemble): a clamped chain and a braced, jittered truss grid pinned along one edge, several aggregates each -- the
+    two-level solve equals the direct solve, needs no more iterations than Jacobi and is bitwise reproducible."""
+    rng = np.random.default_rng(4)
+    if dim == 1:
+        m, _, _ = cases.clamped_truss(1500)   # 1501 nodes -> 4 aggregates
+    else:
+        nx, ny = 60, 40
+        gx, gy = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
+        xyz = np.stack([gx.ravel(), gy.ravel()], axis=1).astype(float) + rng.uniform(-0.1, 0.1, ((nx + 1) * (ny + 1), 2))
+        nid = lambda i, j: i * (ny + 1) + j
+        bars = [(nid(i, j), nid(i + 1, j)) for i in range(nx) for j in range(ny + 1)]
+        bars += [(nid(i, j), nid(i, j + 1)) for i in range(nx + 1) for j in range(ny)]
+        bars += [(nid(i, j), nid(i + 1, j + 1)) for i in range(nx) for j in range(ny)]
+        bars += [(nid(i + 1, j), nid(i, j + 1)) for i in range(nx) for j in range(ny)]
+        bars = np.array(bars, np.int32)
+        free = np.array([2 * n + c for n in range(len(xyz)) for c in range(2) if n >= ny + 1], np.int64)  # edge i = 0 pinned
+        m = oracle.FlatModel(xyz=xyz, dim=2, trusses=bars, truss_area=rng.uniform(0.5, 1.5, len(bars)), truss_strain=1,
+                             mat_kind=[0], mat_params=[[0.0, 50.0]], free_dofs=free)
+    U = rng.uniform(-1e-3, 1e-3, m.n_dofs) * m.free_mask()
+    ref = oracle.Assembly(m).assemble(U)
+    import scipy.sparse.linalg as spla
+    free = np.asarray(m.free_dofs)
+    b = rng.standard_normal(m.n_dofs)
+    xd = np.zeros(m.n_dofs)
+    xd[free] = spla.spsolve(ref.csr()[free][:, free].tocsc(), b[free])
+    ctx = _ctx(ob, m)
+    ctx.set_U(U)
+    ctx.assemble()
+    xj, itj, _ = ctx.pcg(b, ob.PRECOND_JACOBI, 1e-13)
+    x2, it2, _ = ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-13)
+    assert cases.rel_err(xj, xd) < 1e-6 and cases.rel_err(x2, xd) < 1e-6, (cases.rel_err(xj, xd), cases.rel_err(x2, xd))
+    assert it2 <= itj, (it2, itj)
+    x3, it3, _ = ctx.pcg(b, ob.PRECOND_TWO_LEVEL, 1e-13)
+    assert it3 == it2
+    np.testing.assert_array_equal(x3, x2)
+
+
 def test_l2_prefetch_option_does_not_change_a_bit(ob):
     """ONSAS_OPT_CG_L2_PREFETCH (the producer warp asks for the slices behind its ring with cp.async.bulk.prefetch.L2): a pure
     cache hint -- same iterations, same bits, for the Jacobi and the two-level solver."""
