@@ -110,9 +110,14 @@ __device__ __forceinline__ void tet_pair(const AsmArgs& A, const double* sn, con
         if (writer) {  // the pair of the element's first owned node also writes its stress / strain record
             double out[16];
             tet_stress_out<K>(c, p0, p1, out);
-            double2* o = reinterpret_cast<double2*>(A.elem_out + 16 * e);
+            // four 32-byte stores per 128-byte record (sm_100: 256-bit global stores): the writer lanes of a warp sit on
+            // different lines, so every store instruction costs one L1 wavefront per writer -- half as many as with 16-byte stores
+            double* o = A.elem_out + 16 * e;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = make_double2(out[2 * k], out[2 * k + 1]);
+            for (int k = 0; k < 4; ++k)
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * k), "d"(out[4 * k]), "d"(out[4 * k + 1]), "d"(out[4 * k + 2]),
+                             "d"(out[4 * k + 3])
+                             : "memory");
         }
         tet_row<K>(c, U, a, rec, rec + 36);
     };
@@ -228,8 +233,11 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     NodeVec nodes = NodeVec();
     CodeVec chunk = CodeVec();
     int32_t code = 0;
+    // staging runs one thread per (listed node, component): consecutive threads read consecutive doubles inside every run of
+    // consecutive node ids (one thread per node read 24-byte strides: three instructions per vector over the same lines)
+    const int nsd = nsn * DIM;
     int64_t gnode = -1;
-    if (tid < nsn) gnode = __ldg(A.snodes + sn0 + tid);
+    if (tid < nsd) gnode = __ldg(A.snodes + sn0 + tid / DIM);
     if (t < np) {
         nodes = __ldg(pn + t);
         code = __ldg(A.pair_code + p0 + t);
@@ -239,26 +247,17 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     if (tid < nscp) cp0 = __ldg(A.cptr + base * C + tid);
     // ---- level 3: X, U of the listed nodes -> shared memory (consecutive threads hold consecutive list entries)
     {
-        double xv[DIM], uv[DIM];
         if (gnode >= 0) {
-#pragma unroll
-            for (int c = 0; c < DIM; ++c) {
-                xv[c] = __ldg(A.X + gnode * DIM + c);
-                uv[c] = __ldg(A.U + gnode * DIM + c);
-            }
-#pragma unroll
-            for (int c = 0; c < DIM; ++c) {
-                snd[tid * NS + c] = xv[c];
-                snd[tid * NS + DIM + c] = uv[c];
-            }
+            const int c = tid % DIM;
+            const double xv = __ldg(A.X + gnode * DIM + c), uv = __ldg(A.U + gnode * DIM + c);
+            snd[(tid / DIM) * NS + c] = xv;
+            snd[(tid / DIM) * NS + DIM + c] = uv;
         }
-        for (int i = tid + nth; i < nsn; i += nth) {  // lists longer than the CTA (high-valence meshes)
-            const int64_t g = __ldg(A.snodes + sn0 + i);
-#pragma unroll
-            for (int c = 0; c < DIM; ++c) {
-                snd[i * NS + c] = __ldg(A.X + g * DIM + c);
-                snd[i * NS + DIM + c] = __ldg(A.U + g * DIM + c);
-            }
+        for (int i = tid + nth; i < nsd; i += nth) {  // the rest of the list (270 dofs on the structured tet mesh, 192 threads)
+            const int64_t g = __ldg(A.snodes + sn0 + i / DIM);
+            const int c = i % DIM;
+            snd[(i / DIM) * NS + c] = __ldg(A.X + g * DIM + c);
+            snd[(i / DIM) * NS + DIM + c] = __ldg(A.U + g * DIM + c);
         }
     }
     PairMat mat = PairMat();
