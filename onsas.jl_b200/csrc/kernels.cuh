@@ -154,10 +154,7 @@ __device__ __forceinline__ void truss_pair(const AsmArgs& A, const double* sn, c
         for (int k = 0; k < DIM * DIM; ++k) rec[b * DIM * DIM + k] = blk[b][k];
 #pragma unroll
     for (int r = 0; r < DIM; ++r) rec[2 * DIM * DIM + r] = f[r];
-    if (writer) {
-        A.elem_out[2 * e] = se[0];
-        A.elem_out[2 * e + 1] = se[1];
-    }
+    if (writer) *reinterpret_cast<double2*>(A.elem_out + 2 * e) = make_double2(se[0], se[1]);  // one 16-byte store per record
 }
 
 // shared memory of one assembly CTA:
@@ -235,9 +232,12 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     int32_t code = 0;
     // staging runs one thread per (listed node, component): consecutive threads read consecutive doubles inside every run of
     // consecutive node ids (one thread per node read 24-byte strides: three instructions per vector over the same lines)
-    const int nsd = nsn * DIM;
+    // tets: staging runs one thread per (listed node, component); trusses: one thread per listed node (their lists are longer
+    // than the CTA has threads once split by component: 7.6 against 8.5 G bars/s on the 10 M-bar lattice, profiles/r80)
+    constexpr int SD = FAMILY == 0 ? DIM : 1;  // list entries are split into SD parts
+    const int nsd = nsn * SD;
     int64_t gnode = -1;
-    if (tid < nsd) gnode = __ldg(A.snodes + sn0 + tid / DIM);
+    if (tid < nsd) gnode = __ldg(A.snodes + sn0 + tid / SD);
     if (t < np) {
         nodes = __ldg(pn + t);
         code = __ldg(A.pair_code + p0 + t);
@@ -247,17 +247,41 @@ __device__ __forceinline__ void assemble_body(const AsmArgs& A) {
     if (tid < nscp) cp0 = __ldg(A.cptr + base * C + tid);
     // ---- level 3: X, U of the listed nodes -> shared memory (consecutive threads hold consecutive list entries)
     {
-        if (gnode >= 0) {
-            const int c = tid % DIM;
-            const double xv = __ldg(A.X + gnode * DIM + c), uv = __ldg(A.U + gnode * DIM + c);
-            snd[(tid / DIM) * NS + c] = xv;
-            snd[(tid / DIM) * NS + DIM + c] = uv;
-        }
-        for (int i = tid + nth; i < nsd; i += nth) {  // the rest of the list (270 dofs on the structured tet mesh, 192 threads)
-            const int64_t g = __ldg(A.snodes + sn0 + i / DIM);
-            const int c = i % DIM;
-            snd[(i / DIM) * NS + c] = __ldg(A.X + g * DIM + c);
-            snd[(i / DIM) * NS + DIM + c] = __ldg(A.U + g * DIM + c);
+        if constexpr (FAMILY == 0) {
+            if (gnode >= 0) {
+                const int c = tid % DIM;
+                const double xv = __ldg(A.X + gnode * DIM + c), uv = __ldg(A.U + gnode * DIM + c);
+                snd[(tid / DIM) * NS + c] = xv;
+                snd[(tid / DIM) * NS + DIM + c] = uv;
+            }
+            for (int i = tid + nth; i < nsd; i += nth) {  // the rest of the list (270 dofs on the structured tet mesh, 192 threads)
+                const int64_t g = __ldg(A.snodes + sn0 + i / DIM);
+                const int c = i % DIM;
+                snd[(i / DIM) * NS + c] = __ldg(A.X + g * DIM + c);
+                snd[(i / DIM) * NS + DIM + c] = __ldg(A.U + g * DIM + c);
+            }
+        } else {
+            double xv[DIM], uv[DIM];
+            if (gnode >= 0) {
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    xv[c] = __ldg(A.X + gnode * DIM + c);
+                    uv[c] = __ldg(A.U + gnode * DIM + c);
+                }
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    snd[tid * NS + c] = xv[c];
+                    snd[tid * NS + DIM + c] = uv[c];
+                }
+            }
+            for (int i = tid + nth; i < nsn; i += nth) {  // lists longer than the CTA (high-valence meshes)
+                const int64_t g = __ldg(A.snodes + sn0 + i);
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    snd[i * NS + c] = __ldg(A.X + g * DIM + c);
+                    snd[i * NS + DIM + c] = __ldg(A.U + g * DIM + c);
+                }
+            }
         }
     }
     PairMat mat = PairMat();
