@@ -23,7 +23,7 @@ for line in sass.splitlines():
     elif cur is not None and re.match(r"\s*/\*[0-9a-f]{4,}\*/", line):
         kernels[cur].append(line)
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
-WATCH = ["UBLKCP", "SYNCS", "DFMA", "DMUL", "DADD", "LDS", "STS", "LDG", "STG", "LDL", "STL", "BAR", "SHFL", "HMMA", "IMMA", "DMMA", "UTCMMA", "UTMALDG"]
+WATCH = ["UBLKCP", "UBLKPF", "SYNCS", "DFMA", "DMUL", "DADD", "LDS", "STS", "LDG", "STG", "LDL", "STL", "BAR", "SHFL", "HMMA", "IMMA", "DMMA", "UTCMMA", "UTMALDG"]
 rows = []
 for name, lines in kernels.items():
     ops = collections.Counter()
