@@ -103,7 +103,8 @@ typedef struct onsas_ctx onsas_ctx;
 #define ONSAS_OPT_CG_L2_PREFETCH 18  /* streamed persistent solver: slices per consumer warp the producer warp pulls into L2 (cp.async.bulk.prefetch.L2)
                                         behind the shared-memory ring as soon as an SpMV phase has issued its last copy -- HBM idles during the vector
                                         phases and grid barriers of an iteration, so the first part of the next SpMV phase is served from L2.
-                                        0 = off; default: see DESIGN.md section 3.3 */
+                                        0 = off (default).  Measured on B200 (profiles/r64, r66): bitwise identical and slower at every distance --
+                                        the prefetched lines displace the CG vectors from L2; kept as the record of the experiment */
 #define ONSAS_OPT_COARSE_FUSED 11    /* two-level preconditioner: 1 = residual update in aggregate order, fused with w = Z^T r (default), 0 = separate pass */
 
 /* ---------------------------------------------------------------- life cycle */
