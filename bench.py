@@ -30,7 +30,13 @@ import sys
 import tempfile
 import time
 
-import numpy as np
+# torchrun gives its workers OMP_NUM_THREADS = 1 unless the caller set it: the library's host-side table builder and partitioner
+# (OpenMP, once per mesh, outside every timed region) would run serially -- 20 s instead of 5 for the configs[3] mesh.  Share the
+# host cores among the ranks of this node instead; must happen before anything loads the OpenMP runtime.
+if os.environ.get("LOCAL_WORLD_SIZE") and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ["LOCAL_WORLD_SIZE"]))))
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
