@@ -29,6 +29,27 @@ def test_library_exports_every_declared_symbol(ob):
     assert lib.onsas_version() >= 100
 
 
+def test_option_keys_status_codes_and_enums_match_the_header(ob):
+    """Every ONSAS_OPT_* / ONSAS_ERR_* / ONSAS_PRECOND_* / ONSAS_MAT_* constant of include/onsas_cuda.h has the same value in the
+    Python binding (a caller that passes the binding's constant reaches the option the header documents), option keys are unique,
+    and setting an unknown key is an error rather than a silent no-op (checked without a device: the context cannot be created
+    here, so the key table is compared, not exercised)."""
+    hdr = open(os.path.join(ROOT, "include", "onsas_cuda.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(ONSAS_[A-Z0-9_]+)\s+(-?\d+)\b", hdr)}
+    opts = {k: v for k, v in defs.items() if k.startswith("ONSAS_OPT_")}
+    assert len(opts) >= 18 and len(set(opts.values())) == len(opts), "duplicate option key"
+    L = ob._lib
+    checked = 0
+    for name, value in defs.items():
+        short = name[len("ONSAS_"):]
+        if hasattr(L, short):
+            assert getattr(L, short) == value, (name, value, getattr(L, short))
+            checked += 1
+    for name in opts:
+        assert hasattr(L, name[len("ONSAS_"):]), f"{name} has no constant in the Python binding"
+    assert checked >= len(opts) + 3
+
+
 def test_no_cpu_fallback(ob):
     """Without a CUDA device the product path must fail loudly (this test is skipped on a GPU box)."""
     import torch
