@@ -133,6 +133,52 @@ HsModel* hs_create(int dim, int64_t n_nodes, int64_t n_rows, int64_t n_tets, con
 }
 const char* hs_error(HsModel* m) { return m->err.c_str(); }
 void hs_destroy(HsModel* m) { delete m; }
+// FNV-1a over every array and scalar of the host-built tables: a change of the builder (tables.cpp) that is meant to keep its
+// output is checked against the recorded hashes (tests/golden/table_hashes.json)
+uint64_t hs_tables_hash(HsModel* m) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i) {
+            h ^= b[i];
+            h *= 1099511628211ull;
+        }
+    };
+    auto vec = [&](const auto& v) {
+        const uint64_t n = v.size();
+        mix(&n, sizeof n);
+        if (n) mix(v.data(), n * sizeof(v[0]));
+    };
+    const MeshTables& t = m->tab;
+    const int64_t sc[6] = {t.dim, t.n_nodes, t.n_rows, t.n_slices, t.max_width, t.nnz_blocks};
+    mix(sc, sizeof sc);
+    vec(t.slice_ptr);
+    vec(t.col);
+    vec(t.row_nblk);
+    for (int f = 0; f < 2; ++f) {
+        const FamilyTables& F = t.fam[f];
+        const int64_t fs[5] = {F.npe, F.rec, F.n_elem, F.max_snodes, F.max_pairs_per_slice};
+        mix(fs, sizeof fs);
+        vec(F.pair_ptr);
+        vec(F.pair_code);
+        vec(F.pair_lnodes);
+        vec(F.snodes);
+        vec(F.cptr);
+        vec(F.ccode);
+        const uint64_t nh = F.hdr.size();
+        mix(&nh, sizeof nh);
+        for (const SliceHdr& H : F.hdr) {  // field by field: the struct has no padding today, but a hash must not depend on it
+            mix(&H.pair_base, sizeof H.pair_base);
+            mix(&H.slot_base, sizeof H.slot_base);
+            mix(&H.n_pairs, sizeof H.n_pairs);
+            mix(&H.width, sizeof H.width);
+            mix(H.row_off, sizeof H.row_off);
+            mix(&H.n_snodes, sizeof H.n_snodes);
+            mix(&H.snode_base, sizeof H.snode_base);
+        }
+    }
+    return h;
+}
 int64_t hs_nnz(HsModel* m) { return (int64_t)m->colidx.size(); }
 int64_t hs_stat(HsModel* m, int which) {
     switch (which) {

@@ -18,6 +18,8 @@ hs.hs_error.restype = C.c_char_p
 hs.hs_error.argtypes = [_vp]
 hs.hs_destroy.argtypes = [_vp]
 hs.hs_nnz.restype = C.c_int64
+hs.hs_tables_hash.argtypes = [_vp]
+hs.hs_tables_hash.restype = C.c_uint64
 hs.hs_nnz.argtypes = [_vp]
 hs.hs_stat.restype = C.c_int64
 hs.hs_stat.argtypes = [_vp, C.c_int]
@@ -53,6 +55,9 @@ class HostSim:
         if getattr(self, "h", None):
             hs.hs_destroy(self.h)
             self.h = None
+
+    def tables_hash(self):
+        return int(hs.hs_tables_hash(self.h))
 
     def stats(self):
         return [hs.hs_stat(self.h, i) for i in range(5)]

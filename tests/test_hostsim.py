@@ -169,3 +169,23 @@ def test_slice_node_lists_the_assembly_kernel_stages(hostsim, oracle):
     assert part["violations"] == 0 and 0 < part["entries"] < chk["entries"]   # first node is a halo node still have one writer
     mt, _, _ = cases.von_mises_truss(0)
     assert hostsim.HostSim(mt).check_slice_nodes(1, mt.trusses)["violations"] == 0
+
+
+def test_host_built_tables_match_their_recorded_hashes(hostsim, oracle):
+    """The table layout IS the contract between tables.cpp and the kernels (pair lists, slice node lists, contribution codes,
+    slice headers, the BSELL pattern): an FNV-1a hash over every array, for structured and random numbering, trusses in 1-3 D,
+    both families together, partial ownership and a 400-bar hub, must equal the recorded one -- whatever the thread count.
+    A deliberate layout change regenerates tests/golden/table_hashes.json with scripts/table_hashes.py."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("table_hashes", os.path.join(root, "scripts", "table_hashes.py"))
+    th = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(th)
+    golden = json.load(open(os.path.join(root, "tests", "golden", "table_hashes.json")))
+    seen = {}
+    for name, (m, n_rows) in th.meshes().items():
+        sim = hostsim.HostSim(m, n_rows=n_rows)
+        seen[name] = {"hash": f"{sim.tables_hash():016x}", "stats": sim.stats()}
+    assert seen == golden
