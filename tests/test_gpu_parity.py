@@ -406,6 +406,15 @@ def test_two_level_blocked_and_unblocked_coarse_inverse_agree(ob, oracle):
         assert cases.rel_err(x1, x0) < 1e-9, grid
 
 
+def test_newton_step_from_a_plain_c_program():
+    """tests/abi_c/abi_smoke.c (strict C99, gcc, linked against the library): the reference's 6-tet uniaxial-extension cell through
+    onsas_create ... onsas_newton_step ... onsas_destroy without Python or ctypes in between."""
+    from tests.abi_c import run
+    out = run.build_and_run()
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "one Newton step through the C ABI" in out.stdout, out.stdout
+
+
 def test_coarse_operator_both_kernel_forms_agree():
     """E = Z^T (M K M) Z by k_coarse_assemble (own-aggregate blocks summed by all warps, the other targets dealt over thread
     groups) against the first, serial form of the kernel on the same K (ONSAS_COARSE_CHECK runs both and reports the largest

@@ -50,6 +50,16 @@ def test_option_keys_status_codes_and_enums_match_the_header(ob):
     assert checked >= len(opts) + 3
 
 
+def test_header_is_plain_c_and_the_library_links_from_c(ob):
+    """include/onsas_cuda.h compiled as strict C99 (-pedantic -Werror) by gcc, linked against libonsas_cuda.so the way a ccall /
+    cgo / JNI binding would: no C++ type, no torch symbol in the interface.  Without a device the C program sees the loud failure
+    the header promises (ONSAS_ERR_CUDA, no context, a message); with one it runs a Newton step (see the -m gpu twin)."""
+    from tests.abi_c import run
+    out = run.build_and_run()
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "C linkage ok" in out.stdout or "one Newton step through the C ABI" in out.stdout
+
+
 def test_no_cpu_fallback(ob):
     """Without a CUDA device the product path must fail loudly (this test is skipped on a GPU box)."""
     import torch
