@@ -178,6 +178,7 @@ struct onsas_ctx {
     bool coarse_fused = true;  // residual update in aggregate order, fused with w = Z^T r (same-box sweep: profiles/r18)
     bool coarse_rbm = true;  // 3D: rigid-body rotations of every aggregate join the coarse space (6 coarse dofs per aggregate)
     DevBuf<int32_t> co_agg, co_agg_ptr, co_agg_nodes;
+    std::vector<double> h_elem_stage;  // onsas_get_stress_strain: host copy of the tets' 16-double records
     DevBuf<double> co_E, co_w, co_y, co_rowbuf, co_rho;
     // global coarse level across ranks (ONSAS_OPT_COARSE_GLOBAL): level-2 aggregates from the partitioner
     std::vector<int32_t> h_agg2;   // [n_local] global level-2 aggregate of every local node (owned + halo)
@@ -1982,9 +1983,13 @@ int32_t onsas_get_stress_strain(onsas_ctx* c, int32_t family, double* sig, doubl
         require(c->finalized, ONSAS_ERR_NOT_READY, "mesh not finalized");
         require(family == 0 || family == 1, ONSAS_ERR_INVALID_ARG, "unknown element family");
         if (family == 0) {
-            std::vector<double> h(c->tet_out.n);
-            if (!h.empty()) download(c, h.data(), c->tet_out.p, h.size());
+            // the staging buffer lives with the context (a fresh 128 MB vector per call cost more in page faults than the copy
+            // itself: store! runs once per load step) and the records are unpacked by all host threads
+            std::vector<double>& h = c->h_elem_stage;
+            if (h.size() < c->tet_out.n) h.resize(c->tet_out.n);
+            if (c->tet_out.n) download(c, h.data(), c->tet_out.p, c->tet_out.n);
             const int VI[6] = {0, 1, 2, 1, 0, 0}, VJ[6] = {0, 1, 2, 2, 2, 1};
+#pragma omp parallel for schedule(static)
             for (int64_t e = 0; e < c->n_tets; ++e) {
                 for (int k = 0; k < 9; ++k) sig[9 * e + k] = h[16 * e + k];
                 for (int v = 0; v < 6; ++v) {
